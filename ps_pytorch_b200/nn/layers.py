@@ -1,0 +1,127 @@
+"""``torch.nn``-compatible layers whose CUDA forward/backward run on the sm_100a kernels.
+
+Every class subclasses its ``torch.nn`` namesake, so ``state_dict`` keys and shapes are
+those of the reference models (``/root/reference/src/model_ops/*.py``) and checkpoints stay
+loadable by either side.  On CPU tensors (the gloo plumbing tier) or with the ``library``
+backend the stock ``torch.nn.functional`` op is used.
+
+Fusion points are explicit in the layer API, because on B200 the CNNs here are HBM-bound
+outside the convolutions: ``BatchNorm2d(x, residual=..., relu=True)`` is one normalise+add+ReLU
+pass, ``MaxPool2d(..., relu=True)`` fuses LeNet's pool→ReLU.
+"""
+from __future__ import annotations
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from .backend import use_sm100, note_fallback
+
+
+class Conv2d(nn.Conv2d):
+    def forward(self, x):
+        if use_sm100(x):
+            from ..ops import conv as _conv
+            why = _conv.unsupported_reason(x, self.weight, self.stride, self.padding, self.dilation, self.groups)
+            if why is None:
+                return _conv.conv2d(x, self.weight, self.bias, self.stride, self.padding)
+            note_fallback("conv2d", why)
+        return F.conv2d(x, self.weight, self.bias, self.stride, self.padding, self.dilation, self.groups)
+
+
+class Linear(nn.Linear):
+    def forward(self, x, relu: bool = False):
+        if use_sm100(x):
+            from ..ops import gemm as _gemm
+            why = _gemm.linear_unsupported_reason(x, self.weight)
+            if why is None:
+                return _gemm.linear(x, self.weight, self.bias, relu)
+            note_fallback("linear", why)
+        y = F.linear(x, self.weight, self.bias)
+        return F.relu(y) if relu else y
+
+
+class BatchNorm2d(nn.BatchNorm2d):
+    """BatchNorm2d with fused residual-add and ReLU.  Running statistics are kept in fp32
+    whatever the parameter dtype (``_apply`` below), so bf16 replicas do not lose the EMA."""
+
+    def _apply(self, fn, recurse=True):
+        super()._apply(fn, recurse)
+        for name in ("running_mean", "running_var"):
+            buf = getattr(self, name, None)
+            if buf is not None and buf.is_floating_point() and buf.dtype != torch.float32:
+                setattr(self, name, buf.float())
+        return self
+
+    def forward(self, x, residual=None, relu: bool = False):
+        if use_sm100(x):
+            from ..ops import norm as _norm
+            why = _norm.bn_unsupported_reason(x)
+            if why is None:
+                return _norm.batch_norm(x, self, residual, relu)
+            note_fallback("batch_norm", why)
+        if self.training and self.track_running_stats and self.num_batches_tracked is not None:
+            self.num_batches_tracked.add_(1)
+        w, b = self.weight, self.bias
+        rm, rv = self.running_mean, self.running_var
+        if x.dtype != torch.float32 and x.is_cuda:
+            # cuDNN/ATen mixed-precision BN wants fp32 affine params + stats with a 16-bit input
+            w = w.float() if w is not None else None
+            b = b.float() if b is not None else None
+        elif x.dtype != torch.float32:
+            # CPU bf16: compute in fp32
+            y = F.batch_norm(x.float(), rm, rv, None if w is None else w.float(), None if b is None else b.float(),
+                             self.training or not self.track_running_stats, self.momentum, self.eps).to(x.dtype)
+            if residual is not None:
+                y = y + residual
+            return F.relu(y) if relu else y
+        y = F.batch_norm(x, rm, rv, w, b, self.training or not self.track_running_stats, self.momentum, self.eps)
+        if residual is not None:
+            y = y + residual
+        return F.relu(y) if relu else y
+
+
+class ReLU(nn.ReLU):
+    def forward(self, x):
+        if use_sm100(x):
+            from ..ops import elementwise as _ew
+            return _ew.relu(x)
+        return F.relu(x, inplace=self.inplace)
+
+
+class MaxPool2d(nn.MaxPool2d):
+    def forward(self, x, relu: bool = False):
+        if use_sm100(x):
+            from ..ops import elementwise as _ew
+            why = _ew.pool_unsupported_reason(x, self.kernel_size, self.stride, self.padding)
+            if why is None:
+                return _ew.max_pool2x2(x, relu)
+            note_fallback("max_pool2d", why)
+        y = F.max_pool2d(x, self.kernel_size, self.stride, self.padding)
+        return F.relu(y) if relu else y
+
+
+class AvgPool2d(nn.AvgPool2d):
+    def forward(self, x):
+        if use_sm100(x):
+            from ..ops import elementwise as _ew
+            why = _ew.avgpool_unsupported_reason(x, self.kernel_size)
+            if why is None:
+                return _ew.global_avg_pool(x)
+            note_fallback("avg_pool2d", why)
+        return F.avg_pool2d(x, self.kernel_size, self.stride, self.padding)
+
+
+class Dropout(nn.Dropout):
+    def forward(self, x):
+        return F.dropout(x, self.p, self.training, self.inplace)
+
+
+class CrossEntropyLoss(nn.CrossEntropyLoss):
+    """Mean softmax cross-entropy (reference: ``nn.CrossEntropyLoss`` at ``distributed_worker.py:98``)."""
+
+    def forward(self, logits, target):
+        if use_sm100(logits):
+            from ..ops import loss as _loss
+            return _loss.softmax_cross_entropy(logits, target)
+        return F.cross_entropy(logits.float(), target)

@@ -1,0 +1,199 @@
+"""Worker-side compute core: model replica bound to flat weight/gradient arenas, one training step
+(zero-grad → forward → loss → backward) optionally captured in a CUDA graph, with per-bucket hooks that let the
+transport push gradient buckets while the rest of backward is still running (the capability of the reference's
+Split models, ``/root/reference/src/model_ops/resnet_split.py:365-501``, for *any* model)."""
+from __future__ import annotations
+
+import time
+from typing import Callable, List, Optional
+
+import torch
+import torch.nn as tnn
+
+from .arena import FlatBuffer, ParamLayout
+from .. import nn as pnn
+from ..models.layerwise import LayerwiseBackwardMixin, StragglerKilled
+from ..utils.obs import PhaseTimer
+
+
+def resolve_dtype(name: str, device) -> torch.dtype:
+    if name == "auto":
+        return torch.bfloat16 if torch.device(device).type == "cuda" else torch.float32
+    return {"fp32": torch.float32, "bf16": torch.bfloat16}[name]
+
+
+class WorkerCompute:
+    def __init__(self, network: tnn.Module, device, dtype: torch.dtype, layout: Optional[ParamLayout] = None,
+                 weight_storage: Optional[torch.Tensor] = None, grad_dtype: Optional[torch.dtype] = None,
+                 channels_last: Optional[bool] = None, use_graph: bool = False):
+        self.device = torch.device(device)
+        self.dtype = dtype
+        self.channels_last = (self.device.type == "cuda") if channels_last is None else channels_last
+        self.network = network.to(self.device).to(dtype)
+        if self.channels_last:
+            self.network = self.network.to(memory_format=torch.channels_last)
+        self.layout = layout or ParamLayout.from_module(self.network, channels_last=self.channels_last)
+        self.weights = FlatBuffer(self.layout, dtype, self.device, storage=weight_storage)
+        self.weights.bind_params(self.network)
+        self.grads = FlatBuffer(self.layout, grad_dtype or dtype, self.device)
+        self.grads.bind_grads(self.network)
+        self.criterion = pnn.CrossEntropyLoss()
+        self.timer = PhaseTimer(self.device)
+        self.use_graph = use_graph and self.device.type == "cuda"
+        self._graph = None
+        self._static_x = self._static_y = self._static_loss = None
+        self._bucket_hooks: List = []
+        self._on_bucket: Optional[Callable[[int], None]] = None
+        self._kill_poll: Optional[Callable[[], bool]] = None
+        self.kill_deadline: float = 0.0
+
+    # ---- overlap: bucket-complete callbacks during backward ---------------------------------------------
+    def enable_bucket_callbacks(self, buckets, on_bucket: Callable[[int], None]) -> None:
+        """``on_bucket(b)`` fires (inside backward) once every parameter of bucket ``b`` has its gradient."""
+        for h in self._bucket_hooks:
+            h.remove()
+        self._bucket_hooks, self._on_bucket = [], on_bucket
+        self._buckets = buckets
+        params = list(self.network.parameters())
+        self._pending = [0] * len(buckets)
+        owner = {}
+        for b, (_, _, idx) in enumerate(buckets):
+            for i in idx:
+                owner[i] = b
+
+        def make(i):
+            def hook(_p):
+                if self._kill_poll is not None and (self._kill_poll() or (self.kill_deadline and time.time() > self.kill_deadline)):
+                    raise StragglerKilled()
+                b = owner[i]
+                self._pending[b] -= 1
+                if self._pending[b] == 0 and self._on_bucket is not None:
+                    self._on_bucket(b)
+            return hook
+        for i, p in enumerate(params):
+            self._bucket_hooks.append(p.register_post_accumulate_grad_hook(make(i)))
+
+    def enable_kill_poll(self, poll: Callable[[], bool]) -> None:
+        self._kill_poll = poll
+        if not self._bucket_hooks:
+            lo_hi = self.layout.buckets(1)
+            self.enable_bucket_callbacks(lo_hi, lambda b: None)
+
+    def _arm_buckets(self):
+        if self._bucket_hooks:
+            self._pending = [len(idx) for (_, _, idx) in self._buckets]
+
+    # ---- one step ----------------------------------------------------------------------------------------
+    def _step_body(self, x, y):
+        self.grads.flat.zero_()
+        self._arm_buckets()
+        with self.timer.phase("forward"):
+            logits = self.network(x)
+            loss = self.criterion(logits, y)
+        with self.timer.phase("backward"):
+            if isinstance(self.network, LayerwiseBackwardMixin) and self._layerwise_comm is not None:
+                # reference call pattern (nn_ops.py:64-70): loss on detached logits, then the layer-wise walk
+                lg = torch.autograd.grad(loss, self.network.output[-1])[0]
+                mode = self._layerwise_mode
+                if mode == "kill":
+                    _, killed = self.network.backward_signal_kill(lg, self._layerwise_comm, None, self._cur_step)
+                elif mode == "timeout":
+                    _, killed = self.network.backward_timeout_kill(lg, self._layerwise_comm, None, self._cur_step)
+                else:
+                    self.network.backward_normal(lg, self._layerwise_comm, None, self._cur_step)
+                    killed = False
+                if killed:
+                    raise StragglerKilled()
+            else:
+                loss.backward()
+        return loss.detach(), logits.detach()
+
+    _layerwise_comm = None
+    _layerwise_mode = "normal"
+    _cur_step = 0
+
+    def set_layerwise(self, communicator, mode: str = "normal") -> None:
+        self._layerwise_comm, self._layerwise_mode = communicator, mode
+
+    def prepare_input(self, x: torch.Tensor, y: torch.Tensor):
+        x = x.to(self.device, non_blocking=True)
+        if x.dtype != self.dtype:
+            x = x.to(self.dtype)
+        if self.channels_last and x.dim() == 4:
+            x = x.contiguous(memory_format=torch.channels_last)
+        return x, y.to(self.device, non_blocking=True)
+
+    def train_step(self, x: torch.Tensor, y: torch.Tensor, step: int = 0):
+        """Returns ``(loss, logits)`` device tensors.  Gradients land in ``self.grads``."""
+        self._cur_step = step
+        self.network.train()
+        if not self.use_graph:
+            x, y = self.prepare_input(x, y)
+            return self._step_body(x, y)
+        if self._graph is None:
+            self._capture(x, y)
+        self._static_x.copy_(x, non_blocking=True)
+        self._static_y.copy_(y, non_blocking=True)
+        self._graph.replay()
+        return self._static_loss, self._static_logits
+
+    def _capture(self, x, y):
+        xs, ys = self.prepare_input(x, y)
+        self._static_x, self._static_y = xs.clone(memory_format=torch.preserve_format), ys.clone()
+        s = torch.cuda.Stream()
+        s.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(s):
+            for _ in range(3):   # warm-up off-graph: cuDNN autotune, lazy inits
+                self._step_body(self._static_x, self._static_y)
+        torch.cuda.current_stream().wait_stream(s)
+        torch.cuda.synchronize()
+        self.timer.resolve()
+        self._graph = torch.cuda.CUDAGraph()
+        self.timer = _NullTimer()
+        with torch.cuda.graph(self._graph):
+            self._static_loss, self._static_logits = self._step_body(self._static_x, self._static_y)
+
+    @torch.no_grad()
+    def evaluate(self, loader, max_batches: int = 0):
+        """Average NLL + Prec@1/Prec@5 over a loader (reference ``distributed_worker.py:274-299``)."""
+        from ..utils.metrics import accuracy
+        self.network.eval()
+        tot_loss, p1, p5, nb, n = 0.0, 0.0, 0.0, 0, 0
+        for x, y in loader:
+            x, y = self.prepare_input(x, y)
+            out = self.network(x).float()
+            tot_loss += torch.nn.functional.cross_entropy(out, y, reduction='sum').item()
+            a1, a5 = accuracy(out, y, topk=(1, 5))
+            p1 += a1.item(); p5 += a5.item(); nb += 1; n += y.numel()
+            if max_batches and nb >= max_batches:
+                break
+        self.network.train()
+        return tot_loss / max(n, 1), p1 / max(nb, 1), p5 / max(nb, 1)
+
+    def buffers_flat(self) -> torch.Tensor:
+        """BN running statistics (and counters) as one fp32 vector — exchanged with the PS at checkpoint steps."""
+        bs = [b.detach().reshape(-1).float() for b in self.network.buffers()]
+        return torch.cat(bs) if bs else torch.zeros(0, device=self.device)
+
+
+class _NullTimer:
+    import contextlib as _c
+
+    @_c.contextmanager
+    def phase(self, name):
+        yield
+
+    def resolve(self):
+        return {}
+
+    def discard(self):
+        pass
+
+
+def load_buffers_flat(network: tnn.Module, flat: torch.Tensor) -> None:
+    off = 0
+    with torch.no_grad():
+        for b in network.buffers():
+            n = b.numel()
+            b.copy_(flat[off:off + n].reshape(b.shape).to(b.dtype))
+            off += n

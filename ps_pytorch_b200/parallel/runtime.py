@@ -1,0 +1,132 @@
+"""Process runtime: rank/role assignment, process-group bootstrap, transport selection, seeding.
+
+Replaces ``mpirun`` + ``MPI.COMM_WORLD`` (``/root/reference/src/distributed_nn.py:70-126``): one process per GPU
+(or per CPU rank on the gloo tier), rank 0 = parameter server, ranks 1..P = workers.  Ranks come from the
+torchrun-style environment (RANK / LOCAL_RANK / WORLD_SIZE / MASTER_ADDR / MASTER_PORT) set by
+``ps_pytorch_b200.launch`` or ``torch.distributed.run``.  torch.distributed is used only for rendezvous and
+the CPU tier; on GPUs the gradient/weight traffic goes through the peer-memory kernels (``nvl.py``).
+"""
+from __future__ import annotations
+
+import datetime
+import os
+import random
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+from ..config import num_classes_for
+from ..models import build_model
+from .arena import ParamLayout
+from .compute import resolve_dtype
+from .transport import GlooTransport, LocalTransport
+from ..utils.data import prepare_data
+from ..utils.obs import logger
+
+
+def env_rank():
+    return int(os.environ.get("RANK", 0)), int(os.environ.get("LOCAL_RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
+
+
+def seed_everything(seed: int, rank: int = 0) -> None:
+    random.seed(seed + rank)
+    np.random.seed(seed + rank)
+    torch.manual_seed(seed)          # identical init on every rank; PS's init is the global init anyway
+
+
+def parse_stragglers(spec: str):
+    out = {}
+    for item in filter(None, (spec or "").split(",")):
+        r, ms = item.split(":")
+        out[int(r)] = float(ms)
+    return out
+
+
+def init_process_group(use_cuda: bool, timeout_s: int = 600):
+    rank, local_rank, world = env_rank()
+    if world > 1 and not dist.is_initialized():
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ.setdefault("MASTER_PORT", "29511")
+        if use_cuda:
+            torch.cuda.set_device(local_rank)
+        # gloo always: bootstrap/handle exchange + CPU tier.  NCCL is not used by the product path.
+        dist.init_process_group("gloo", rank=rank, world_size=world, timeout=datetime.timedelta(seconds=timeout_s))
+    return rank, local_rank, world
+
+
+def make_transport(args, layout: ParamLayout, device: torch.device, world: int):
+    kind = args.transport
+    if kind == "auto":
+        kind = "local" if world == 1 else ("nvl" if device.type == "cuda" else "gloo")
+    compress = str(args.compress_grad).lower() == "compress"
+    if kind == "local":
+        return LocalTransport(layout, device)
+    if kind == "gloo":
+        return GlooTransport(layout, compress=compress, colocate=args.colocate_worker)
+    if kind == "nvl":
+        from .nvl import NvlTransport
+        gd = args.grad_dtype
+        if gd == "auto":
+            gd = "fp8" if compress else "bf16"
+        return NvlTransport(layout, device, grad_dtype=gd, colocate=args.colocate_worker, num_buckets=(args.num_buckets if args.overlap else 1))
+    raise ValueError(kind)
+
+
+def run_distributed(args):
+    """Body of ``distributed_nn.py``: build data, roles and transport from flags, then run."""
+    use_cuda = bool(args.enable_gpu) and not args.no_cuda and torch.cuda.is_available()
+    rank, local_rank, world = init_process_group(use_cuda)
+    device = torch.device("cuda", local_rank) if use_cuda else torch.device("cpu")
+    seed_everything(args.seed, rank)
+    if args.backend != "auto":
+        from .. import nn as pnn
+        pnn.set_backend(args.backend)
+    num_classes = num_classes_for(args.dataset)
+    dtype = resolve_dtype(args.dtype, device)
+    proto = build_model(args.network, num_classes)
+    layout = ParamLayout.from_module(proto, channels_last=(device.type == "cuda"))
+    comm = make_transport(args, layout, device, world)
+    stragglers = parse_stragglers(args.inject_straggler)
+    common = dict(batch_size=args.batch_size, learning_rate=args.lr, max_epochs=args.epochs, momentum=args.momentum,
+                  network=args.network, comm_method=args.comm_type, eval_freq=args.eval_freq, train_dir=args.train_dir,
+                  max_steps=args.max_steps, compress_grad=args.compress_grad, device=device, mode=args.mode, dtype=args.dtype)
+    kwargs_master = dict(common, num_aggregate=args.num_aggregate, timeout_threshold=args.kill_threshold,
+                         optimizer=args.optimizer, weight_decay=args.weight_decay, nesterov=args.nesterov,
+                         dampening=args.dampening, amsgrad=args.amsgrad, strict_reference=args.strict_reference,
+                         worker_dtype=dtype, resume=args.resume)
+    kwargs_worker = dict(common, kill_threshold=args.kill_threshold, overlap=args.overlap, num_buckets=args.num_buckets,
+                         cuda_graph=args.cuda_graph, straggle_ms=stragglers.get(rank, 0.0), log_interval=args.log_interval,
+                         jsonl=(args.jsonl + ".rank%d" % rank) if args.jsonl else "")
+    from .ps import SyncReplicasMaster_NN
+    from .worker import DistributedWorker
+    is_worker = rank in comm.worker_ranks
+    train_loader = test_loader = None
+    if is_worker:
+        train_loader, test_loader = prepare_data(args, rank=rank, pin=use_cuda, out_dtype=torch.float32,
+                                                 channels_last=use_cuda)
+    result = {}
+    if rank == 0:
+        master = SyncReplicasMaster_NN(comm=comm, **kwargs_master)
+        master.build_model(num_classes=num_classes, network=proto)
+        print("I am the master: the world size is {}, cur step: {}".format(master.world_size, master.cur_step))
+        if is_worker:
+            w = DistributedWorker(comm=comm, **kwargs_worker)
+            w.build_model(num_classes=num_classes)
+            w.attach_loader(train_loader)
+            master._colocated_worker = w
+            result["worker"] = w
+        master.start()
+        print("Done sending messages to workers!")
+        result["master"] = master
+    else:
+        w = DistributedWorker(comm=comm, **kwargs_worker)
+        w.build_model(num_classes=num_classes)
+        print("I am worker: {} in all {} workers, next step: {}".format(w.rank, comm.num_workers, w.next_step))
+        w.train(train_loader=train_loader, test_loader=test_loader)
+        print("Now the next step is: {}".format(w.next_step))
+        result["worker"] = w
+    comm.close()
+    if dist.is_initialized():
+        dist.barrier()
+    return result

@@ -1,0 +1,3 @@
+import os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
+from ps_pytorch_b200.utils.data import DataLoader, BatchLoader  # noqa: F401,E402
