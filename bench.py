@@ -1,0 +1,210 @@
+#!/usr/bin/env python
+"""Headline benchmark (BASELINE.json): ResNet-18 / CIFAR-10-shaped synthetic data, bf16, per-worker batch 1024
+(the reference's ``run_pytorch.sh`` configuration), synchronous parameter-server training — images/s over the whole
+job, device-timed, max over ranks.
+
+    python bench.py --gpus 1 --steps 30 --warmup 5
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29500 bench.py --gpus 8 ...
+
+``--impl reference`` is the reference arm (unmodified hwang595/ps_pytorch): it cannot be installed here — the tree has no
+setup.py/pyproject (pip: "not installable"), and it imports mpi4py + blosc which are absent — so that arm prints
+``{"impl": "reference", "unavailable": ...}``.  ``--impl nccl-baseline`` runs ``baseline/nccl_ps.py``: the reference
+algorithm re-expressed with NCCL reduce/broadcast + stock torch.nn (the operative baseline of BASELINE.md §2).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=30)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", type=str, default="ours", choices=["ours", "reference", "nccl-baseline"])
+    ap.add_argument("--network", type=str, default="ResNet18")
+    ap.add_argument("--dataset", type=str, default="Cifar10")
+    ap.add_argument("--batch-size", type=int, default=1024, help="per-worker batch (reference run_pytorch.sh: 1024)")
+    ap.add_argument("--topology", type=str, default="ps", choices=["ps", "sharded"])
+    ap.add_argument("--grad-dtype", type=str, default="bf16", choices=["bf16", "fp8", "fp32"])
+    ap.add_argument("--backend", type=str, default="auto", choices=["auto", "sm100", "library"])
+    ap.add_argument("--no-colocate", action="store_true", help="reference topology: the PS GPU runs no worker")
+    ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--overlap", action="store_true")
+    ap.add_argument("--optimizer", type=str, default="sgd")
+    ap.add_argument("--skip-e2e", action="store_true")
+    return ap.parse_args()
+
+
+class ClockSampler:
+    """Samples SM clocks / throttle reasons with nvidia-smi while the timed region runs (B200_PROFILING.md)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self):
+        self.rows, self.proc = [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self, ngpu):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        clk, mx, reasons, pw = [], [], set(), []
+        for r in self.rows:
+            f = [x.strip() for x in r.split(",")]
+            if len(f) < 9 or not f[0].isdigit() or int(f[0]) >= ngpu:
+                continue
+            try:
+                clk.append(float(f[1])); mx.append(float(f[2])); pw.append(float(f[3]))
+            except ValueError:
+                continue
+            for name, v in zip(["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"], f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(clk) if clk else None, "sm_max_mhz": max(mx) if mx else None,
+                "power_w_max": max(pw) if pw else None, "samples": len(clk), "reasons": sorted(reasons)}
+
+
+def main():
+    a = parse()
+    if a.impl == "reference":
+        print(json.dumps({"impl": "reference", "unavailable": "hwang595/ps_pytorch has no setup.py/pyproject (pip: 'not installable'), and its "
+                          "entry points import mpi4py + blosc (absent, no network) and need mpirun + dataset downloads; see DESIGN.md"}))
+        return 0
+    import torch
+    import torch.distributed as dist
+    rank, local, world = int(os.environ.get("RANK", 0)), int(os.environ.get("LOCAL_RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
+    if world != a.gpus:
+        if world == 1 and a.gpus > 1:    # convenience: self-launch
+            from ps_pytorch_b200.launch import launch
+            return launch(a.gpus, [sys.executable, os.path.abspath(__file__)] + sys.argv[1:])
+        raise SystemExit("WORLD_SIZE=%d but --gpus %d" % (world, a.gpus))
+    assert torch.cuda.is_available(), "bench.py needs a GPU"
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("gloo", rank=rank, world_size=world)
+    if a.impl == "nccl-baseline":
+        sys.path.insert(0, os.path.join(ROOT, "baseline"))
+        import nccl_ps
+        return nccl_ps.bench(a, rank, local, world)
+
+    from ps_pytorch_b200 import ops
+    from ps_pytorch_b200.engine import PSJob
+    from ps_pytorch_b200.config import input_shape_for, num_classes_for
+    colocate = not a.no_colocate
+    job = PSJob(network=a.network, dataset=a.dataset, batch_size=a.batch_size, device=dev, dtype="bf16", lr=0.1, momentum=0.9,
+                optimizer=a.optimizer, topology=a.topology, colocate=colocate, grad_dtype=a.grad_dtype, overlap=a.overlap,
+                cuda_graph=not a.no_graph, backend=a.backend)
+    nworkers = job.comm.num_workers
+    c, h, w = input_shape_for(a.dataset)
+    B = a.batch_size
+    # synthetic data of the named shape, resident in PINNED host memory; 8 distinct batches rotate so no step re-reads
+    # the previous step's input (and the ~3 GB/step activation working set is >> the 126 MB L2 anyway)
+    nb = 8
+    g = torch.Generator().manual_seed(1234 + rank)
+    xs = [torch.randn(B, c, h, w, generator=g).to(torch.bfloat16).contiguous(memory_format=torch.channels_last).pin_memory() for _ in range(nb)]
+    ys = [torch.randint(0, num_classes_for(a.dataset), (B,), generator=g).pin_memory() for _ in range(nb)]
+    h2d = xs[0].numel() * xs[0].element_size() + ys[0].numel() * 8 if job.is_worker else 0
+
+    def run(nsteps, read_loss):
+        last = None
+        for i in range(nsteps):
+            last = job.step(xs[i % nb], ys[i % nb])
+            if read_loss and last is not None:
+                last = float(last)            # D2H read of the step's result, every step
+        return last
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+
+    def timed(nsteps, read_loss):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0 = time.perf_counter()
+        e0.record()
+        last = run(nsteps, read_loss)
+        e1.record()
+        torch.cuda.synchronize()
+        wall = (time.perf_counter() - t0) * 1e3
+        barrier()
+        ms = e0.elapsed_time(e1)
+        t = torch.tensor([ms, wall], dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t[0]), float(t[1]), last
+
+    run(max(a.warmup, 3), False)          # untimed warm-up (includes CUDA-graph capture)
+    barrier()
+    if hasattr(job.comm, "check_error"):
+        job.comm.check_error()
+    sampler = ClockSampler()
+    if rank == 0:
+        sampler.start()
+    l0 = ops.launch_count
+    ms, wall_ms, loss = timed(a.steps, False)
+    launches = ops.launch_count - l0
+    clocks = sampler.stop(world) if rank == 0 else None
+    e2e = None
+    if not a.skip_e2e:
+        ems, ewall, loss = timed(a.steps, True)
+        e2e_ms = max(ems, ewall)          # the D2H read blocks the host: wall time is the honest end-to-end clock
+        e2e = {"value": nworkers * B * a.steps / (e2e_ms * 1e-3), "unit": "images/s", "ms_per_step": e2e_ms / a.steps,
+               "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4 if job.is_worker else 0}
+    if hasattr(job.comm, "check_error"):
+        job.comm.check_error()
+    lt = torch.tensor([float(loss) if loss is not None else float("nan")])
+    if rank == 0:
+        value = nworkers * B * a.steps / (ms * 1e-3)
+        out = {"metric": "ResNet-18/CIFAR-10 images/sec (whole box, device-timed, max over ranks)" if a.network == "ResNet18" else a.network + " images/sec",
+               "value": value, "unit": "images/s", "n_gpus": world, "steps": a.steps, "warmup": a.warmup, "ms_per_step": ms / a.steps,
+               "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic (random images of the dataset shape, random-init weights)",
+               "impl": "ours",
+               "config": {"model": a.network, "dataset_shape": "%s %dx%dx%d" % (a.dataset, c, h, w), "global_batch": nworkers * B,
+                          "per_worker_batch": B, "seq_len": None,
+                          "parallelism": "%s: 1 server + %d workers on %d GPUs%s" % (a.topology, nworkers, world, " (worker co-located on the PS GPU)" if colocate else ""),
+                          "grad_wire": a.grad_dtype, "optimizer": a.optimizer + " momentum 0.9, fused in the PS kernel", "backend": a.backend,
+                          "transport": job.comm.name + ":" + getattr(getattr(job.comm, "arena", None), "backend", "-"),
+                          "cuda_graph": not a.no_graph,
+                          "l2": "inputs rotate over 8 distinct pinned host batches; per-step activation working set (~3 GB) >> 126 MB L2"},
+               "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "wall_ms_per_step": wall_ms / a.steps,
+               "final_loss": float(lt[0])}
+        print(json.dumps(out))
+    job.close()
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main() or 0)

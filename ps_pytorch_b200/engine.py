@@ -1,0 +1,93 @@
+"""Programmatic API: one object that is this rank's share of a parameter-server job.
+
+``PSJob`` builds the transport and the roles exactly as ``src/distributed_nn.py`` does from flags, and exposes
+``step(x_host, y_host)`` — one synchronous PS iteration on this rank: (rank 0) publish → (workers) wait weights, forward,
+backward, push → (server ranks) reduce + optimizer + broadcast.  ``bench.py`` and ``__graft_entry__.smoke`` drive this;
+the ``SyncReplicasMaster_NN.start()`` / ``DistributedWorker.train()`` loops of the reference API are the same body in a loop.
+"""
+from __future__ import annotations
+
+from typing import Optional
+
+import torch
+import torch.distributed as dist
+
+from . import nn as pnn
+from .config import num_classes_for
+from .models import build_model
+from .parallel.arena import ParamLayout
+from .parallel.compute import resolve_dtype
+from .parallel.ps import SyncReplicasMaster_NN
+from .parallel.transport import GlooTransport, LocalTransport
+from .parallel.worker import DistributedWorker
+
+
+class PSJob:
+    def __init__(self, network: str = "ResNet18", dataset: str = "Cifar10", batch_size: int = 1024, device="cuda", dtype: str = "auto",
+                 lr: float = 0.1, momentum: float = 0.9, optimizer: str = "sgd", weight_decay: float = 0.0, nesterov: bool = False,
+                 transport: str = "auto", topology: str = "ps", colocate: bool = True, grad_dtype: str = "bf16", num_aggregate: Optional[int] = None,
+                 overlap: bool = False, num_buckets: int = 4, cuda_graph: bool = True, backend: str = "auto", max_steps: int = 10 ** 9,
+                 eval_freq: int = 10 ** 9, train_dir: str = "output/models/", mode: str = "normal", compress: bool = False, seed: int = 1):
+        self.device = torch.device(device)
+        self.rank = dist.get_rank() if dist.is_initialized() else 0
+        self.world = dist.get_world_size() if dist.is_initialized() else 1
+        if backend != "auto":
+            pnn.set_backend(backend)
+        torch.manual_seed(seed)
+        nc = num_classes_for(dataset)
+        self.dtype = resolve_dtype(dtype, self.device)
+        proto = build_model(network, nc)
+        self.layout = ParamLayout.from_module(proto, channels_last=self.device.type == "cuda")
+        n_buf = sum(b.numel() for b in proto.buffers())
+        if transport == "auto":
+            transport = "nvl" if self.device.type == "cuda" else ("local" if self.world == 1 else "gloo")
+        if transport == "local":
+            self.comm = LocalTransport(self.layout, self.device)
+        elif transport == "gloo":
+            self.comm = GlooTransport(self.layout, compress=compress, colocate=colocate)
+        else:
+            from .parallel.nvl import NvlTransport
+            self.comm = NvlTransport(self.layout, self.device, grad_dtype=grad_dtype, colocate=colocate,
+                                     num_buckets=num_buckets if overlap else 1, topology=topology, n_buffers=n_buf)
+        self.topology = getattr(self.comm, "topology", "ps")
+        P = self.comm.num_workers
+        self.k = P if num_aggregate is None else max(1, min(num_aggregate, P))
+        common = dict(batch_size=batch_size, learning_rate=lr, max_epochs=10 ** 9, momentum=momentum, network=network, eval_freq=eval_freq,
+                      train_dir=train_dir, max_steps=max_steps, compress_grad="compress" if compress else "None", device=self.device,
+                      mode=mode, dtype=dtype)
+        self.master = self.worker = None
+        self.is_server = self.rank == 0 or self.topology == "sharded"
+        self.is_worker = self.rank in self.comm.worker_ranks
+        if self.is_server:
+            self.master = SyncReplicasMaster_NN(comm=self.comm, num_aggregate=self.k, optimizer=optimizer, weight_decay=weight_decay,
+                                                nesterov=nesterov, worker_dtype=self.dtype, **common)
+            self.master.build_model(num_classes=nc, network=proto)
+        if self.is_worker:
+            self.worker = DistributedWorker(comm=self.comm, overlap=overlap, num_buckets=num_buckets, cuda_graph=cuda_graph,
+                                            log_interval=10 ** 9, **common)
+            self.worker.build_model(num_classes=nc)
+        self.batch_size = batch_size
+        self.step_id = 0
+        self.last_loss = None
+
+    def step(self, x_host: Optional[torch.Tensor] = None, y_host: Optional[torch.Tensor] = None):
+        """One PS iteration.  Returns this rank's loss tensor (device, async) or None on a pure-PS rank."""
+        self.step_id += 1
+        m, w = self.master, self.worker
+        if m is not None and self.rank == 0 or (m is not None and self.topology == "sharded"):
+            m.async_bcast_step()
+        if w is not None:
+            w.sync_fetch_step()
+            w.update_step()
+            loss, _ = w.compute.train_step(x_host, y_host, w.cur_step)
+            w._send_grads()
+            self.last_loss = loss
+        if m is not None:
+            self.comm.ps_reduce_update(m.cur_step, self.k, m.optimizer, m.master, **m._ru_kwargs())
+            if m.lowp is not m.master and not getattr(self.comm, "fused_lowp", False):
+                m.lowp.flat.copy_(m.master.flat)
+            m.cur_step += 1
+        return self.last_loss
+
+    def close(self):
+        self.comm.close()

@@ -1,0 +1,344 @@
+// BatchNorm2d (training + inference) for NHWC bf16 activations, fused with the residual add and ReLU that follow it
+// in every ResNet/VGG block of the reference models (/root/reference/src/model_ops/resnet.py:32-35,59-64, vgg.py:55).
+//
+// On B200 these layers are pure HBM streaming: stock ATen spends 7.6 ms of a 13.4 ms ResNet-18/b1024 step in its BN
+// kernels (profiles/probe0_stock_torch.md) at ~0.5 TB/s.  Here every pass is a 16-byte-vector grid-stride stream:
+//   forward : stats (1 read)  -> finalize (tiny)  -> apply+residual+ReLU (1-2 reads, 1 write)
+//   backward: reduce (dz, z, x reads) -> finalize (tiny) -> dx (+ d_residual) (3 reads, 1-2 writes)
+// Per-channel statistics use a shifted sum (shift = first row) so E[x^2]-E[x]^2 does not cancel; partial sums are
+// written per CTA and merged by the finalize kernel in a fixed order (deterministic, no atomics).
+//
+// Thread mapping: a row of C channels is LC = C/8 16-byte lanes; LC is a power of two <= 256, so with 256-thread
+// CTAs and strides that are multiples of 256 every thread keeps ONE channel lane for its whole life and holds that
+// lane's 8 per-channel coefficients in registers.
+#include <torch/extension.h>
+#include <ATen/cuda/CUDAContext.h>
+#include "common.cuh"
+
+namespace psb {
+
+constexpr int kBnThreads = 256;
+
+// ---- forward: partial statistics --------------------------------------------------------------------------------------
+// partial[blk][0][C] = sum(x - K), partial[blk][1][C] = sum((x-K)^2), K = x[row 0]
+__global__ void __launch_bounds__(kBnThreads) bn_stats_kernel(const uint4* __restrict__ x, long long M, int LC, float* __restrict__ partial) {
+    extern __shared__ float sm[];                       // [kBnThreads][16]
+    const int lane = threadIdx.x % LC;
+    const int ty = threadIdx.x / LC;
+    const int RP = kBnThreads / LC;                     // rows per CTA pass
+    float K[8], s[8], q[8];
+    unpack8(ld_nc_v4(x + lane), K);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { s[j] = 0.f; q[j] = 0.f; }
+    const long long rstride = (long long)gridDim.x * RP;
+    long long r = (long long)blockIdx.x * RP + ty;
+    // 4 independent 16-byte loads in flight per thread
+    for (; r + 3 * rstride < M; r += 4 * rstride) {
+        uint4 v0 = ld_nc_v4(x + r * LC + lane), v1 = ld_nc_v4(x + (r + rstride) * LC + lane);
+        uint4 v2 = ld_nc_v4(x + (r + 2 * rstride) * LC + lane), v3 = ld_nc_v4(x + (r + 3 * rstride) * LC + lane);
+        float f[8];
+#define ACC(v) unpack8(v, f); _Pragma("unroll") for (int j = 0; j < 8; ++j) { float d = f[j] - K[j]; s[j] += d; q[j] = fmaf(d, d, q[j]); }
+        ACC(v0) ACC(v1) ACC(v2) ACC(v3)
+    }
+    for (; r < M; r += rstride) { uint4 v = ld_nc_v4(x + r * LC + lane); float f[8]; ACC(v) }
+#undef ACC
+    float* my = sm + threadIdx.x * 16;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { my[j] = s[j]; my[8 + j] = q[j]; }
+    __syncthreads();
+    if (ty == 0) {
+        for (int t = 1; t < RP; ++t) {
+            const float* o = sm + (t * LC + lane) * 16;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) { s[j] += o[j]; q[j] += o[8 + j]; }
+        }
+        const int C = LC * 8;
+        float* ps = partial + (long long)blockIdx.x * 2 * C + lane * 8;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { ps[j] = s[j]; ps[C + j] = q[j]; }
+    }
+}
+
+// one CTA per 32 channels, 8 partial-groups x 32 channels
+template <typename PT>
+__global__ void __launch_bounds__(256) bn_finalize_kernel(const float* __restrict__ partial, int nblk, int C, long long M,
+                                                          const __nv_bfloat16* __restrict__ x_row0, const PT* __restrict__ gamma,
+                                                          const PT* __restrict__ beta, float* running_mean, float* running_var,
+                                                          float momentum, float eps, float* __restrict__ mean, float* __restrict__ invstd,
+                                                          float* __restrict__ coef_a, float* __restrict__ coef_b) {
+    __shared__ float ss[8][32], sq[8][32];
+    const int cl = threadIdx.x & 31, grp = threadIdx.x >> 5;
+    const int c = blockIdx.x * 32 + cl;
+    float s = 0.f, q = 0.f;
+    if (c < C)
+        for (int b = grp; b < nblk; b += 8) { s += partial[(long long)b * 2 * C + c]; q += partial[(long long)b * 2 * C + C + c]; }
+    ss[grp][cl] = s; sq[grp][cl] = q;
+    __syncthreads();
+    if (grp == 0 && c < C) {
+        for (int g = 1; g < 8; ++g) { s += ss[g][cl]; q += sq[g][cl]; }
+        const float inv_m = 1.f / (float)M;
+        const float dm = s * inv_m;
+        const float K = __bfloat162float(x_row0[c]);
+        const float mu = K + dm;
+        const float var = fmaxf(q * inv_m - dm * dm, 0.f);
+        const float is = rsqrtf(var + eps);
+        mean[c] = mu; invstd[c] = is;
+        const float ga = gamma ? to_f(gamma[c]) : 1.f, be = beta ? to_f(beta[c]) : 0.f;
+        coef_a[c] = ga * is;
+        coef_b[c] = be - mu * ga * is;
+        if (running_mean) {
+            const float unbiased = M > 1 ? var * (float)M / (float)(M - 1) : var;
+            running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * mu;
+            running_var[c] = (1.f - momentum) * running_var[c] + momentum * unbiased;
+        }
+    }
+}
+
+// inference: coefficients from running statistics
+template <typename PT>
+__global__ void bn_eval_coef_kernel(int C, const PT* gamma, const PT* beta, const float* rm, const float* rv, float eps, float* a, float* b) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= C) return;
+    const float is = rsqrtf(rv[c] + eps);
+    const float ga = gamma ? to_f(gamma[c]) : 1.f, be = beta ? to_f(beta[c]) : 0.f;
+    a[c] = ga * is; b[c] = be - rm[c] * ga * is;
+}
+
+// ---- forward: z = relu(x*a + b + res) -----------------------------------------------------------------------------------
+template <bool RELU, bool RES>
+__global__ void __launch_bounds__(kBnThreads) bn_apply_kernel(const uint4* __restrict__ x, const uint4* __restrict__ res, uint4* __restrict__ z,
+                                                              const float* __restrict__ coef_a, const float* __restrict__ coef_b, long long nvec, int LC) {
+    const int lane = threadIdx.x % LC;
+    float a[8], b[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { a[j] = coef_a[lane * 8 + j]; b[j] = coef_b[lane * 8 + j]; }
+    const long long stride = (long long)gridDim.x * kBnThreads;
+    for (long long i = (long long)blockIdx.x * kBnThreads + threadIdx.x; i < nvec; i += 2 * stride) {
+        const bool two = i + stride < nvec;
+        uint4 v0 = ld_nc_v4(x + i), v1 = two ? ld_nc_v4(x + i + stride) : v0;
+        uint4 r0, r1;
+        if (RES) { r0 = ld_nc_v4(res + i); r1 = two ? ld_nc_v4(res + i + stride) : r0; }
+        float f[8], g[8];
+        unpack8(v0, f);
+        if (RES) unpack8(r0, g);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { float y = fmaf(f[j], a[j], b[j]); if (RES) y += g[j]; f[j] = RELU ? fmaxf(y, 0.f) : y; }
+        st_v4(z + i, pack8(f));
+        if (two) {
+            unpack8(v1, f);
+            if (RES) unpack8(r1, g);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) { float y = fmaf(f[j], a[j], b[j]); if (RES) y += g[j]; f[j] = RELU ? fmaxf(y, 0.f) : y; }
+            st_v4(z + i + stride, pack8(f));
+        }
+    }
+}
+
+// ---- backward: partial reductions ------------------------------------------------------------------------------------------
+// dy = dz * (z > 0) if RELU else dz;  partial[blk][0][C] = sum(dy), partial[blk][1][C] = sum(dy * (x - mean))
+template <bool RELU>
+__global__ void __launch_bounds__(kBnThreads) bn_bwd_reduce_kernel(const uint4* __restrict__ dz, const uint4* __restrict__ z, const uint4* __restrict__ x,
+                                                                   const float* __restrict__ mean, long long M, int LC, float* __restrict__ partial) {
+    extern __shared__ float sm[];
+    const int lane = threadIdx.x % LC, ty = threadIdx.x / LC, RP = kBnThreads / LC;
+    float mu[8], s[8], q[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { mu[j] = mean[lane * 8 + j]; s[j] = 0.f; q[j] = 0.f; }
+    const long long rstride = (long long)gridDim.x * RP;
+    long long r = (long long)blockIdx.x * RP + ty;
+#define ACCB(idx) { float d[8], xx[8], zz[8]; unpack8(vd##idx, d); unpack8(vx##idx, xx); if (RELU) unpack8(vz##idx, zz); \
+        _Pragma("unroll") for (int j = 0; j < 8; ++j) { float dy = (RELU && !(zz[j] > 0.f)) ? 0.f : d[j]; s[j] += dy; q[j] = fmaf(dy, xx[j] - mu[j], q[j]); } }
+    for (; r + rstride < M; r += 2 * rstride) {
+        const long long i0 = r * LC + lane, i1 = (r + rstride) * LC + lane;
+        uint4 vd0 = ld_nc_v4(dz + i0), vx0 = ld_nc_v4(x + i0), vd1 = ld_nc_v4(dz + i1), vx1 = ld_nc_v4(x + i1), vz0, vz1;
+        if (RELU) { vz0 = ld_nc_v4(z + i0); vz1 = ld_nc_v4(z + i1); }
+        ACCB(0) ACCB(1)
+    }
+    for (; r < M; r += rstride) {
+        const long long i0 = r * LC + lane;
+        uint4 vd0 = ld_nc_v4(dz + i0), vx0 = ld_nc_v4(x + i0), vz0;
+        if (RELU) vz0 = ld_nc_v4(z + i0);
+        ACCB(0)
+    }
+#undef ACCB
+    float* my = sm + threadIdx.x * 16;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { my[j] = s[j]; my[8 + j] = q[j]; }
+    __syncthreads();
+    if (ty == 0) {
+        for (int t = 1; t < RP; ++t) {
+            const float* o = sm + (t * LC + lane) * 16;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) { s[j] += o[j]; q[j] += o[8 + j]; }
+        }
+        const int C = LC * 8;
+        float* ps = partial + (long long)blockIdx.x * 2 * C + lane * 8;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { ps[j] = s[j]; ps[C + j] = q[j]; }
+    }
+}
+
+// dgamma = sum(dy*xhat) = invstd*sum(dy*(x-mean)); dbeta = sum(dy);
+// dx = c1*(dy - c2 - (x-mean)*c3), c1 = gamma*invstd, c2 = sum_dy/M, c3 = invstd^2*sum(dy*(x-mean))/M
+template <typename PT>
+__global__ void __launch_bounds__(256) bn_bwd_finalize_kernel(const float* __restrict__ partial, int nblk, int C, long long M,
+                                                              const PT* __restrict__ gamma, const float* __restrict__ invstd,
+                                                              PT* __restrict__ dgamma, PT* __restrict__ dbeta, float* __restrict__ c1,
+                                                              float* __restrict__ c2, float* __restrict__ c3) {
+    __shared__ float ss[8][32], sq[8][32];
+    const int cl = threadIdx.x & 31, grp = threadIdx.x >> 5;
+    const int c = blockIdx.x * 32 + cl;
+    float s = 0.f, q = 0.f;
+    if (c < C)
+        for (int b = grp; b < nblk; b += 8) { s += partial[(long long)b * 2 * C + c]; q += partial[(long long)b * 2 * C + C + c]; }
+    ss[grp][cl] = s; sq[grp][cl] = q;
+    __syncthreads();
+    if (grp == 0 && c < C) {
+        for (int g = 1; g < 8; ++g) { s += ss[g][cl]; q += sq[g][cl]; }
+        const float is = invstd[c];
+        const float ga = gamma ? to_f(gamma[c]) : 1.f;
+        if (dgamma) dgamma[c] = from_f<PT>(q * is);
+        if (dbeta) dbeta[c] = from_f<PT>(s);
+        const float inv_m = 1.f / (float)M;
+        c1[c] = ga * is; c2[c] = s * inv_m; c3[c] = q * is * is * inv_m;
+    }
+}
+
+template <bool RELU, bool RES>
+__global__ void __launch_bounds__(kBnThreads) bn_bwd_apply_kernel(const uint4* __restrict__ dz, const uint4* __restrict__ z, const uint4* __restrict__ x,
+                                                                  const float* __restrict__ mean, const float* __restrict__ c1, const float* __restrict__ c2,
+                                                                  const float* __restrict__ c3, uint4* __restrict__ dx, uint4* __restrict__ dres,
+                                                                  long long nvec, int LC) {
+    const int lane = threadIdx.x % LC;
+    float mu[8], k1[8], k2[8], k3[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { mu[j] = mean[lane * 8 + j]; k1[j] = c1[lane * 8 + j]; k2[j] = c2[lane * 8 + j]; k3[j] = c3[lane * 8 + j]; }
+    const long long stride = (long long)gridDim.x * kBnThreads;
+    for (long long i = (long long)blockIdx.x * kBnThreads + threadIdx.x; i < nvec; i += 2 * stride) {
+        const bool two = i + stride < nvec;
+        const long long i1 = two ? i + stride : i;
+        uint4 vd0 = ld_nc_v4(dz + i), vx0 = ld_nc_v4(x + i), vd1 = ld_nc_v4(dz + i1), vx1 = ld_nc_v4(x + i1), vz0, vz1;
+        if (RELU) { vz0 = ld_nc_v4(z + i); vz1 = ld_nc_v4(z + i1); }
+#define APP(idx, off) { float d[8], xx[8], zz[8], o[8]; unpack8(vd##idx, d); unpack8(vx##idx, xx); if (RELU) unpack8(vz##idx, zz); \
+        _Pragma("unroll") for (int j = 0; j < 8; ++j) { float dy = (RELU && !(zz[j] > 0.f)) ? 0.f : d[j]; d[j] = dy; \
+            o[j] = k1[j] * (dy - k2[j] - (xx[j] - mu[j]) * k3[j]); } \
+        st_v4(dx + off, pack8(o)); if (RES && RELU) st_v4(dres + off, pack8(d)); }
+        APP(0, i)
+        if (two) APP(1, i1)
+#undef APP
+    }
+}
+
+// ---- host ---------------------------------------------------------------------------------------------------------------------
+static int stream_grid(long long work_items, int per_block) {
+    long long blocks = (work_items + per_block - 1) / per_block;
+    return (int)std::max<long long>(1, std::min<long long>(blocks, (long long)kNumSMs * 4));
+}
+
+static void check_act(const at::Tensor& t, const char* name) {
+    TORCH_CHECK(t.is_cuda() && t.scalar_type() == at::kBFloat16, name, ": bf16 CUDA tensor expected");
+    TORCH_CHECK(t.dim() == 4 && t.is_contiguous(at::MemoryFormat::ChannelsLast), name, ": NHWC (channels_last) layout expected");
+}
+
+// returns {z, mean, invstd}
+std::vector<at::Tensor> bn_forward(at::Tensor x, c10::optional<at::Tensor> gamma, c10::optional<at::Tensor> beta,
+                                   c10::optional<at::Tensor> running_mean, c10::optional<at::Tensor> running_var,
+                                   c10::optional<at::Tensor> residual, bool training, double momentum, double eps, bool relu) {
+    check_act(x, "x");
+    const int C = (int)x.size(1);
+    const long long M = x.numel() / C;
+    const int LC = C / 8;
+    TORCH_CHECK(C % 8 == 0 && LC >= 1 && LC <= 256 && (LC & (LC - 1)) == 0, "bn: C/8 must be a power of two <= 256");
+    if (residual.has_value()) { check_act(*residual, "residual"); TORCH_CHECK(residual->sizes() == x.sizes()); }
+    auto stream = at::cuda::getCurrentCUDAStream();
+    auto fopt = x.options().dtype(at::kFloat);
+    at::Tensor z = at::empty_like(x);
+    at::Tensor mean = at::empty({C}, fopt), invstd = at::empty({C}, fopt), ca = at::empty({C}, fopt), cb = at::empty({C}, fopt);
+    const bool p_bf16 = gamma.has_value() && gamma->scalar_type() == at::kBFloat16;
+    if (gamma.has_value()) TORCH_CHECK(p_bf16 || gamma->scalar_type() == at::kFloat);
+    const void* gp = gamma.has_value() ? gamma->data_ptr() : nullptr;
+    const void* bp = beta.has_value() ? beta->data_ptr() : nullptr;
+    float* rm = running_mean.has_value() ? running_mean->data_ptr<float>() : nullptr;
+    float* rv = running_var.has_value() ? running_var->data_ptr<float>() : nullptr;
+    const uint4* xp = reinterpret_cast<const uint4*>(x.data_ptr());
+    if (training) {
+        const int RP = kBnThreads / LC;
+        const int nblk = stream_grid(M, RP * 8);
+        at::Tensor partial = at::empty({nblk, 2, C}, fopt);
+        bn_stats_kernel<<<nblk, kBnThreads, kBnThreads * 16 * sizeof(float), stream>>>(xp, M, LC, partial.data_ptr<float>());
+        C10_CUDA_KERNEL_LAUNCH_CHECK();
+        const int fb = (C + 31) / 32;
+        if (p_bf16)
+            bn_finalize_kernel<__nv_bfloat16><<<fb, 256, 0, stream>>>(partial.data_ptr<float>(), nblk, C, M, (const __nv_bfloat16*)x.data_ptr(),
+                (const __nv_bfloat16*)gp, (const __nv_bfloat16*)bp, rm, rv, (float)momentum, (float)eps, mean.data_ptr<float>(), invstd.data_ptr<float>(),
+                ca.data_ptr<float>(), cb.data_ptr<float>());
+        else
+            bn_finalize_kernel<float><<<fb, 256, 0, stream>>>(partial.data_ptr<float>(), nblk, C, M, (const __nv_bfloat16*)x.data_ptr(),
+                (const float*)gp, (const float*)bp, rm, rv, (float)momentum, (float)eps, mean.data_ptr<float>(), invstd.data_ptr<float>(),
+                ca.data_ptr<float>(), cb.data_ptr<float>());
+        C10_CUDA_KERNEL_LAUNCH_CHECK();
+    } else {
+        TORCH_CHECK(rm && rv, "bn eval needs running statistics");
+        if (p_bf16) bn_eval_coef_kernel<__nv_bfloat16><<<(C + 127) / 128, 128, 0, stream>>>(C, (const __nv_bfloat16*)gp, (const __nv_bfloat16*)bp, rm, rv, (float)eps, ca.data_ptr<float>(), cb.data_ptr<float>());
+        else bn_eval_coef_kernel<float><<<(C + 127) / 128, 128, 0, stream>>>(C, (const float*)gp, (const float*)bp, rm, rv, (float)eps, ca.data_ptr<float>(), cb.data_ptr<float>());
+        C10_CUDA_KERNEL_LAUNCH_CHECK();
+    }
+    const long long nvec = x.numel() / 8;
+    const int grid = stream_grid(nvec, kBnThreads * 2);
+    const uint4* rp = residual.has_value() ? reinterpret_cast<const uint4*>(residual->data_ptr()) : nullptr;
+    uint4* zp = reinterpret_cast<uint4*>(z.data_ptr());
+    const float *pa = ca.data_ptr<float>(), *pb = cb.data_ptr<float>();
+    if (relu && rp) bn_apply_kernel<true, true><<<grid, kBnThreads, 0, stream>>>(xp, rp, zp, pa, pb, nvec, LC);
+    else if (relu) bn_apply_kernel<true, false><<<grid, kBnThreads, 0, stream>>>(xp, rp, zp, pa, pb, nvec, LC);
+    else if (rp) bn_apply_kernel<false, true><<<grid, kBnThreads, 0, stream>>>(xp, rp, zp, pa, pb, nvec, LC);
+    else bn_apply_kernel<false, false><<<grid, kBnThreads, 0, stream>>>(xp, rp, zp, pa, pb, nvec, LC);
+    C10_CUDA_KERNEL_LAUNCH_CHECK();
+    return {z, mean, invstd};
+}
+
+// returns {dx, dres (or undefined), dgamma, dbeta}
+std::vector<at::Tensor> bn_backward(at::Tensor dz, at::Tensor z, at::Tensor x, c10::optional<at::Tensor> gamma, at::Tensor mean,
+                                    at::Tensor invstd, bool relu, bool has_res) {
+    check_act(dz, "dz"); check_act(x, "x");
+    if (relu) check_act(z, "z");
+    const int C = (int)x.size(1);
+    const long long M = x.numel() / C;
+    const int LC = C / 8;
+    auto stream = at::cuda::getCurrentCUDAStream();
+    auto fopt = x.options().dtype(at::kFloat);
+    const int RP = kBnThreads / LC;
+    const int nblk = stream_grid(M, RP * 8);
+    at::Tensor partial = at::empty({nblk, 2, C}, fopt);
+    const uint4 *dzp = (const uint4*)dz.data_ptr(), *zp = relu ? (const uint4*)z.data_ptr() : nullptr, *xp = (const uint4*)x.data_ptr();
+    if (relu) bn_bwd_reduce_kernel<true><<<nblk, kBnThreads, kBnThreads * 16 * sizeof(float), stream>>>(dzp, zp, xp, mean.data_ptr<float>(), M, LC, partial.data_ptr<float>());
+    else bn_bwd_reduce_kernel<false><<<nblk, kBnThreads, kBnThreads * 16 * sizeof(float), stream>>>(dzp, zp, xp, mean.data_ptr<float>(), M, LC, partial.data_ptr<float>());
+    C10_CUDA_KERNEL_LAUNCH_CHECK();
+    at::Tensor c1 = at::empty({C}, fopt), c2 = at::empty({C}, fopt), c3 = at::empty({C}, fopt);
+    at::Tensor dgamma, dbeta;
+    const int fb = (C + 31) / 32;
+    if (gamma.has_value() && gamma->scalar_type() == at::kBFloat16) {
+        dgamma = at::empty({C}, x.options()); dbeta = at::empty({C}, x.options());
+        bn_bwd_finalize_kernel<__nv_bfloat16><<<fb, 256, 0, stream>>>(partial.data_ptr<float>(), nblk, C, M, (const __nv_bfloat16*)gamma->data_ptr(), invstd.data_ptr<float>(),
+            (__nv_bfloat16*)dgamma.data_ptr(), (__nv_bfloat16*)dbeta.data_ptr(), c1.data_ptr<float>(), c2.data_ptr<float>(), c3.data_ptr<float>());
+    } else {
+        dgamma = at::empty({C}, fopt); dbeta = at::empty({C}, fopt);
+        bn_bwd_finalize_kernel<float><<<fb, 256, 0, stream>>>(partial.data_ptr<float>(), nblk, C, M, gamma.has_value() ? gamma->data_ptr<float>() : nullptr, invstd.data_ptr<float>(),
+            dgamma.data_ptr<float>(), dbeta.data_ptr<float>(), c1.data_ptr<float>(), c2.data_ptr<float>(), c3.data_ptr<float>());
+    }
+    C10_CUDA_KERNEL_LAUNCH_CHECK();
+    at::Tensor dx = at::empty_like(x);
+    at::Tensor dres;
+    if (has_res) dres = relu ? at::empty_like(x) : dz;       // without ReLU the residual gradient IS dz: no copy
+    const long long nvec = x.numel() / 8;
+    const int grid = stream_grid(nvec, kBnThreads * 2);
+    uint4* dxp = (uint4*)dx.data_ptr();
+    uint4* drp = (has_res && relu) ? (uint4*)dres.data_ptr() : nullptr;
+    const float *mp = mean.data_ptr<float>(), *p1 = c1.data_ptr<float>(), *p2 = c2.data_ptr<float>(), *p3 = c3.data_ptr<float>();
+    if (relu && has_res) bn_bwd_apply_kernel<true, true><<<grid, kBnThreads, 0, stream>>>(dzp, zp, xp, mp, p1, p2, p3, dxp, drp, nvec, LC);
+    else if (relu) bn_bwd_apply_kernel<true, false><<<grid, kBnThreads, 0, stream>>>(dzp, zp, xp, mp, p1, p2, p3, dxp, drp, nvec, LC);
+    else bn_bwd_apply_kernel<false, false><<<grid, kBnThreads, 0, stream>>>(dzp, zp, xp, mp, p1, p2, p3, dxp, drp, nvec, LC);
+    C10_CUDA_KERNEL_LAUNCH_CHECK();
+    return {dx, dres, dgamma, dbeta};
+}
+
+}  // namespace psb

@@ -1,0 +1,409 @@
+// The two communication-bound hot paths of the parameter server as fused kernels over peer-mapped memory
+// (NVLink 5 / NVSwitch), with no NCCL/MPI call on the path:
+//
+//   push_kernel           worker side.  gradient arena -> cast (bf16) or block-scaled fp8 quantise (32-element blocks,
+//                         e8m0 scale) -> 16-byte stores straight into the PS's slot for this worker (a peer pointer)
+//                         -> system-scope release of the arrival flag (value = step id).  Also zeroes the local
+//                         gradient arena for the next backward.  Replaces D2H + numpy + Blosc + pickle + MPI isend
+//                         (/root/reference/src/distributed_worker.py:254-272, compression.py:18-23).
+//   reduce_update_kernel  PS side.  per bucket: acquire-poll the P arrival flags (first K of P win; stale step ids are
+//                         ignored), load the K slots (local HBM in push mode, or peers' gradient arenas by P2P loads in
+//                         pull mode), dequantise, fp32 sum, x 1/K, SGD-momentum/Nesterov/WD or Adam/AMSGrad on the fp32
+//                         master + state, and store the fresh bf16 weights into every worker's replica (peer stores, or
+//                         ONE multimem.st through the NVLS multicast mapping) followed by a release of the per-bucket
+//                         "weights ready" flag (value = next step id, which doubles as the step message).  Replaces
+//                         Waitany + decompress + numpy sum + /K + optimizer.step + per-layer Blosc bcast
+//                         (/root/reference/src/sync_replicas_master_nn.py:157-225, optim/*.py).
+//   wait_flag_kernel      worker side: acquire-spin until the local "weights ready" flag reaches this worker's step.
+//
+// All step counters live in device memory, so a whole worker step (wait -> fwd -> bwd -> push) and a whole PS step are
+// CUDA-graph capturable.  Every spin has a wall-clock timeout (globaltimer) that raises an error word instead of
+// hanging the GPU.
+#include <torch/extension.h>
+#include <ATen/cuda/CUDAContext.h>
+#include "optim_math.cuh"
+
+namespace psb {
+
+constexpr int kMaxPeers = 8;
+constexpr int kMaxBuckets = 16;
+enum WireMode { WIRE_BF16 = 0, WIRE_FP8 = 1, WIRE_FP32 = 2 };
+
+// ---- block-scaled fp8 (e4m3 payload, one e8m0 scale per 32 elements) ---------------------------------------------
+__device__ __forceinline__ int e8m0_exponent(float amax) {
+    // smallest e with amax / 2^e <= 448 (e4m3 max finite)
+    float s = amax * (1.0f / 448.0f);
+    if (!(s > 0.f)) return -127;
+    uint32_t u = __float_as_uint(s);
+    int e = (int)((u >> 23) & 0xff) - 127 + ((u & 0x7fffffu) ? 1 : 0);
+    return max(-126, min(127, e));
+}
+__device__ __forceinline__ float exp2i(int e) { return __uint_as_float((uint32_t)(e + 127) << 23); }   // e in [-126,127]
+
+__device__ __forceinline__ uint32_t quant4(float a, float b, float c, float d, float inv) {
+    __nv_fp8x2_storage_t lo = __nv_cvt_float2_to_fp8x2(make_float2(a * inv, b * inv), __NV_SATFINITE, __NV_E4M3);
+    __nv_fp8x2_storage_t hi = __nv_cvt_float2_to_fp8x2(make_float2(c * inv, d * inv), __NV_SATFINITE, __NV_E4M3);
+    return (uint32_t)lo | ((uint32_t)hi << 16);
+}
+__device__ __forceinline__ void dequant4(uint32_t q, float sc, float* f) {
+    __half2_raw lo = __nv_cvt_fp8x2_to_halfraw2((__nv_fp8x2_storage_t)(q & 0xffffu), __NV_E4M3);
+    __half2_raw hi = __nv_cvt_fp8x2_to_halfraw2((__nv_fp8x2_storage_t)(q >> 16), __NV_E4M3);
+    float2 a = __half22float2(*reinterpret_cast<__half2*>(&lo));
+    float2 b = __half22float2(*reinterpret_cast<__half2*>(&hi));
+    f[0] = a.x * sc; f[1] = a.y * sc; f[2] = b.x * sc; f[3] = b.y * sc;
+}
+
+// ================================================================================================================
+struct PushArgs {
+    const void* src;          // local gradient arena (bf16 or fp32), element-indexed
+    void* dst;                // slot base in the PS's memory (peer or local), element-indexed in the wire type
+    uint8_t* dst_scale;       // fp8 mode: scale bytes, one per 32 elements
+    long long lo, hi;         // element range, multiples of 128
+    long long* flag;          // arrival flag in the PS's memory
+    const long long* step_ptr;
+    int* counter;             // local, zero-initialised; used to detect the last CTA
+    int mode, src_fp32, zero_src;
+};
+
+__device__ __forceinline__ void load32(const PushArgs& a, long long i, float* f) {
+    if (a.src_fp32) {
+        const float* s = reinterpret_cast<const float*>(a.src) + i;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            uint4 v = ld_nc_v4(s + 4 * k);
+            f[4 * k] = __uint_as_float(v.x); f[4 * k + 1] = __uint_as_float(v.y);
+            f[4 * k + 2] = __uint_as_float(v.z); f[4 * k + 3] = __uint_as_float(v.w);
+        }
+    } else {
+        const __nv_bfloat16* s = reinterpret_cast<const __nv_bfloat16*>(a.src) + i;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) unpack8(ld_nc_v4(s + 8 * k), f + 8 * k);
+    }
+}
+
+__global__ void __launch_bounds__(256) push_kernel(PushArgs a) {
+    const int lane = threadIdx.x & 31;
+    const long long nthreads = (long long)gridDim.x * blockDim.x;
+    const long long t0 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const uint4 zero = make_uint4(0, 0, 0, 0);
+    for (long long i = a.lo + t0 * 32; i < a.hi; i += nthreads * 32) {
+        float f[32];
+        load32(a, i, f);
+        if (a.zero_src) {   // next backward accumulates into a clean arena: saves a separate 2-4 B/param memset pass
+            if (a.src_fp32) { float* s = (float*)a.src + i;
+#pragma unroll
+                for (int k = 0; k < 8; ++k) st_v4(s + 4 * k, zero);
+            } else { __nv_bfloat16* s = (__nv_bfloat16*)a.src + i;
+#pragma unroll
+                for (int k = 0; k < 4; ++k) st_v4(s + 8 * k, zero);
+            }
+        }
+        if (a.mode == WIRE_BF16) {
+            __nv_bfloat16* d = reinterpret_cast<__nv_bfloat16*>(a.dst) + i;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) st_na_v4(d + 8 * k, pack8(f + 8 * k));
+        } else if (a.mode == WIRE_FP32) {
+            float* d = reinterpret_cast<float*>(a.dst) + i;
+#pragma unroll
+            for (int k = 0; k < 8; ++k)
+                st_na_v4(d + 4 * k, make_uint4(__float_as_uint(f[4 * k]), __float_as_uint(f[4 * k + 1]), __float_as_uint(f[4 * k + 2]), __float_as_uint(f[4 * k + 3])));
+        } else {
+            float amax = 0.f;
+#pragma unroll
+            for (int k = 0; k < 32; ++k) amax = fmaxf(amax, fabsf(f[k]));
+            const int e = e8m0_exponent(amax);
+            const float inv = exp2i(-e);
+            uint8_t* d = reinterpret_cast<uint8_t*>(a.dst) + i;
+            st_na_v4(d, make_uint4(quant4(f[0], f[1], f[2], f[3], inv), quant4(f[4], f[5], f[6], f[7], inv),
+                                   quant4(f[8], f[9], f[10], f[11], inv), quant4(f[12], f[13], f[14], f[15], inv)));
+            st_na_v4(d + 16, make_uint4(quant4(f[16], f[17], f[18], f[19], inv), quant4(f[20], f[21], f[22], f[23], inv),
+                                        quant4(f[24], f[25], f[26], f[27], inv), quant4(f[28], f[29], f[30], f[31], inv)));
+            // gather 4 neighbouring lanes' scale bytes into one 32-bit peer store (the whole warp is in this iteration:
+            // ranges are multiples of 32*32 elements per warp only when aligned, so guard with the active mask)
+            const unsigned act = __activemask();
+            const uint32_t sb = (uint32_t)(e + 127);
+            const int base = (lane & ~3);
+            uint32_t w = __shfl_sync(act, sb, base) | (__shfl_sync(act, sb, base + 1) << 8) |
+                         (__shfl_sync(act, sb, base + 2) << 16) | (__shfl_sync(act, sb, base + 3) << 24);
+            if ((lane & 3) == 0) *reinterpret_cast<volatile uint32_t*>(a.dst_scale + i / 32) = w;
+        }
+    }
+    // publish: every CTA fences its peer stores; the last CTA to arrive releases the flag with this worker's step id
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const int old = atomicAdd(a.counter, 1);
+        if (old == (int)gridDim.x - 1) {
+            *a.counter = 0;
+            __threadfence_system();
+            st_release_sys(a.flag, *a.step_ptr);
+        }
+    }
+}
+
+// ================================================================================================================
+struct RUArgs {
+    const void* src[kMaxPeers];           // gradient sources, element-indexed (slots in push mode, peer arenas in pull mode)
+    const uint8_t* src_scale[kMaxPeers];
+    int P, take, mode;                    // P sources; sum the first `take` arrivals
+    float inv_div;                        // 1 / divisor
+    const long long* g_ready;             // [P][kMaxBuckets] arrival flags (local memory)
+    long long* step_ptr;                  // PS step counter (device)
+    int NB;
+    long long lo[kMaxBuckets], hi[kMaxBuckets];
+    float *w, *s0, *s1, *s2;              // fp32 master; SGD: s0 = momentum buf; Adam: s0 = m, s1 = v, s2 = vmax|null
+    OptHP* hp;
+    void* dst[kMaxPeers + 1];             // bf16 weight replicas (element-indexed); D of them
+    int D;
+    void* mc_dst;                         // NVLS multicast mapping of the replicas (or null)
+    long long* w_ready[kMaxPeers + 1];    // per destination: [kMaxBuckets] "weights ready" flags
+    int* counters;                        // [kMaxBuckets]
+    long long* err;
+    unsigned long long timeout_ns;
+    int advance_step;                     // last CTA bumps *step_ptr and hp->steps
+};
+
+__device__ __forceinline__ void load_src8(const RUArgs& a, int k, long long i, float* f) {
+    if (a.mode == WIRE_BF16) {
+        unpack8(ld_relaxed_sys_v4(reinterpret_cast<const __nv_bfloat16*>(a.src[k]) + i), f);
+    } else if (a.mode == WIRE_FP32) {
+        const float* s = reinterpret_cast<const float*>(a.src[k]) + i;
+        uint4 x = ld_relaxed_sys_v4(s), y = ld_relaxed_sys_v4(s + 4);
+        f[0] = __uint_as_float(x.x); f[1] = __uint_as_float(x.y); f[2] = __uint_as_float(x.z); f[3] = __uint_as_float(x.w);
+        f[4] = __uint_as_float(y.x); f[5] = __uint_as_float(y.y); f[6] = __uint_as_float(y.z); f[7] = __uint_as_float(y.w);
+    } else {
+        const uint8_t* q = reinterpret_cast<const uint8_t*>(a.src[k]) + i;
+        uint2 v;
+        asm volatile("ld.relaxed.sys.global.v2.u32 {%0,%1}, [%2];" : "=r"(v.x), "=r"(v.y) : "l"(q) : "memory");
+        uint32_t sb;
+        asm volatile("ld.relaxed.sys.global.u8 %0, [%1];" : "=r"(sb) : "l"(a.src_scale[k] + i / 32) : "memory");
+        const float sc = exp2i(max(-126, (int)sb - 127));
+        dequant4(v.x, sc, f);
+        dequant4(v.y, sc, f + 4);
+    }
+}
+
+__global__ void __launch_bounds__(256) reduce_update_kernel(RUArgs a) {
+    __shared__ unsigned s_mask;
+    const long long step = *a.step_ptr;
+    const OptHP hp = *a.hp;
+    const bool first = hp.steps == 0;
+    const float adam_ss = hp.kind == 1 ? adam_step_size(hp, hp.steps + 1) : 0.f;
+    const long long stride = (long long)gridDim.x * blockDim.x * 8;
+
+    for (int b = a.NB - 1; b >= 0; --b) {          // gradients arrive last-layer-first
+        if (threadIdx.x == 0) {
+            unsigned mask = 0;
+            const unsigned long long t0 = globaltimer_ns();
+            while (true) {
+                mask = 0;
+                int cnt = 0;
+                for (int k = 0; k < a.P && cnt < a.take; ++k)
+                    if (ld_acquire_sys(a.g_ready + k * kMaxBuckets + b) == step) { mask |= 1u << k; ++cnt; }
+                if (cnt >= a.take) break;
+                if (globaltimer_ns() - t0 > a.timeout_ns) { mask = 0; atomicExch((unsigned long long*)a.err, 1ull + (unsigned long long)b); break; }
+                __nanosleep(200);
+            }
+            s_mask = mask;
+        }
+        __syncthreads();
+        const unsigned mask = s_mask;
+        if (mask == 0) return;                     // timed out: error word is set, host raises
+        for (long long i = a.lo[b] + ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 8; i < a.hi[b]; i += stride) {
+            float g[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+#pragma unroll 1
+            for (int k = 0; k < a.P; ++k) {
+                if (!(mask >> k & 1)) continue;
+                float f[8];
+                load_src8(a, k, i, f);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) g[j] += f[j];
+            }
+            float wf[8], x0[8], x1[8], x2[8];
+            {
+                uint4 p = ld_v4(a.w + i), q = ld_v4(a.w + i + 4);
+                wf[0] = __uint_as_float(p.x); wf[1] = __uint_as_float(p.y); wf[2] = __uint_as_float(p.z); wf[3] = __uint_as_float(p.w);
+                wf[4] = __uint_as_float(q.x); wf[5] = __uint_as_float(q.y); wf[6] = __uint_as_float(q.z); wf[7] = __uint_as_float(q.w);
+            }
+            auto ldf = [&](const float* ptr, float* o) {
+                uint4 p = ld_v4(ptr + i), q = ld_v4(ptr + i + 4);
+                o[0] = __uint_as_float(p.x); o[1] = __uint_as_float(p.y); o[2] = __uint_as_float(p.z); o[3] = __uint_as_float(p.w);
+                o[4] = __uint_as_float(q.x); o[5] = __uint_as_float(q.y); o[6] = __uint_as_float(q.z); o[7] = __uint_as_float(q.w);
+            };
+            auto stf = [&](float* ptr, const float* o) {
+                st_v4(ptr + i, make_uint4(__float_as_uint(o[0]), __float_as_uint(o[1]), __float_as_uint(o[2]), __float_as_uint(o[3])));
+                st_v4(ptr + i + 4, make_uint4(__float_as_uint(o[4]), __float_as_uint(o[5]), __float_as_uint(o[6]), __float_as_uint(o[7])));
+            };
+            if (hp.kind == 0) {
+                if (hp.momentum != 0.f && !first) ldf(a.s0, x0);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) wf[j] = sgd_update(wf[j], g[j] * a.inv_div, x0[j], hp, first);
+                if (hp.momentum != 0.f) stf(a.s0, x0);
+            } else {
+                ldf(a.s0, x0); ldf(a.s1, x1);
+                if (a.s2) ldf(a.s2, x2);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) wf[j] = adam_update(wf[j], g[j] * a.inv_div, x0[j], x1[j], a.s2 ? &x2[j] : nullptr, hp, adam_ss);
+                stf(a.s0, x0); stf(a.s1, x1);
+                if (a.s2) stf(a.s2, x2);
+            }
+            stf(a.w, wf);
+            // broadcast the fresh compute copy: one multicast store through the switch, or D peer stores
+            const uint4 lp = pack8(wf);
+            if (a.mc_dst) {
+                multimem_st_v4(reinterpret_cast<__nv_bfloat16*>(a.mc_dst) + i, lp);
+            } else {
+#pragma unroll 1
+                for (int d = 0; d < a.D; ++d) st_na_v4(reinterpret_cast<__nv_bfloat16*>(a.dst[d]) + i, lp);
+            }
+        }
+        __threadfence_system();
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            const int old = atomicAdd(a.counters + b, 1);
+            if (old == (int)gridDim.x - 1) {
+                a.counters[b] = 0;
+                __threadfence_system();
+                for (int d = 0; d < a.D; ++d) st_release_sys(a.w_ready[d] + b, step + 1);
+                if (b == 0 && a.advance_step) { a.hp->steps = hp.steps + 1; *a.step_ptr = step + 1; }
+            }
+        }
+        __syncthreads();
+    }
+}
+
+// Initial publish / re-publish of the bf16 replica (step 1, resume) and the worker-pull path (--comm-type Async):
+// copy `src` (local or peer) to D destinations, then release their flags with value `*step_ptr + step_add`.
+struct BcastArgs {
+    const void* src; void* dst[kMaxPeers + 1]; int D; void* mc_dst;
+    long long n_vec;            // 16-byte vectors
+    long long* flags[kMaxPeers + 1]; int nflags;      // per destination: set flags[0..nflags)
+    const long long* step_ptr; long long step_add; int* counter;
+};
+__global__ void __launch_bounds__(256) bcast_kernel(BcastArgs a) {
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < a.n_vec; i += stride) {
+        const uint4 v = ld_relaxed_sys_v4(reinterpret_cast<const uint4*>(a.src) + i);
+        if (a.mc_dst) multimem_st_v4(reinterpret_cast<uint4*>(a.mc_dst) + i, v);
+        else for (int d = 0; d < a.D; ++d) st_na_v4(reinterpret_cast<uint4*>(a.dst[d]) + i, v);
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const int old = atomicAdd(a.counter, 1);
+        if (old == (int)gridDim.x - 1) {
+            *a.counter = 0;
+            __threadfence_system();
+            const long long v = *a.step_ptr + a.step_add;
+            for (int d = 0; d < a.D; ++d)
+                for (int f = 0; f < a.nflags; ++f) st_release_sys(a.flags[d] + f, v);
+        }
+    }
+}
+
+// acquire-spin until flags[0..n) >= *step_ptr (weights for this worker's step have landed), with timeout
+__global__ void wait_flag_kernel(const long long* flags, int n, const long long* step_ptr, long long* err, unsigned long long timeout_ns) {
+    if (threadIdx.x >= n) return;
+    const long long want = *step_ptr;
+    const unsigned long long t0 = globaltimer_ns();
+    while (ld_acquire_sys(flags + threadIdx.x) < want) {
+        if (globaltimer_ns() - t0 > timeout_ns) { atomicExch((unsigned long long*)err, 100ull + threadIdx.x); return; }
+        __nanosleep(100);
+    }
+}
+
+__global__ void add_step_kernel(long long* p, long long v) { *p += v; }
+__global__ void set_word_kernel(long long* p, long long v) { __threadfence_system(); st_release_sys(p, v); }
+
+// ---- host wrappers (raw pointers as int64: they may be peer mappings that no torch tensor owns) ---------------------
+static inline void* P(int64_t x) { return reinterpret_cast<void*>(x); }
+
+static int grid_for(long long elems, int per_thread) {
+    long long blocks = (elems / per_thread + 255) / 256;
+    return (int)std::max<long long>(1, std::min<long long>(blocks, (long long)kNumSMs * 4));
+}
+
+void push(int64_t src, bool src_fp32, int64_t dst, int64_t dst_scale, int64_t lo, int64_t hi, int64_t flag, int64_t step_ptr,
+          int64_t counter, int64_t mode, bool zero_src) {
+    TORCH_CHECK(lo % 128 == 0 && hi % 128 == 0 && hi > lo, "push range must be 128-element aligned");
+    PushArgs a{P(src), P(dst), (uint8_t*)P(dst_scale), lo, hi, (long long*)P(flag), (const long long*)P(step_ptr), (int*)P(counter),
+               (int)mode, src_fp32 ? 1 : 0, zero_src ? 1 : 0};
+    push_kernel<<<grid_for(hi - lo, 32), 256, 0, at::cuda::getCurrentCUDAStream()>>>(a);
+    C10_CUDA_KERNEL_LAUNCH_CHECK();
+}
+
+void reduce_update(std::vector<int64_t> src, std::vector<int64_t> src_scale, int64_t take, double inv_div, int64_t mode,
+                   int64_t g_ready, int64_t step_ptr, std::vector<int64_t> lo, std::vector<int64_t> hi, at::Tensor w,
+                   c10::optional<at::Tensor> s0, c10::optional<at::Tensor> s1, c10::optional<at::Tensor> s2, int64_t hp,
+                   std::vector<int64_t> dst, int64_t mc_dst, std::vector<int64_t> w_ready, int64_t counters, int64_t err,
+                   double timeout_s, bool advance_step) {
+    RUArgs a{};
+    TORCH_CHECK(src.size() <= kMaxPeers && dst.size() <= kMaxPeers + 1 && lo.size() <= kMaxBuckets && lo.size() == hi.size());
+    a.P = (int)src.size(); a.take = (int)take; a.mode = (int)mode; a.inv_div = (float)inv_div;
+    for (size_t k = 0; k < src.size(); ++k) { a.src[k] = P(src[k]); a.src_scale[k] = (const uint8_t*)P(k < src_scale.size() ? src_scale[k] : 0); }
+    a.g_ready = (const long long*)P(g_ready); a.step_ptr = (long long*)P(step_ptr);
+    a.NB = (int)lo.size();
+    for (size_t b = 0; b < lo.size(); ++b) { TORCH_CHECK(lo[b] % 32 == 0 && hi[b] % 32 == 0); a.lo[b] = lo[b]; a.hi[b] = hi[b]; }
+    TORCH_CHECK(w.scalar_type() == at::kFloat && w.is_cuda());
+    a.w = w.data_ptr<float>();
+    a.s0 = s0.has_value() ? s0->data_ptr<float>() : nullptr;
+    a.s1 = s1.has_value() ? s1->data_ptr<float>() : nullptr;
+    a.s2 = s2.has_value() ? s2->data_ptr<float>() : nullptr;
+    a.hp = (OptHP*)P(hp);
+    a.D = (int)dst.size();
+    for (size_t d = 0; d < dst.size(); ++d) { a.dst[d] = P(dst[d]); a.w_ready[d] = (long long*)P(w_ready[d]); }
+    a.mc_dst = P(mc_dst);
+    a.counters = (int*)P(counters); a.err = (long long*)P(err);
+    a.timeout_ns = (unsigned long long)(timeout_s * 1e9);
+    a.advance_step = advance_step;
+    long long tot = 0;
+    for (size_t b = 0; b < lo.size(); ++b) tot = std::max<long long>(tot, hi[b] - lo[b]);
+    reduce_update_kernel<<<grid_for(tot, 8), 256, 0, at::cuda::getCurrentCUDAStream()>>>(a);
+    C10_CUDA_KERNEL_LAUNCH_CHECK();
+}
+
+void bcast(int64_t src, std::vector<int64_t> dst, int64_t mc_dst, int64_t nbytes, std::vector<int64_t> flags, int64_t nflags,
+           int64_t step_ptr, int64_t step_add, int64_t counter) {
+    BcastArgs a{};
+    TORCH_CHECK(nbytes % 16 == 0 && dst.size() <= kMaxPeers + 1 && flags.size() == dst.size());
+    a.src = P(src); a.D = (int)dst.size(); a.mc_dst = P(mc_dst); a.n_vec = nbytes / 16;
+    for (size_t d = 0; d < dst.size(); ++d) { a.dst[d] = P(dst[d]); a.flags[d] = (long long*)P(flags[d]); }
+    a.nflags = (int)nflags; a.step_ptr = (const long long*)P(step_ptr); a.step_add = step_add; a.counter = (int*)P(counter);
+    bcast_kernel<<<grid_for(a.n_vec, 1), 256, 0, at::cuda::getCurrentCUDAStream()>>>(a);
+    C10_CUDA_KERNEL_LAUNCH_CHECK();
+}
+
+void wait_flag(int64_t flags, int64_t n, int64_t step_ptr, int64_t err, double timeout_s) {
+    TORCH_CHECK(n >= 1 && n <= kMaxBuckets);
+    wait_flag_kernel<<<1, 32, 0, at::cuda::getCurrentCUDAStream()>>>((const long long*)P(flags), (int)n, (const long long*)P(step_ptr),
+                                                                      (long long*)P(err), (unsigned long long)(timeout_s * 1e9));
+    C10_CUDA_KERNEL_LAUNCH_CHECK();
+}
+
+void add_step(int64_t p, int64_t v) {
+    add_step_kernel<<<1, 1, 0, at::cuda::getCurrentCUDAStream()>>>((long long*)P(p), v);
+    C10_CUDA_KERNEL_LAUNCH_CHECK();
+}
+void set_word(int64_t p, int64_t v) {
+    set_word_kernel<<<1, 1, 0, at::cuda::getCurrentCUDAStream()>>>((long long*)P(p), v);
+    C10_CUDA_KERNEL_LAUNCH_CHECK();
+}
+
+// OptHP blob <-> host
+at::Tensor make_hp(double lr, double momentum, double dampening, double wd, bool nesterov, double beta1, double beta2, double eps,
+                   bool amsgrad, int64_t kind, int64_t steps) {
+    OptHP h{};
+    h.lr = (float)lr; h.momentum = (float)momentum; h.dampening = (float)dampening; h.weight_decay = (float)wd;
+    h.beta1 = (float)beta1; h.beta2 = (float)beta2; h.eps = (float)eps; h.nesterov = nesterov; h.amsgrad = amsgrad;
+    h.kind = (int)kind; h.steps = steps;
+    auto t = at::empty({(long long)sizeof(OptHP)}, at::TensorOptions().dtype(at::kByte));
+    memcpy(t.data_ptr(), &h, sizeof(OptHP));
+    return t;
+}
+int64_t hp_steps(at::Tensor host_blob) {
+    OptHP h;
+    memcpy(&h, host_blob.data_ptr(), sizeof(OptHP));
+    return h.steps;
+}
+
+}  // namespace psb

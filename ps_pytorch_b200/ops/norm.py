@@ -1,0 +1,55 @@
+"""BatchNorm2d (+residual, +ReLU) autograd wrapper over ``csrc/bn_kernels.cu``."""
+from __future__ import annotations
+
+import torch
+
+from . import count_launch, require
+
+
+def bn_unsupported_reason(x: torch.Tensor):
+    if x.dtype != torch.bfloat16:
+        return "activations are not bf16"
+    if x.dim() != 4:
+        return "not a 4-D activation"
+    c = x.size(1)
+    lc = c // 8
+    if c % 8 or lc > 256 or (lc & (lc - 1)):
+        return "C/8 is not a power of two <= 256 (C=%d)" % c
+    return None
+
+
+class _BatchNormFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, weight, bias, residual, running_mean, running_var, training, momentum, eps, relu):
+        ext = require()
+        x = x.contiguous(memory_format=torch.channels_last)
+        if residual is not None:
+            residual = residual.contiguous(memory_format=torch.channels_last)
+        z, mean, invstd = ext.bn_forward(x, weight, bias, running_mean if training else running_mean,
+                                         running_var, residual, training, momentum, eps, relu)
+        count_launch(3 if training else 2)
+        ctx.relu, ctx.has_res, ctx.training = relu, residual is not None, training
+        ctx.save_for_backward(x, z if relu else None, weight, mean, invstd)
+        return z
+
+    @staticmethod
+    def backward(ctx, dz):
+        x, z, weight, mean, invstd = ctx.saved_tensors
+        if not ctx.training:
+            raise RuntimeError("bn backward in eval mode is not supported by the sm100 kernels")
+        ext = require()
+        dz = dz.contiguous(memory_format=torch.channels_last)
+        dx, dres, dgamma, dbeta = ext.bn_backward(dz, z if z is not None else x, x, weight, mean, invstd, ctx.relu, ctx.has_res)
+        count_launch(3)
+        if weight is None:
+            dgamma = dbeta = None
+        return dx, dgamma, dbeta, (dres if ctx.has_res else None), None, None, None, None, None, None
+
+
+def batch_norm(x, module, residual=None, relu=False):
+    training = module.training or not module.track_running_stats
+    if training and module.track_running_stats and module.num_batches_tracked is not None:
+        module.num_batches_tracked.add_(1)
+    mom = 0.1 if module.momentum is None else module.momentum
+    return _BatchNormFn.apply(x, module.weight, module.bias, residual, module.running_mean, module.running_var,
+                              training, mom, module.eps, relu)

@@ -113,11 +113,13 @@ class FlatBuffer:
             for v, p in zip(self.views, module.parameters()):
                 p.copy_(v)
 
-    def bind_params(self, module: nn.Module) -> None:
-        """Make the module's parameters views of this arena (values are preserved)."""
+    def bind_params(self, module: nn.Module, keep_arena_values: bool = False) -> None:
+        """Make the module's parameters views of this arena.  By default the module's values move into the arena;
+        with ``keep_arena_values`` the arena content wins (a replica the PS has written or will write)."""
         with torch.no_grad():
             for v, p in zip(self.views, module.parameters()):
-                v.copy_(p.detach())
+                if not keep_arena_values:
+                    v.copy_(p.detach())
                 p.data = v
 
     def bind_grads(self, module: nn.Module) -> None:

@@ -12,6 +12,7 @@ import torch.nn as tnn
 
 from .arena import FlatBuffer, ParamLayout
 from .. import nn as pnn
+from .. import ops as _ops
 from ..models.layerwise import LayerwiseBackwardMixin, StragglerKilled
 from ..utils.obs import PhaseTimer
 
@@ -25,7 +26,8 @@ def resolve_dtype(name: str, device) -> torch.dtype:
 class WorkerCompute:
     def __init__(self, network: tnn.Module, device, dtype: torch.dtype, layout: Optional[ParamLayout] = None,
                  weight_storage: Optional[torch.Tensor] = None, grad_dtype: Optional[torch.dtype] = None,
-                 channels_last: Optional[bool] = None, use_graph: bool = False):
+                 channels_last: Optional[bool] = None, use_graph: bool = False, grad_storage: Optional[torch.Tensor] = None,
+                 zero_grads_in_step: bool = True):
         self.device = torch.device(device)
         self.dtype = dtype
         self.channels_last = (self.device.type == "cuda") if channels_last is None else channels_last
@@ -34,8 +36,9 @@ class WorkerCompute:
             self.network = self.network.to(memory_format=torch.channels_last)
         self.layout = layout or ParamLayout.from_module(self.network, channels_last=self.channels_last)
         self.weights = FlatBuffer(self.layout, dtype, self.device, storage=weight_storage)
-        self.weights.bind_params(self.network)
-        self.grads = FlatBuffer(self.layout, grad_dtype or dtype, self.device)
+        self.weights.bind_params(self.network, keep_arena_values=weight_storage is not None)
+        self.grads = FlatBuffer(self.layout, grad_dtype or dtype, self.device, storage=grad_storage)
+        self.zero_grads_in_step = zero_grads_in_step
         self.grads.bind_grads(self.network)
         self.criterion = pnn.CrossEntropyLoss()
         self.timer = PhaseTimer(self.device)
@@ -85,7 +88,8 @@ class WorkerCompute:
 
     # ---- one step ----------------------------------------------------------------------------------------
     def _step_body(self, x, y):
-        self.grads.flat.zero_()
+        if self.zero_grads_in_step:
+            self.grads.flat.zero_()
         self._arm_buckets()
         with self.timer.phase("forward"):
             logits = self.network(x)
@@ -132,9 +136,10 @@ class WorkerCompute:
             return self._step_body(x, y)
         if self._graph is None:
             self._capture(x, y)
-        self._static_x.copy_(x, non_blocking=True)
+        self._static_x.copy_(x, non_blocking=True)       # H2D from the loader's pinned buffer (dtype cast on the fly)
         self._static_y.copy_(y, non_blocking=True)
         self._graph.replay()
+        _ops.count_launch(self.graph_launches)
         return self._static_loss, self._static_logits
 
     def _capture(self, x, y):
@@ -150,8 +155,10 @@ class WorkerCompute:
         self.timer.resolve()
         self._graph = torch.cuda.CUDAGraph()
         self.timer = _NullTimer()
+        n0 = _ops.launch_count
         with torch.cuda.graph(self._graph):
             self._static_loss, self._static_logits = self._step_body(self._static_x, self._static_y)
+        self.graph_launches = _ops.launch_count - n0      # our kernels recorded in the graph, re-counted per replay
 
     @torch.no_grad()
     def evaluate(self, loader, max_batches: int = 0):

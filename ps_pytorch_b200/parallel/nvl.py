@@ -1,0 +1,298 @@
+"""NVLink tier of the parameter server: gradient push, PS reduce+update and weight broadcast are fused kernels over
+peer-mapped memory (``ops/csrc/comm_kernels.cu``); ``torch.distributed`` is only the bootstrap.
+
+Two topologies share the same kernels:
+
+``ps``       the reference topology (rank 0 = parameter server).  Workers *push*: cast/quantise + peer-store into their
+             slot on the PS + release flag.  The PS kernel polls flags (first K of P), reduces the K slots from its own
+             HBM, applies the optimizer to the fp32 master and stores the bf16 weights into every worker replica
+             (one NVLS multicast store when available) + releases their "weights ready" flags.
+``sharded``  every rank is a worker *and* the server of 1/W of the arena (the role the vendored DDP all-reduce plays in the
+             reference, ``/root/reference/src/data_parallel_dist/data_parallel_dist.py:252-261``, without the single-PS
+             incast): after backward a rank only raises its "gradients ready" flag on every peer; each owner *pulls* its
+             shard from all peers' gradient arenas with P2P loads, updates, and stores the new weights to all replicas.
+             Reduce-scatter + optimizer + all-gather in one kernel per rank.
+
+All step counters are device-resident, so the whole worker step and the whole PS step are graph-capturable and the host
+never blocks on a peer; every device-side wait has a timeout that sets ``err`` instead of hanging the GPU.
+"""
+from __future__ import annotations
+
+import os
+import time
+from typing import List, Optional
+
+import torch
+import torch.distributed as dist
+
+from .arena import FlatBuffer, ParamLayout
+from .symm import SymmetricArena
+from .transport import Transport
+from .. import ops
+
+WIRE = {"bf16": 0, "fp8": 1, "fp32": 2}
+MAXB = 16          # kMaxBuckets in comm_kernels.cu
+MAXP = 8
+
+
+def _align(x, a=4096):
+    return (x + a - 1) // a * a
+
+
+class NvlTransport(Transport):
+    name = "nvl"
+    fused_lowp = True            # the reduce-update kernel writes the low-precision replicas itself
+
+    def __init__(self, layout: ParamLayout, device, grad_dtype: str = "bf16", colocate: bool = False, num_buckets: int = 1,
+                 topology: str = "ps", n_buffers: int = 0, timeout_s: float = None, weight_dtype: torch.dtype = torch.bfloat16):
+        rank = dist.get_rank() if dist.is_initialized() else 0
+        world = dist.get_world_size() if dist.is_initialized() else 1
+        if world == 1:
+            colocate = True
+        if topology == "sharded":
+            colocate = True
+        super().__init__(rank, world, layout, colocate)
+        assert world <= MAXP, "one NVSwitch box: at most 8 ranks"
+        assert weight_dtype == torch.bfloat16, "NVLink tier broadcasts bf16 replicas"
+        self.device = torch.device(device)
+        self.topology = topology
+        self.wire = WIRE[grad_dtype]
+        self.grad_dtype = grad_dtype
+        self.timeout_s = float(os.environ.get("PSB200_TIMEOUT_S", timeout_s or 30.0))
+        self.ext = ops.require()
+        T = layout.total
+        self.T = T
+        P = self.num_workers
+        if topology == "ps":
+            self.buckets = [(lo, hi) for lo, hi, _ in layout.buckets(min(num_buckets, MAXB))]
+            self.bucket_params = [idx for _, _, idx in layout.buckets(min(num_buckets, MAXB))]
+        else:
+            # shard boundaries on 128-element multiples; rank r owns [cuts[r], cuts[r+1])
+            per = (T // world) // 128 * 128
+            cuts = [r * per for r in range(world)] + [T]
+            self.shards = [(cuts[r], cuts[r + 1]) for r in range(world)]
+            self.buckets = [(0, T)]
+            self.bucket_params = [list(range(len(layout.numels)))]
+        self.NB = len(self.buckets)
+        # ---- arena layout (identical on every rank) --------------------------------------------------------
+        self.off_w = 0
+        self.off_flags = _align(T * 2)
+        self.off_grads = self.off_flags + 4096
+        gbytes = T * 4                                   # room for an fp32 gradient arena
+        self.off_slots = _align(self.off_grads + gbytes)
+        self.slot_q_bytes = {0: T * 2, 1: T, 2: T * 4}[self.wire]
+        self.slot_s_bytes = _align(T // 32, 256) if self.wire == 1 else 0
+        self.slot_stride = _align(self.slot_q_bytes + self.slot_s_bytes, 256)
+        nslots = P if topology == "ps" else 0
+        self.off_bufs = _align(self.off_slots + nslots * self.slot_stride)
+        self.n_buffers = n_buffers
+        total = self.off_bufs + _align(max(n_buffers, 1) * 4 + 64)
+        self.arena = SymmetricArena(total, self.device, tag="ps")
+        A = self.arena
+        # flag words (int64) inside the flags page
+        self.F_WREADY, self.F_GREADY, self.F_ABORT, self.F_BUFS = 0, MAXB * 8, MAXB * 8 + MAXP * MAXB * 8, MAXB * 8 + MAXP * MAXB * 8 + 8
+        self.flags_local = A.view(self.off_flags, 4096, torch.int64)
+        # ---- device-side control block ------------------------------------------------------------------------
+        self.ctl = torch.zeros(64, dtype=torch.int64, device=self.device)     # [0]=worker step, [1]=ps step, [2]=err, [8..]=counters (int32 pairs)
+        self.ctl[0] = 1
+        self.ctl[1] = 1
+        self.p_wstep = self.ctl.data_ptr()
+        self.p_psstep = self.ctl.data_ptr() + 8
+        self.p_err = self.ctl.data_ptr() + 16
+        self.p_counters = self.ctl.data_ptr() + 64           # int32 counters: [0..MAXB) reduce, [MAXB..2MAXB) push, [2MAXB] bcast
+        self._host_wstep = 0
+        self._host_psstep = 0
+        self._published = 0
+        self._hp_dev = None
+        self._hp_key = None
+        self._side = torch.cuda.Stream(device=self.device)
+        self._pushed = [False] * self.NB
+        self.zeroes_grads = topology == "ps"
+        torch.cuda.synchronize(self.device)
+
+    # ---- storage handed to the roles -------------------------------------------------------------------------------
+    def worker_weight_storage(self, dtype):
+        assert dtype == torch.bfloat16, "NVLink tier: worker replicas are bf16 (use --dtype bf16)"
+        return self.arena.view(self.off_w, self.T * 2, torch.bfloat16)
+
+    ps_weight_storage = lambda self: self.arena.view(self.off_w, self.T * 2, torch.bfloat16)   # noqa: E731
+
+    def worker_grad_storage(self, dtype):
+        nb = self.T * (2 if dtype == torch.bfloat16 else 4)
+        return self.arena.view(self.off_grads, nb, dtype)
+
+    def _wptr(self, rank):
+        return self.arena.peer_ptrs[rank] + self.off_w
+
+    def _flag(self, rank, word_off):
+        return self.arena.peer_ptrs[rank] + self.off_flags + word_off
+
+    # ---- PS side ---------------------------------------------------------------------------------------------------------
+    def _dests(self):
+        return list(self.worker_ranks)
+
+    def ps_publish(self, step, weights):
+        """Step 1 / resume: copy the PS's bf16 weights (already in its W region) to every replica and release the
+        ready flags.  Later steps are published by the reduce-update kernel itself."""
+        if self._published >= step:
+            return
+        if self.topology == "sharded" and self.rank != 0:
+            self._published = step         # rank 0 seeds every replica (identical init everywhere)
+            return
+        assert weights.flat.data_ptr() == self.arena.local_ptr + self.off_w, "PS low-precision copy must live in the arena"
+        d = self._dests()
+        use_mc = self.arena.mc_ptr and len(d) == self.world
+        nfl = self.NB if self.topology == "ps" else self.world
+        self.ext.bcast(self.arena.local_ptr + self.off_w, [self._wptr(r) for r in d], (self.arena.mc_ptr + self.off_w) if use_mc else 0,
+                       self.T * 2, [self._flag(r, self.F_WREADY) for r in d], nfl, self.p_psstep, 0, self.p_counters + 4 * 2 * MAXB)
+        ops.count_launch()
+        self._published = step
+        self.stats["bcast_bytes"] += self.T * 2
+
+    def _hp(self, optimizer):
+        g = optimizer.param_groups[0]
+        fs = optimizer.flat_state()
+        kind = 1 if "betas" in g else 0
+        key = (kind, g['lr'], g.get('momentum', 0), g.get('dampening', 0), g['weight_decay'], g.get('nesterov', False),
+               g.get('betas', (0, 0)), g.get('eps', 0), g.get('amsgrad', False))
+        if self._hp_dev is None or key != self._hp_key:
+            steps = fs["steps"]
+            blob = self.ext.make_hp(g['lr'], g.get('momentum', 0.0), g.get('dampening', 0.0), g['weight_decay'], bool(g.get('nesterov', False)),
+                                    g.get('betas', (0.9, 0.999))[0], g.get('betas', (0.9, 0.999))[1], g.get('eps', 1e-8), bool(g.get('amsgrad', False)), kind, steps)
+            if self._hp_dev is None:
+                self._hp_dev = blob.to(self.device)
+            else:
+                torch.cuda.current_stream().synchronize()
+                self._hp_dev.copy_(blob)
+            self._hp_key = key
+        return self._hp_dev.data_ptr(), kind, fs
+
+    def ps_reduce_update(self, step, k, optimizer, master, strict_reference=False, kill_stragglers=False, timeout_s=0.0, lowp=None):
+        hp_ptr, kind, fs = self._hp(optimizer)
+        P = self.num_workers
+        if self.topology == "ps":
+            src = [self.arena.local_ptr + self.off_slots + s * self.slot_stride for s in range(P)]
+            scl = [p + self.slot_q_bytes for p in src] if self.wire == 1 else []
+            lo = [b[0] for b in self.buckets]
+            hi = [b[1] for b in self.buckets]
+            wready = [self._flag(r, self.F_WREADY) for r in self._dests()]
+            mode = self.wire
+        else:
+            gdt = 2 if self._grad_is_fp32 else 0
+            src = [self.arena.peer_ptrs[r] + self.off_grads for r in self.worker_ranks]
+            scl, mode = [], gdt
+            lo, hi = [self.shards[self.rank][0]], [self.shards[self.rank][1]]
+            wready = [self._flag(r, self.F_WREADY + 8 * self.rank) for r in self._dests()]
+        take = min(P, (k + 1) if strict_reference else k)
+        d = self._dests()
+        use_mc = bool(self.arena.mc_ptr) and len(d) == self.world
+        if kind == 0:
+            s0, s1, s2 = fs["buf"], None, None
+        else:
+            s0, s1, s2 = fs["m"], fs["v"], fs["vmax"]
+        self.ext.reduce_update(src, scl, int(take), 1.0 / float(k), int(mode), self.arena.local_ptr + self.off_flags + self.F_GREADY,
+                               self.p_psstep, lo, hi, master.flat, s0, s1, s2, hp_ptr, [self._wptr(r) for r in d],
+                               (self.arena.mc_ptr + self.off_w) if use_mc else 0, wready, self.p_counters, self.p_err,
+                               float(timeout_s or self.timeout_s), True)
+        ops.count_launch()
+        fs["steps"] += 1
+        self._host_psstep += 1
+        self._published = step + 1
+        self.stats["bcast_bytes"] += self.T * 2
+
+    def ps_signal_kill(self, ranks, step):
+        for r in ranks:
+            self.ext.set_word(self._flag(r, self.F_ABORT), int(step))
+
+    def ps_recv_buffers(self, step, numel):
+        if numel == 0:
+            return None
+        t0 = time.time()
+        while self._read_word(self.F_BUFS) < step:
+            if time.time() - t0 > self.timeout_s:
+                raise TimeoutError("BN statistics for step %d never arrived" % step)
+            time.sleep(0.0005)
+        return self.arena.view(self.off_bufs + 64, numel * 4, torch.float32).clone()
+
+    # ---- worker side -----------------------------------------------------------------------------------------------------
+    def worker_fetch(self, weights, timeout_s=0.0):
+        """Enqueue the device-side wait for this step's weights; the host does not block."""
+        n = self.NB if self.topology == "ps" else self.world
+        self.ext.wait_flag(self.arena.local_ptr + self.off_flags + self.F_WREADY, n, self.p_wstep, self.p_err, self.timeout_s)
+        ops.count_launch()
+        self._host_wstep += 1
+        self._pushed = [False] * self.NB
+        return self._host_wstep
+
+    def _my_slot(self):
+        return self.worker_slot(self.rank)
+
+    def worker_push_bucket(self, b: int, grads: FlatBuffer):
+        lo, hi = self.buckets[b]
+        slot = self._my_slot()
+        fp32 = grads.dtype == torch.float32
+        if self.topology == "ps":
+            base = self.arena.peer_ptrs[0] + self.off_slots + slot * self.slot_stride
+            self.ext.push(grads.flat.data_ptr(), fp32, base, base + self.slot_q_bytes, lo, hi,
+                          self._flag(0, self.F_GREADY + 8 * (slot * MAXB + b)), self.p_wstep, self.p_counters + 4 * (MAXB + b), self.wire, True)
+            ops.count_launch()
+            wbytes = {0: 2, 1: 1.03125, 2: 4}[self.wire]
+            self.stats["push_bytes"] += int((hi - lo) * wbytes)
+        else:
+            self._grad_is_fp32 = fp32
+            assert grads.flat.data_ptr() == self.arena.local_ptr + self.off_grads, "sharded topology: gradients must live in the arena"
+            self._raise_ready(slot)      # pull mode: no data moves here, only "gradients ready" on every shard owner
+        self._pushed[b] = True
+
+    def _raise_ready(self, slot):
+        # one tiny kernel per peer would be W launches; bcast_kernel with zero payload releases all flags in one launch
+        d = self.worker_ranks
+        self.ext.bcast(self.arena.local_ptr + self.off_grads, [self.arena.peer_ptrs[r] + self.off_grads for r in d], 0, 0,
+                       [self._flag(r, self.F_GREADY + 8 * (slot * MAXB)) for r in d], 1, self.p_wstep, 0, self.p_counters + 4 * (2 * MAXB + 1))
+        ops.count_launch()
+        self.stats["push_bytes"] += 0
+
+    def worker_push(self, step, grads, lo=0, hi=None, last=True):
+        if hi is not None and not last:
+            for b, (blo, bhi) in enumerate(self.buckets):
+                if blo >= lo and bhi <= hi and not self._pushed[b]:
+                    self.worker_push_bucket(b, grads)
+            return
+        for b in range(self.NB - 1, -1, -1):
+            if not self._pushed[b]:
+                self.worker_push_bucket(b, grads)
+        self.ext.add_step(self.p_wstep, 1)
+        ops.count_launch()
+
+    def worker_push_killed(self, step):
+        self.ext.add_step(self.p_wstep, 1)
+
+    def _read_word(self, word_off) -> int:
+        with torch.cuda.stream(self._side):
+            v = self.flags_local[word_off // 8].item()
+        return int(v)
+
+    def worker_poll_kill(self, step):
+        return self._read_word(self.F_ABORT) == step
+
+    def worker_send_buffers(self, step, flat):
+        if flat.numel() == 0:
+            return
+        dst = self.arena.peer_view(0, self.off_bufs + 64, flat.numel() * 4, torch.float32)
+        dst.copy_(flat.float())
+        self.ext.set_word(self._flag(0, self.F_BUFS), int(step))
+
+    # ---- misc --------------------------------------------------------------------------------------------------------------
+    def check_error(self):
+        e = int(self.ctl[2].item())
+        if e:
+            raise RuntimeError("NVLink transport: device-side wait timed out (code %d) — a peer is missing or dead" % e)
+
+    def barrier(self):
+        if dist.is_initialized():
+            torch.cuda.synchronize(self.device)
+            dist.barrier()
+
+    def close(self):
+        torch.cuda.synchronize(self.device)
+        self.check_error()

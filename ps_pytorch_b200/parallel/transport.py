@@ -203,6 +203,7 @@ class GlooTransport(Transport):
         self._step_t[0], self._step_t[1] = step, 0
         dist.broadcast(self._step_t, src=0, group=self.group)          # C1
         self._bcast_payload(weights.flat, src=0)                        # C2 (one arena, not L messages)
+        self._published_weights = weights
 
     def ps_shutdown(self, step):
         # workers stop on their own at --max-steps (as in the reference); only stragglers' late messages remain
@@ -212,10 +213,9 @@ class GlooTransport(Transport):
         """Finish (and drop) receives from stragglers of earlier steps."""
         while True:
             for rx in self._pending:
-                rx.poll()
-            done = [rx for rx in self._pending if rx.done]
-            self.stats["stale_dropped"] += sum(1 for rx in done if rx.grad_blob is not None)
-            self._pending = [rx for rx in self._pending if not rx.done]
+                if rx.poll() and rx.grad_blob is not None:
+                    self.stats["stale_dropped"] += 1
+            self._pending = [rx for rx in self._pending if not rx._seen]
             if not block or not self._pending:
                 return
             time.sleep(0.0002)
@@ -242,7 +242,7 @@ class GlooTransport(Transport):
                         arrived.append(g)
                     elif rx.done:
                         self.stats["killed"] += 1
-            open_rx = [rx for rx in rxs if not rx.done]
+            open_rx = [rx for rx in rxs if not rx._seen]      # 'seen', not 'done': a thread may finish between poll and here
             if not open_rx:
                 break
             timed_out = bool(timeout_s) and (time.time() - t0) > timeout_s and len(arrived) >= 1
@@ -273,6 +273,9 @@ class GlooTransport(Transport):
             if int(self._step_t[1]) == 1:
                 return -1                                               # shutdown
             self._bcast_payload(weights.flat, src=0)
+        elif getattr(self, "_published_weights", None) is not None and \
+                self._published_weights.flat.data_ptr() != weights.flat.data_ptr():
+            weights.flat.copy_(self._published_weights.flat)              # co-located worker: local hand-off
         return int(self._step_t[0])
 
     def worker_push(self, step, grads, lo=0, hi=None, last=True):

@@ -86,8 +86,10 @@ class DistributedWorker(object):
         if getattr(net, "kill_threshold", None) is not None:
             net.kill_threshold = self.kill_threshold
         storage = self.comm.worker_weight_storage(self._dtype) if hasattr(self.comm, "worker_weight_storage") else None
+        gstorage = self.comm.worker_grad_storage(self._dtype) if hasattr(self.comm, "worker_grad_storage") else None
         self.compute = WorkerCompute(net, self._device, self._dtype, layout=self.comm.layout, weight_storage=storage,
-                                     use_graph=self._use_graph)
+                                     use_graph=self._use_graph, grad_storage=gstorage,
+                                     zero_grads_in_step=not getattr(self.comm, "zeroes_grads", False))
         self.network = self.compute.network
         self.optimizer = torch.optim.SGD(self.network.parameters(), lr=self.lr, momentum=self.momentum)  # zero_grad only, as in the reference
         self.criterion = self.compute.criterion

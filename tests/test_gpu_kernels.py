@@ -1,0 +1,268 @@
+"""GPU numerics: every sm_100a kernel against a plain PyTorch fp32 reference of the same op."""
+import math
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ext():
+    from ps_pytorch_b200 import ops
+    return ops.require()
+
+
+def _nhwc(*shape, scale=1.0, shift=0.0):
+    x = (torch.randn(*shape, device="cuda") * scale + shift).to(torch.bfloat16)
+    return x.contiguous(memory_format=torch.channels_last)
+
+
+# ---------------------------------------------------------------------------------------------------- optimizers
+@pytest.mark.parametrize("gdt", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("kw", [dict(momentum=0.9), dict(momentum=0.9, nesterov=True, weight_decay=1e-2), dict(momentum=0.0), dict(momentum=0.5, dampening=0.2)])
+def test_sgd_flat(ext, gdt, kw):
+    from ps_pytorch_b200.ops import optim as K
+    n = 128 * 1031
+    w = torch.randn(n, device="cuda"); buf = torch.zeros(n, device="cuda")
+    wr, bufr = w.clone(), None
+    lowp = torch.empty(n, device="cuda", dtype=torch.bfloat16)
+    mom, damp, wd, nest = kw.get("momentum", 0), kw.get("dampening", 0), kw.get("weight_decay", 0), kw.get("nesterov", False)
+    for it in range(3):
+        g = torch.randn(n, device="cuda").to(gdt)
+        K.sgd_flat(w, g, buf, 0.1, mom, damp, wd, nest, it == 0, 0.5, lowp)
+        d = g.float() * 0.5 + wd * wr
+        if mom:
+            bufr = d.clone() if it == 0 else mom * bufr + (1 - damp) * d
+            d = d + mom * bufr if nest else bufr
+        wr = wr - 0.1 * d
+        assert torch.allclose(w, wr, atol=1e-5, rtol=1e-5)
+        assert torch.equal(lowp, w.to(torch.bfloat16))
+
+
+@pytest.mark.parametrize("ams", [False, True])
+def test_adam_flat(ext, ams):
+    from ps_pytorch_b200.ops import optim as K
+    n = 128 * 517
+    w = torch.randn(n, device="cuda"); m = torch.zeros_like(w); v = torch.zeros_like(w); vm = torch.zeros_like(w) if ams else None
+    p = torch.nn.Parameter(w.clone())
+    ref = torch.optim.Adam([p], lr=1e-2, amsgrad=ams, weight_decay=1e-3)
+    for t in range(1, 4):
+        g = torch.randn(n, device="cuda")
+        ss = 1e-2 * math.sqrt(1 - 0.999 ** t) / (1 - 0.9 ** t)
+        K.adam_flat(w, g, m, v, vm, ss, 0.9, 0.999, 1e-8, 1e-3, 1.0, None)
+        p.grad = g.clone(); ref.step()
+        assert torch.allclose(w, p.data, atol=2e-5, rtol=1e-4)
+
+
+# ---------------------------------------------------------------------------------------------------- batch norm
+@pytest.mark.parametrize("shape", [(8, 64, 32, 32), (4, 128, 16, 16), (16, 512, 4, 4), (3, 256, 8, 8), (2, 2048, 2, 2), (5, 8, 3, 3)])
+@pytest.mark.parametrize("relu,res", [(False, False), (True, False), (True, True)])
+def test_batchnorm_fwd_bwd(ext, shape, relu, res):
+    from ps_pytorch_b200 import nn as pnn
+    torch.manual_seed(0)
+    n, c, h, w = shape
+    x = _nhwc(*shape, scale=2.0, shift=0.7).requires_grad_(True)
+    r = _nhwc(*shape).requires_grad_(True) if res else None
+    bn = pnn.BatchNorm2d(c).cuda().to(torch.bfloat16)
+    with torch.no_grad():
+        bn.weight.copy_(torch.rand(c) + 0.5); bn.bias.copy_(torch.randn(c) * 0.1)
+    assert bn.running_mean.dtype == torch.float32
+    with pnn.backend("sm100"):
+        z = bn(x, residual=r, relu=relu)
+    dz = torch.randn_like(z)
+    z.backward(dz)
+    # fp32 reference on the same bf16-rounded inputs
+    xr = x.detach().float().requires_grad_(True)
+    rr = r.detach().float().requires_grad_(True) if res else None
+    wr, br = bn.weight.detach().float().requires_grad_(True), bn.bias.detach().float().requires_grad_(True)
+    rm, rv = torch.zeros(c, device="cuda"), torch.ones(c, device="cuda")
+    y = F.batch_norm(xr, rm, rv, wr, br, True, 0.1, bn.eps)
+    if res:
+        y = y + rr
+    if relu:
+        y = F.relu(y)
+    y.backward(dz.float())
+    assert torch.allclose(z.float(), y, atol=3e-2, rtol=2e-2)
+    assert torch.allclose(bn.running_mean, rm, atol=1e-3, rtol=1e-3) and torch.allclose(bn.running_var, rv, atol=2e-3, rtol=2e-3)
+    # z was rounded to bf16 before the ReLU mask is taken, so compare gradients where |y| is not ~0
+    tol = dict(atol=6e-2, rtol=6e-2)
+    mask = (y.abs() > 2e-2) if relu else torch.ones_like(y, dtype=torch.bool)
+    assert torch.allclose(x.grad.float()[mask], xr.grad[mask], **tol)
+    if res:
+        assert torch.allclose(r.grad.float()[mask], rr.grad[mask], **tol)
+    scale = max(1.0, wr.grad.abs().max().item())
+    assert (bn.weight.grad.float() - wr.grad).abs().max().item() < 0.03 * scale
+    assert (bn.bias.grad.float() - br.grad).abs().max().item() < 0.03 * max(1.0, br.grad.abs().max().item())
+
+
+def test_batchnorm_eval(ext):
+    from ps_pytorch_b200 import nn as pnn
+    bn = pnn.BatchNorm2d(64).cuda().to(torch.bfloat16).eval()
+    bn.running_mean.normal_(); bn.running_var.uniform_(0.5, 2)
+    x = _nhwc(4, 64, 8, 8)
+    with pnn.backend("sm100"):
+        z = bn(x, relu=True)
+    ref = F.relu(F.batch_norm(x.float(), bn.running_mean, bn.running_var, bn.weight.float(), bn.bias.float(), False, 0.1, bn.eps))
+    assert torch.allclose(z.float(), ref, atol=3e-2, rtol=2e-2)
+
+
+# ---------------------------------------------------------------------------------------------------- pools / relu / loss
+@pytest.mark.parametrize("relu", [False, True])
+def test_maxpool(ext, relu):
+    from ps_pytorch_b200.ops import elementwise as E
+    x = _nhwc(4, 64, 16, 16).requires_grad_(True)
+    y = E.max_pool2x2(x, relu)
+    dy = torch.randn_like(y)
+    y.backward(dy)
+    xr = x.detach().float().requires_grad_(True)
+    yr = F.max_pool2d(xr, 2, 2)
+    if relu:
+        yr = F.relu(yr)
+    yr.backward(dy.float())
+    assert torch.equal(y.float(), yr) and torch.allclose(x.grad.float(), xr.grad)
+
+
+def test_global_avgpool_and_relu(ext):
+    from ps_pytorch_b200.ops import elementwise as E
+    x = _nhwc(8, 512, 4, 4).requires_grad_(True)
+    y = E.global_avg_pool(x)
+    dy = torch.randn_like(y)
+    y.backward(dy)
+    xr = x.detach().float().requires_grad_(True)
+    yr = F.avg_pool2d(xr, 4); yr.backward(dy.float())
+    assert torch.allclose(y.float(), yr, atol=1e-2, rtol=1e-2) and torch.allclose(x.grad.float(), xr.grad, atol=1e-3, rtol=1e-2)
+    a = _nhwc(2, 64, 8, 8).requires_grad_(True)
+    b = E.relu(a); b.backward(torch.ones_like(b))
+    assert torch.equal(b, F.relu(a.detach())) and torch.equal(a.grad, (a.detach() > 0).to(a.dtype))
+
+
+@pytest.mark.parametrize("dt,nc", [(torch.bfloat16, 10), (torch.float32, 100), (torch.bfloat16, 1000)])
+def test_softmax_ce(ext, dt, nc):
+    from ps_pytorch_b200.ops import loss as L
+    lg = (torch.randn(257, nc, device="cuda") * 3).to(dt).requires_grad_(True)
+    t = torch.randint(0, nc, (257,), device="cuda")
+    loss = L.softmax_cross_entropy(lg, t); loss.backward()
+    lr = lg.detach().float().requires_grad_(True)
+    ref = F.cross_entropy(lr, t); ref.backward()
+    assert abs(loss.item() - ref.item()) < 2e-3
+    assert torch.allclose(lg.grad.float(), lr.grad, atol=2e-4 if dt == torch.float32 else 2e-3, rtol=2e-2)
+
+
+# ---------------------------------------------------------------------------------------------------- comm kernels (one GPU)
+def _ru_setup(T, P, wire):
+    from ps_pytorch_b200.parallel.arena import ParamLayout
+    lay = ParamLayout(["w"], [(T,)], [T], [0], [False], T)
+    return lay
+
+
+@pytest.mark.parametrize("wire", ["bf16", "fp32", "fp8"])
+@pytest.mark.parametrize("opt", ["sgd", "adam"])
+def test_push_reduce_update_single_gpu(ext, wire, opt):
+    """P simulated workers push into the PS slots of one GPU; the fused kernel must equal mean-of-K + optimizer."""
+    import torch.distributed as dist
+    assert not dist.is_initialized()
+    from ps_pytorch_b200.parallel.arena import FlatBuffer, ParamLayout
+    from ps_pytorch_b200.parallel.nvl import NvlTransport
+    from ps_pytorch_b200.optim import build_optimizer
+    torch.manual_seed(1)
+    T = 128 * 1024 * 3
+    lay = ParamLayout(["w"], [(T,)], [T], [0], [False], T)
+    tr = NvlTransport(lay, torch.device("cuda"), grad_dtype=wire)
+    master = FlatBuffer(lay, torch.float32, "cuda"); master.flat.normal_()
+    ref_w = master.flat.clone()
+    opt_ = build_optimizer(opt, [torch.nn.Parameter(master.flat)], lr=0.05, momentum=0.9, weight_decay=1e-3)
+    opt_.attach_flat(master)
+    lowp = FlatBuffer(lay, torch.bfloat16, "cuda", storage=tr.ps_weight_storage())
+    lowp.flat.copy_(master.flat)
+    p = torch.nn.Parameter(ref_w.clone())
+    ref = torch.optim.SGD([p], lr=0.05, momentum=0.9, weight_decay=1e-3) if opt == "sgd" else torch.optim.Adam([p], lr=1e-3 if False else 1e-3, weight_decay=1e-3)
+    if opt == "adam":
+        opt_.param_groups[0]['lr'] = 1e-3
+    gdt = torch.float32 if wire == "fp32" else torch.bfloat16
+    grads = FlatBuffer(lay, gdt, "cuda", storage=tr.worker_grad_storage(gdt))
+    for step in range(1, 4):
+        tr.ps_publish(step, lowp)
+        assert tr.worker_fetch(lowp) == step
+        g = (torch.randn(T, device="cuda") * 0.1).to(gdt)
+        grads.flat.copy_(g)
+        tr.worker_push(step, grads)
+        assert grads.flat.abs().max().item() == 0, "push must leave a zeroed gradient arena"
+        tr.ps_reduce_update(step, 1, opt_, master, lowp=lowp)
+        torch.cuda.synchronize(); tr.check_error()
+        gq = g.float()
+        if wire == "fp8":
+            blk = gq.view(-1, 32)
+            amax = blk.abs().amax(1, keepdim=True)
+            e = torch.ceil(torch.log2(torch.clamp(amax / 448.0, min=2.0 ** -126)))
+            sc = torch.exp2(e)
+            gq = ((blk / sc).to(torch.float8_e4m3fn).float() * sc).view(-1)
+        p.grad = gq.clone(); ref.step()
+        assert torch.allclose(master.flat, p.data, atol=2e-5, rtol=1e-4), (wire, opt, step)
+        assert torch.equal(lowp.flat, master.flat.to(torch.bfloat16))
+    if wire == "fp8":   # quantisation error bound: e4m3 has 3 mantissa bits -> <= 2^-4 relative to the block max
+        blk, qb = g.float().view(-1, 32), gq.view(-1, 32)
+        assert ((blk - qb).abs() <= blk.abs().amax(1, keepdim=True) * 0.0625 + 1e-12).all()
+
+
+def test_k_of_p_and_stale_rejection(ext):
+    """3 slots on one GPU: only slots whose flag equals the PS step are summed; K=2 takes the first two arrivals."""
+    from ps_pytorch_b200.parallel.arena import FlatBuffer, ParamLayout
+    from ps_pytorch_b200.parallel import nvl as N
+    from ps_pytorch_b200.optim import build_optimizer
+    T = 128 * 256
+    lay = ParamLayout(["w"], [(T,)], [T], [0], [False], T)
+    tr = _three_slot_transport(lay)
+    master = FlatBuffer(lay, torch.float32, "cuda")
+    opt_ = build_optimizer("sgd", [torch.nn.Parameter(master.flat)], lr=1.0, momentum=0.0)
+    opt_.attach_flat(master)
+    lowp = FlatBuffer(lay, torch.bfloat16, "cuda", storage=tr.ps_weight_storage())
+    grads = FlatBuffer(lay, torch.float32, "cuda", storage=tr.worker_grad_storage(torch.float32))
+    vals = [1.0, 10.0, 100.0]
+    for slot, v in enumerate(vals):
+        grads.flat.fill_(v)
+        tr._slot_override = slot
+        if slot == 1:
+            tr.ctl[0] = 0          # slot 1 pushes with a STALE step id (0 instead of 1)
+        tr.worker_push_bucket(0, grads)
+        tr.ctl[0] = 1
+    tr.ps_reduce_update(1, 2, opt_, master, lowp=lowp)
+    torch.cuda.synchronize(); tr.check_error()
+    # arrivals with step 1: slots 0 and 2 -> mean over K=2 of (1 + 100) -> w = -(101/2)
+    assert torch.allclose(master.flat, torch.full((T,), -50.5, device="cuda"))
+
+
+def _three_slot_transport(lay):
+    from ps_pytorch_b200.parallel import nvl as N
+
+    # build through the normal constructor, then widen the worker list before the arena is sized
+    orig = N.Transport.__init__
+
+    def patched(self, rank, world, layout, colocate=False):
+        orig(self, rank, world, layout, colocate)
+        self.worker_ranks, self.num_workers = [0, 0, 0], 3
+    N.Transport.__init__ = patched
+    try:
+        tr = N.NvlTransport(lay, torch.device("cuda"), grad_dtype="fp32")
+    finally:
+        N.Transport.__init__ = orig
+    tr.__class__ = type("T3", (N.NvlTransport,), {"_slot_override": 0, "_my_slot": lambda self: self._slot_override})
+    return tr
+
+
+def test_timeout_sets_error_instead_of_hanging(ext):
+    from ps_pytorch_b200.parallel.arena import FlatBuffer, ParamLayout
+    from ps_pytorch_b200.parallel.nvl import NvlTransport
+    from ps_pytorch_b200.optim import build_optimizer
+    T = 128 * 64
+    lay = ParamLayout(["w"], [(T,)], [T], [0], [False], T)
+    tr = NvlTransport(lay, torch.device("cuda"), grad_dtype="bf16", timeout_s=0.2)
+    tr.timeout_s = 0.2
+    master = FlatBuffer(lay, torch.float32, "cuda")
+    opt_ = build_optimizer("sgd", [torch.nn.Parameter(master.flat)], lr=1.0, momentum=0.0)
+    opt_.attach_flat(master)
+    tr.ps_reduce_update(1, 1, opt_, master, timeout_s=0.2)      # nobody pushed
+    torch.cuda.synchronize()
+    with pytest.raises(RuntimeError):
+        tr.check_error()
