@@ -65,7 +65,11 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append(line.strip())
+            self.rows.append((time.perf_counter(), line.strip()))
+
+    def window(self, t0, t1):
+        """Keep only the samples taken inside the timed region."""
+        self.rows = [r for t, r in self.rows if t0 <= t <= t1] or [r for _t, r in self.rows[-max(1, len(self.rows) // 4):]]
 
     def stop(self, ngpu):
         if self.proc is None:
@@ -77,6 +81,8 @@ class ClockSampler:
             self.proc.kill()
         clk, mx, reasons, pw = [], [], set(), []
         for r in self.rows:
+            if isinstance(r, tuple):
+                r = r[1]
             f = [x.strip() for x in r.split(",")]
             if len(f) < 9 or not f[0].isdigit() or int(f[0]) >= ngpu:
                 continue
@@ -163,17 +169,27 @@ def main():
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t[0]), float(t[1]), last
 
+    sampler = ClockSampler()
+    if rank == 0:
+        sampler.start()                   # nvidia-smi needs ~1 s to start streaming: launch it before the warm-up
     run(max(a.warmup, 3), False)          # untimed warm-up (includes CUDA-graph capture)
     barrier()
     if hasattr(job.comm, "check_error"):
         job.comm.check_error()
-    sampler = ClockSampler()
-    if rank == 0:
-        sampler.start()
     l0 = ops.launch_count
+    tw0 = time.perf_counter()
     ms, wall_ms, loss = timed(a.steps, False)
+    tw1 = time.perf_counter()
     launches = ops.launch_count - l0
-    clocks = sampler.stop(world) if rank == 0 else None
+    clocks = None
+    if ms < 350.0:                        # too short for a 100 ms sampler: keep the load on (untimed, all ranks) so 3+ samples exist
+        run(int(500.0 / max(ms / a.steps, 0.1)) + 1, False)
+        torch.cuda.synchronize()
+        tw1 = time.perf_counter()
+    if rank == 0:
+        time.sleep(0.15)
+        sampler.window(tw0, tw1 + 0.1)
+        clocks = sampler.stop(world)
     e2e = None
     if not a.skip_e2e:
         ems, ewall, loss = timed(a.steps, True)

@@ -1,19 +1,76 @@
-"""Convolutions on the tcgen05 implicit-GEMM kernels (``csrc/gemm_tcgen05.cu``)."""
+"""Convolutions on the tcgen05 implicit-GEMM kernel (``csrc/gemm_tcgen05.cu``).
+
+Forward (fprop) and the data gradient of stride-1 convolutions run on the hand-written kernel; the weight gradient and the
+data gradient of strided convolutions currently go through cuDNN (``torch.ops.aten.convolution_backward``) — logged
+once per process by ``note_fallback``."""
 from __future__ import annotations
+
+import os
 
 import torch
 
 from . import count_launch, require
+from ..nn.backend import note_fallback
+
+_ENABLED = os.environ.get("PSB200_TC_CONV", "1") != "0"
 
 
 def unsupported_reason(x, weight, stride, padding, dilation, groups):
+    if not _ENABLED:
+        return "disabled by PSB200_TC_CONV=0"
     ext = require()
     if not hasattr(ext, "conv_fprop"):
         return "tcgen05 implicit-GEMM conv not built"
-    return ext.conv_unsupported_reason(list(x.shape), list(weight.shape), list(stride), list(padding), list(dilation), groups,
-                                       x.dtype == torch.bfloat16 and weight.dtype == torch.bfloat16)
+    if isinstance(padding, str):
+        return "string padding"
+    r = ext.conv_unsupported_reason(list(x.shape), list(weight.shape), list(stride), list(padding), list(dilation), groups,
+                                    x.dtype == torch.bfloat16 and weight.dtype == torch.bfloat16)
+    return r or None
+
+
+def _krsc(w):
+    """[Cout,Cin,R,S] logical -> physically [Cout][R][S][Cin] (no copy for channels-last parameters)."""
+    return w if w.is_contiguous(memory_format=torch.channels_last) else w.contiguous(memory_format=torch.channels_last)
+
+
+class _ConvFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, weight, bias, stride, pad):
+        ext = require()
+        x = x.contiguous(memory_format=torch.channels_last)
+        y = ext.conv_fprop(x, _krsc(weight), bias, stride, pad, False)
+        count_launch()
+        ctx.save_for_backward(x, weight)
+        ctx.stride, ctx.pad, ctx.has_bias = stride, pad, bias is not None
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, weight = ctx.saved_tensors
+        ext = require()
+        dy = dy.contiguous(memory_format=torch.channels_last)
+        s, p = ctx.stride, ctx.pad
+        r = weight.size(2)
+        dx = dw = db = None
+        need_dx, need_dw = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
+        if need_dx and s == 1 and weight.size(0) % 64 == 0 and weight.size(1) % 8 == 0:
+            # dX = conv(dY, flip(W)^T, pad = R-1-pad): the same implicit-GEMM kernel on transformed weights
+            wt = weight.flip(2, 3).permute(1, 0, 2, 3).contiguous(memory_format=torch.channels_last)
+            dx = ext.conv_fprop(dy, wt, None, 1, r - 1 - p, False)
+            count_launch()
+            need_dx = False
+        if need_dx or need_dw:
+            note_fallback("conv2d.backward", "weight gradient / strided data gradient use cuDNN")
+            gi, gw, _ = torch.ops.aten.convolution_backward(dy, x, weight, None, (s, s), (p, p), (1, 1), False, (0, 0), 1,
+                                                            (need_dx, need_dw, False))
+            if need_dx:
+                dx = gi
+            if need_dw:
+                dw = gw
+        if ctx.has_bias and ctx.needs_input_grad[2]:
+            db = dy.float().sum((0, 2, 3)).to(dy.dtype)
+        return dx, dw, db, None, None
 
 
 def conv2d(x, weight, bias, stride, padding):
-    from .conv_impl import conv2d as _c
-    return _c(x, weight, bias, stride, padding)
+    return _ConvFn.apply(x, weight, bias, int(stride[0]), int(padding[0]))

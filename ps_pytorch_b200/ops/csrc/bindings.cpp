@@ -42,7 +42,10 @@ void close_fd(int64_t);
 at::Tensor tensor_from_ptr(int64_t, int64_t, int64_t);
 }  // namespace psb
 
+void bind_gemm(pybind11::module_& m);
+
 PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
+    bind_gemm(m);
     using namespace psb;
     m.def("sgd_flat", &sgd_flat); m.def("adam_flat", &adam_flat);
     m.def("push", &push); m.def("reduce_update", &reduce_update); m.def("bcast", &bcast); m.def("wait_flag", &wait_flag);

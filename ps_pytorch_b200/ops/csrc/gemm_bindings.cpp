@@ -1,0 +1,63 @@
+// torch-facing wrappers of the tcgen05 GEMM / implicit-GEMM convolution launchers (gemm_tcgen05.cu is torch-free so it
+// compiles in seconds).
+#include <torch/extension.h>
+#include <ATen/cuda/CUDAContext.h>
+
+namespace psb {
+const char* tc_gemm_tn(const void*, const void*, void*, const void*, int, int, int, int, cudaStream_t);
+const char* tc_conv_fprop(const void*, const void*, void*, const void*, int, int, int, int, int, int, int, int, int, int, cudaStream_t);
+int tc_check_error();
+
+static const void* opt_ptr(const c10::optional<at::Tensor>& t, int64_t n) {
+    if (!t.has_value()) return nullptr;
+    TORCH_CHECK(t->scalar_type() == at::kBFloat16 && t->is_contiguous() && t->numel() == n, "bias must be contiguous bf16 of size N");
+    return t->data_ptr();
+}
+
+// y[M,N] = x[M,K] @ w[N,K]^T (+bias)(+relu); all bf16
+at::Tensor gemm_tn(at::Tensor x, at::Tensor w, c10::optional<at::Tensor> bias, bool relu) {
+    TORCH_CHECK(x.is_cuda() && w.is_cuda() && x.scalar_type() == at::kBFloat16 && w.scalar_type() == at::kBFloat16);
+    TORCH_CHECK(x.dim() == 2 && w.dim() == 2 && x.is_contiguous() && w.is_contiguous() && x.size(1) == w.size(1));
+    const int64_t M = x.size(0), K = x.size(1), N = w.size(0);
+    TORCH_CHECK((reinterpret_cast<uintptr_t>(x.data_ptr()) % 16) == 0 && (reinterpret_cast<uintptr_t>(w.data_ptr()) % 16) == 0, "operands must be 16-byte aligned");
+    at::Tensor y = at::empty({M, N}, x.options());
+    const char* e = tc_gemm_tn(x.data_ptr(), w.data_ptr(), y.data_ptr(), opt_ptr(bias, N), (int)M, (int)N, (int)K, relu, at::cuda::getCurrentCUDAStream());
+    TORCH_CHECK(e == nullptr, "tc_gemm_tn: ", e);
+    return y;
+}
+
+// x: [NB,Cin,H,W] channels_last; w: [Cout,Cin,R,S] channels_last (physically [Cout][R][S][Cin]); returns channels_last y
+at::Tensor conv_fprop(at::Tensor x, at::Tensor w, c10::optional<at::Tensor> bias, int64_t stride, int64_t pad, bool relu) {
+    TORCH_CHECK(x.is_cuda() && x.scalar_type() == at::kBFloat16 && w.scalar_type() == at::kBFloat16 && x.dim() == 4 && w.dim() == 4);
+    TORCH_CHECK(x.is_contiguous(at::MemoryFormat::ChannelsLast), "x must be NHWC");
+    TORCH_CHECK(w.is_contiguous(at::MemoryFormat::ChannelsLast), "w must be [Cout][R][S][Cin]");
+    const int NB = x.size(0), Cin = x.size(1), H = x.size(2), W = x.size(3), Cout = w.size(0), R = w.size(2), S = w.size(3);
+    TORCH_CHECK(w.size(1) == Cin);
+    const int Ho = (H + 2 * pad - R) / stride + 1, Wo = (W + 2 * pad - S) / stride + 1;
+    at::Tensor y = at::empty({NB, Cout, Ho, Wo}, x.options().memory_format(at::MemoryFormat::ChannelsLast));
+    const char* e = tc_conv_fprop(x.data_ptr(), w.data_ptr(), y.data_ptr(), opt_ptr(bias, Cout), NB, H, W, Cin, Cout, R, S, (int)stride, (int)pad, relu,
+                                  at::cuda::getCurrentCUDAStream());
+    TORCH_CHECK(e == nullptr, "tc_conv_fprop: ", e);
+    return y;
+}
+
+std::string conv_unsupported_reason(std::vector<int64_t> xs, std::vector<int64_t> ws, std::vector<int64_t> stride, std::vector<int64_t> pad,
+                                    std::vector<int64_t> dil, int64_t groups, bool bf16) {
+    if (!bf16) return "needs bf16 operands";
+    if (groups != 1) return "grouped convolution";
+    if (dil[0] != 1 || dil[1] != 1) return "dilated convolution";
+    if (stride[0] != stride[1] || pad[0] != pad[1]) return "anisotropic stride/padding";
+    if (xs[1] % 64) return "Cin is not a multiple of 64";
+    if (ws[0] % 8) return "Cout is not a multiple of 8";
+    return "";
+}
+
+int64_t tc_error() { return tc_check_error(); }
+}  // namespace psb
+
+void bind_gemm(pybind11::module_& m) {
+    m.def("gemm_tn", &psb::gemm_tn);
+    m.def("conv_fprop", &psb::conv_fprop);
+    m.def("conv_unsupported_reason", &psb::conv_unsupported_reason);
+    m.def("tc_error", &psb::tc_error);
+}

@@ -1,0 +1,317 @@
+// tcgen05 GEMM and implicit-GEMM convolution for sm_100a.
+//
+//   C[M,N] (bf16) = A[M,K] x B[N,K]^T (+bias) (+ReLU)        A, B bf16 K-major ("TN"), fp32 accumulation in TMEM
+//
+// One persistent, warp-specialised kernel (grid = #SMs, static tile scheduler):
+//   warp 0   TMA producer      cp.async.bulk.tensor -> 128B-swizzled smem ring (kStages deep), mbarrier complete_tx
+//   warp 1   MMA issuer        one elected lane issues tcgen05.mma.cta_group::1.kind::f16 (128 x BN x 16), accumulators
+//                              double-buffered in TMEM so the epilogue of tile i overlaps the MMAs of tile i+1
+//   warp 2   TMEM allocator
+//   warps 4-7 epilogue         tcgen05.ld (32 lanes x 32 columns per warp) -> bias/ReLU -> bf16 -> global
+//
+// Convolution (fprop; dgrad of stride-1 convs is the same kernel on flipped/transposed weights) is the same GEMM with
+// M = output pixels, N = Cout, K = R*S*Cin and NO im2col buffer: for filter tap (r,s) and channel block cb the A tile of
+// 128 output pixels (a BNI x BH x BW rectangle of the NHWC activation) is ONE 4-D TMA box load at coordinates
+// (cb*64, w0*stride+s-pad, h0*stride+r-pad, n0); out-of-bounds rows/columns (the padding halo) are zero-filled by
+// the TMA unit, stride-2 convolutions use the tensor map's element strides.  Weights are [Cout][R][S][Cin] (the
+// physical layout of channels-last parameters in the flat arena), i.e. already the K-major B operand.
+//
+// Reference ops replaced: nn.Conv2d / nn.Linear -> cuDNN / cuBLAS (/root/reference/src/model_ops/*.py).
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <mutex>
+#include "tc_ptx.cuh"
+
+namespace psb {
+
+using namespace tc;
+
+constexpr int BM = 128;
+constexpr int BK = 64;                 // 64 bf16 = one 128-byte swizzle row
+constexpr int kThreads = 256;
+constexpr int kEpiWarp0 = 4;
+
+struct TcParams {
+    int M, N, num_kb;
+    int mode;                          // 0 GEMM, 1 implicit-GEMM conv
+    int n_tiles_m, n_tiles_n;
+    // conv geometry
+    int Hout, Wout, NB, stride, pad, S, cblocks;
+    int BW, BH, BNI, tiles_w, tiles_h;
+    const __nv_bfloat16* bias;
+    int relu;
+    __nv_bfloat16* C;
+    int* err;                          // set to 1 if a barrier wait timed out (protocol bug), never hang
+};
+
+template <int BN> struct TcCfg {
+    static constexpr int kStages = BN == 64 ? 8 : 6;
+    static constexpr int kABytes = BM * BK * 2;
+    static constexpr int kBBytes = BN * BK * 2;
+    static constexpr int kStageBytes = kABytes + kBBytes;
+    static constexpr int kTmemCols = 2 * BN;                      // two accumulator stages (power of two: 128 / 256)
+    static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+};
+
+template <int BN>
+__global__ void __launch_bounds__(kThreads, 1)
+tc_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, const TcParams p) {
+    using Cfg = TcCfg<BN>;
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + Cfg::kStages * Cfg::kStageBytes);
+    uint64_t* empty_bar = full_bar + Cfg::kStages;
+    uint64_t* tmem_full = empty_bar + Cfg::kStages;
+    uint64_t* tmem_empty = tmem_full + 2;
+    uint32_t* tmem_base_smem = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (warp == 0 && lane == 0) { prefetch_tmap(&tmap_a); prefetch_tmap(&tmap_b); }
+    if (warp == 1 && lane == 0) {
+        for (int s = 0; s < Cfg::kStages; ++s) { mbar_init(full_bar + s, 1); mbar_init(empty_bar + s, 1); }
+        for (int s = 0; s < 2; ++s) { mbar_init(tmem_full + s, 1); mbar_init(tmem_empty + s, 4); }
+        fence_barrier_init();
+    }
+    if (warp == 2) tmem_alloc(tmem_base_smem, Cfg::kTmemCols);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_base_smem;
+    const int n_tiles = p.n_tiles_m * p.n_tiles_n;
+
+    if (warp == 0) {
+        // ===================================================== TMA producer
+        if (lane == 0) {
+            int stage = 0; uint32_t phase = 0;
+            for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+                const int mt = tile / p.n_tiles_n, nt = tile % p.n_tiles_n;
+                int n0 = 0, h0 = 0, w0 = 0;
+                if (p.mode == 1) {
+                    const int tw = mt % p.tiles_w, th = (mt / p.tiles_w) % p.tiles_h, tn = mt / (p.tiles_w * p.tiles_h);
+                    n0 = tn * p.BNI; h0 = th * p.BH; w0 = tw * p.BW;
+                }
+                for (int kb = 0; kb < p.num_kb; ++kb) {
+                    if (!mbar_wait(empty_bar + stage, phase ^ 1)) { *p.err = 1; return; }
+                    uint8_t* sa = smem + stage * Cfg::kStageBytes;
+                    uint8_t* sb = sa + Cfg::kABytes;
+                    mbar_arrive_expect_tx(full_bar + stage, Cfg::kStageBytes);
+                    if (p.mode == 0) {
+                        tma_load_2d(sa, &tmap_a, full_bar + stage, kb * BK, mt * BM);
+                    } else {
+                        const int tap = kb / p.cblocks, cb = kb % p.cblocks;
+                        const int r = tap / p.S, s = tap % p.S;
+                        tma_load_4d(sa, &tmap_a, full_bar + stage, cb * BK, w0 * p.stride + s - p.pad, h0 * p.stride + r - p.pad, n0);
+                    }
+                    tma_load_2d(sb, &tmap_b, full_bar + stage, kb * BK, nt * BN);
+                    if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================================================== MMA issuer
+        if (lane == 0) {
+            constexpr uint32_t idesc = umma_idesc_bf16(BM, BN, 0, 0);
+            int stage = 0; uint32_t phase = 0; int acc = 0; uint32_t acc_phase = 0;
+            for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+                if (!mbar_wait(tmem_empty + acc, acc_phase ^ 1)) { *p.err = 2; return; }
+                tc_fence_after();
+                const uint32_t tmem_d = tmem_base + acc * BN;
+                for (int kb = 0; kb < p.num_kb; ++kb) {
+                    if (!mbar_wait(full_bar + stage, phase)) { *p.err = 3; return; }
+                    tc_fence_after();
+                    const uint32_t sa = smem_u32(smem + stage * Cfg::kStageBytes);
+                    const uint32_t sb = sa + Cfg::kABytes;
+#pragma unroll
+                    for (int k = 0; k < BK / 16; ++k) {
+                        const uint64_t ad = umma_desc_k_sw128(sa + k * 32);
+                        const uint64_t bd = umma_desc_k_sw128(sb + k * 32);
+                        tc_mma_bf16(tmem_d, ad, bd, idesc, (kb | k) != 0);
+                    }
+                    tc_commit(empty_bar + stage);                   // smem slot reusable once these MMAs retire
+                    if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
+                }
+                tc_commit(tmem_full + acc);                          // accumulator complete -> epilogue
+                if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+            }
+        }
+    } else if (warp >= kEpiWarp0) {
+        // ===================================================== epilogue (4 warps, one TMEM lane quarter each)
+        const int q = warp & 3;
+        int acc = 0; uint32_t acc_phase = 0;
+        const bool vec_ok = (p.N % 8) == 0;
+        for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+            const int mt = tile / p.n_tiles_n, nt = tile % p.n_tiles_n;
+            const int row_in_tile = q * 32 + lane;
+            long long out_row = -1;
+            if (p.mode == 0) {
+                const int m = mt * BM + row_in_tile;
+                if (m < p.M) out_row = m;
+            } else {
+                const int tw = mt % p.tiles_w, th = (mt / p.tiles_w) % p.tiles_h, tn = mt / (p.tiles_w * p.tiles_h);
+                const int bw = row_in_tile % p.BW, bh = (row_in_tile / p.BW) % p.BH, bn = row_in_tile / (p.BW * p.BH);
+                const int n = tn * p.BNI + bn, h = th * p.BH + bh, w = tw * p.BW + bw;
+                if (n < p.NB && h < p.Hout && w < p.Wout) out_row = ((long long)n * p.Hout + h) * p.Wout + w;
+            }
+            if (!mbar_wait(tmem_full + acc, acc_phase)) { if (lane == 0) *p.err = 4; return; }
+            tc_fence_after();
+            __nv_bfloat16* crow = p.C + out_row * (long long)p.N + (long long)nt * BN;
+#pragma unroll 1
+            for (int c0 = 0; c0 < BN; c0 += 32) {
+                uint32_t v[32];
+                tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + c0), v);
+                tmem_ld_wait();
+                const int col0 = nt * BN + c0;
+                if (out_row >= 0 && col0 < p.N) {
+                    float f[32];
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
+                    if (p.bias) {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) if (col0 + j < p.N) f[j] += __bfloat162float(p.bias[col0 + j]);
+                    }
+                    if (p.relu) {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.f);
+                    }
+                    if (vec_ok && col0 + 32 <= p.N) {
+#pragma unroll
+                        for (int j = 0; j < 32; j += 8) {
+                            uint4 o;
+                            __nv_bfloat162 h0 = __floats2bfloat162_rn(f[j], f[j + 1]), h1 = __floats2bfloat162_rn(f[j + 2], f[j + 3]);
+                            __nv_bfloat162 h2 = __floats2bfloat162_rn(f[j + 4], f[j + 5]), h3 = __floats2bfloat162_rn(f[j + 6], f[j + 7]);
+                            o.x = *reinterpret_cast<uint32_t*>(&h0); o.y = *reinterpret_cast<uint32_t*>(&h1);
+                            o.z = *reinterpret_cast<uint32_t*>(&h2); o.w = *reinterpret_cast<uint32_t*>(&h3);
+                            *reinterpret_cast<uint4*>(crow + c0 + j) = o;
+                        }
+                    } else {
+                        for (int j = 0; j < 32; ++j) if (col0 + j < p.N) crow[c0 + j] = __float2bfloat16_rn(f[j]);
+                    }
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(tmem_empty + acc);
+            if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+        }
+    }
+    // ---- teardown
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    if (warp == 2) tmem_dealloc(tmem_base, Cfg::kTmemCols);
+}
+
+// ------------------------------------------------------------------------------------------------------------------ host
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn get_encode() {
+    static EncodeTiledFn fn = nullptr;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess) fn = reinterpret_cast<EncodeTiledFn>(p);
+    });
+    return fn;
+}
+
+// rank-`rank` bf16 tensor map with 128-byte swizzle; dims/strides innermost first (strides in BYTES, for dims 1..rank-1)
+static const char* make_tmap(CUtensorMap* m, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                             const uint32_t* box, const uint32_t* estrides) {
+    EncodeTiledFn enc = get_encode();
+    if (!enc) return "cuTensorMapEncodeTiled unavailable";
+    CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base), (const cuuint64_t*)dims,
+                     (const cuuint64_t*)strides_bytes, (const cuuint32_t*)box, (const cuuint32_t*)estrides, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { static char buf[64]; snprintf(buf, sizeof buf, "cuTensorMapEncodeTiled failed (%d)", (int)r); return buf; }
+    return nullptr;
+}
+
+static int* err_word() {                // one device word shared by all launches; checked by tc_check_error()
+    static int* p = nullptr;
+    if (!p) { cudaMalloc(&p, sizeof(int)); cudaMemset(p, 0, sizeof(int)); }
+    return p;
+}
+int tc_check_error() {
+    int h = 0;
+    cudaMemcpy(&h, err_word(), sizeof(int), cudaMemcpyDeviceToHost);
+    if (h) cudaMemset(err_word(), 0, sizeof(int));
+    return h;
+}
+
+static int num_sms() {
+    static int n = 0;
+    if (!n) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev); }
+    return n;
+}
+
+template <int BN>
+static const char* launch(const CUtensorMap& ta, const CUtensorMap& tb, const TcParams& p, cudaStream_t stream) {
+    using Cfg = TcCfg<BN>;
+    static bool attr = false;
+    if (!attr) {
+        if (cudaFuncSetAttribute(tc_gemm_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes) != cudaSuccess) return "cannot raise dynamic smem";
+        attr = true;
+    }
+    const int tiles = p.n_tiles_m * p.n_tiles_n;
+    const int grid = tiles < num_sms() ? tiles : num_sms();
+    tc_gemm_kernel<BN><<<grid, kThreads, Cfg::kSmemBytes, stream>>>(ta, tb, p);
+    return cudaGetLastError() == cudaSuccess ? nullptr : "kernel launch failed";
+}
+
+// C[M,N] = A[M,K] B[N,K]^T ; lda/ldb = K (dense rows)
+const char* tc_gemm_tn(const void* A, const void* B, void* C, const void* bias, int M, int N, int K, int relu, cudaStream_t stream) {
+    if (K % 8) return "K must be a multiple of 8";
+    const int BN = N <= 64 ? 64 : 128;
+    CUtensorMap ta, tb;
+    uint64_t da[2] = {(uint64_t)K, (uint64_t)M}, sa[1] = {(uint64_t)K * 2};
+    uint64_t db[2] = {(uint64_t)K, (uint64_t)N}, sb[1] = {(uint64_t)K * 2};
+    uint32_t boxa[2] = {BK, BM}, boxb[2] = {BK, (uint32_t)BN}, es[2] = {1, 1};
+    if (const char* e = make_tmap(&ta, A, 2, da, sa, boxa, es)) return e;
+    if (const char* e = make_tmap(&tb, B, 2, db, sb, boxb, es)) return e;
+    TcParams p{};
+    p.M = M; p.N = N; p.num_kb = (K + BK - 1) / BK; p.mode = 0;
+    p.n_tiles_m = (M + BM - 1) / BM; p.n_tiles_n = (N + BN - 1) / BN;
+    p.bias = (const __nv_bfloat16*)bias; p.relu = relu; p.C = (__nv_bfloat16*)C; p.err = err_word();
+    return BN == 64 ? launch<64>(ta, tb, p, stream) : launch<128>(ta, tb, p, stream);
+}
+
+// Y[NB,Hout,Wout,Cout] = conv(X[NB,Hin,Win,Cin], Wt[Cout][R][S][Cin]), NHWC bf16
+const char* tc_conv_fprop(const void* X, const void* Wt, void* Y, const void* bias, int NB, int Hin, int Win, int Cin, int Cout,
+                          int R, int S, int stride, int pad, int relu, cudaStream_t stream) {
+    if (Cin % 64) return "Cin must be a multiple of 64";
+    if (Cout % 8) return "Cout must be a multiple of 8";
+    const int Hout = (Hin + 2 * pad - R) / stride + 1, Wout = (Win + 2 * pad - S) / stride + 1;
+    // tile rectangle: BW = largest power of two <= min(Wout,32), then rows, then images, product 128
+    int BW = 1; while (BW * 2 <= Wout && BW * 2 <= 32) BW *= 2;
+    int BH = 1; while (BH * 2 <= Hout && BW * BH * 2 <= 128) BH *= 2;
+    int BNI = 128 / (BW * BH);
+    if (BW * stride > 256 || BH * stride > 256 || BNI > 256) return "tile rectangle exceeds the TMA box limit";
+    const int BN = Cout <= 64 ? 64 : 128;
+    CUtensorMap ta, tb;
+    uint64_t da[4] = {(uint64_t)Cin, (uint64_t)Win, (uint64_t)Hin, (uint64_t)NB};
+    uint64_t sa[3] = {(uint64_t)Cin * 2, (uint64_t)Win * Cin * 2, (uint64_t)Hin * Win * Cin * 2};
+    // with element strides the box extent is given in source elements: ceil(box/stride) elements are fetched
+    uint32_t boxa[4] = {BK, (uint32_t)((BW - 1) * stride + 1), (uint32_t)((BH - 1) * stride + 1), (uint32_t)BNI};
+    uint32_t esa[4] = {1, (uint32_t)stride, (uint32_t)stride, 1};
+    const int Ktot = R * S * Cin;
+    uint64_t db[2] = {(uint64_t)Ktot, (uint64_t)Cout}, sb[1] = {(uint64_t)Ktot * 2};
+    uint32_t boxb[2] = {BK, (uint32_t)BN}, esb[2] = {1, 1};
+    if (const char* e = make_tmap(&ta, X, 4, da, sa, boxa, esa)) return e;
+    if (const char* e = make_tmap(&tb, Wt, 2, db, sb, boxb, esb)) return e;
+    TcParams p{};
+    p.M = NB * Hout * Wout; p.N = Cout; p.num_kb = Ktot / BK; p.mode = 1;
+    p.Hout = Hout; p.Wout = Wout; p.NB = NB; p.stride = stride; p.pad = pad; p.S = S; p.cblocks = Cin / BK;
+    p.BW = BW; p.BH = BH; p.BNI = BNI;
+    p.tiles_w = (Wout + BW - 1) / BW; p.tiles_h = (Hout + BH - 1) / BH;
+    const int tiles_n_img = (NB + BNI - 1) / BNI;
+    p.n_tiles_m = p.tiles_w * p.tiles_h * tiles_n_img; p.n_tiles_n = (Cout + BN - 1) / BN;
+    p.bias = (const __nv_bfloat16*)bias; p.relu = relu; p.C = (__nv_bfloat16*)Y; p.err = err_word();
+    return BN == 64 ? launch<64>(ta, tb, p, stream) : launch<128>(ta, tb, p, stream);
+}
+
+}  // namespace psb
