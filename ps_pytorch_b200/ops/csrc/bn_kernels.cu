@@ -70,8 +70,22 @@ __global__ void __launch_bounds__(256) bn_finalize_kernel(const float* __restric
     const int cl = threadIdx.x & 31, grp = threadIdx.x >> 5;
     const int c = blockIdx.x * 32 + cl;
     float s = 0.f, q = 0.f;
-    if (c < C)
-        for (int b = grp; b < nblk; b += 8) { s += partial[(long long)b * 2 * C + c]; q += partial[(long long)b * 2 * C + C + c]; }
+    if (c < C) {
+        // the partial rows are independent: keep 8 loads in flight instead of one dependent load per iteration
+        // (a serial loop here cost ~32 us per call: 74 dependent L2/DRAM round trips)
+        float s8[8] = {0, 0, 0, 0, 0, 0, 0, 0}, q8[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        int b = grp;
+        for (; b + 56 < nblk; b += 64) {
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                s8[u] += __ldg(partial + (long long)(b + 8 * u) * 2 * C + c);
+                q8[u] += __ldg(partial + (long long)(b + 8 * u) * 2 * C + C + c);
+            }
+        }
+        for (; b < nblk; b += 8) { s8[0] += __ldg(partial + (long long)b * 2 * C + c); q8[0] += __ldg(partial + (long long)b * 2 * C + C + c); }
+#pragma unroll
+        for (int u = 0; u < 8; ++u) { s += s8[u]; q += q8[u]; }
+    }
     ss[grp][cl] = s; sq[grp][cl] = q;
     __syncthreads();
     if (grp == 0 && c < C) {
@@ -189,8 +203,22 @@ __global__ void __launch_bounds__(256) bn_bwd_finalize_kernel(const float* __res
     const int cl = threadIdx.x & 31, grp = threadIdx.x >> 5;
     const int c = blockIdx.x * 32 + cl;
     float s = 0.f, q = 0.f;
-    if (c < C)
-        for (int b = grp; b < nblk; b += 8) { s += partial[(long long)b * 2 * C + c]; q += partial[(long long)b * 2 * C + C + c]; }
+    if (c < C) {
+        // the partial rows are independent: keep 8 loads in flight instead of one dependent load per iteration
+        // (a serial loop here cost ~32 us per call: 74 dependent L2/DRAM round trips)
+        float s8[8] = {0, 0, 0, 0, 0, 0, 0, 0}, q8[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        int b = grp;
+        for (; b + 56 < nblk; b += 64) {
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                s8[u] += __ldg(partial + (long long)(b + 8 * u) * 2 * C + c);
+                q8[u] += __ldg(partial + (long long)(b + 8 * u) * 2 * C + C + c);
+            }
+        }
+        for (; b < nblk; b += 8) { s8[0] += __ldg(partial + (long long)b * 2 * C + c); q8[0] += __ldg(partial + (long long)b * 2 * C + C + c); }
+#pragma unroll
+        for (int u = 0; u < 8; ++u) { s += s8[u]; q += q8[u]; }
+    }
     ss[grp][cl] = s; sq[grp][cl] = q;
     __syncthreads();
     if (grp == 0 && c < C) {
@@ -230,9 +258,9 @@ __global__ void __launch_bounds__(kBnThreads) bn_bwd_apply_kernel(const uint4* _
 }
 
 // ---- host ---------------------------------------------------------------------------------------------------------------------
-static int stream_grid(long long work_items, int per_block) {
+static int stream_grid(long long work_items, int per_block, int ctas_per_sm = 4) {
     long long blocks = (work_items + per_block - 1) / per_block;
-    return (int)std::max<long long>(1, std::min<long long>(blocks, (long long)kNumSMs * 4));
+    return (int)std::max<long long>(1, std::min<long long>(blocks, (long long)kNumSMs * ctas_per_sm));
 }
 
 static void check_act(const at::Tensor& t, const char* name) {

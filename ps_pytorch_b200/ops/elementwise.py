@@ -28,7 +28,8 @@ class _ReluFn(torch.autograd.Function):
 
 
 def relu(x):
-    if x.dtype != torch.bfloat16 or x.numel() % 8 or not x.is_non_overlapping_and_dense():
+    dense = x.is_contiguous() or (x.dim() == 4 and x.is_contiguous(memory_format=torch.channels_last))
+    if x.dtype != torch.bfloat16 or x.numel() % 8 or not dense:
         return torch.relu(x)
     return _ReluFn.apply(x)
 

@@ -40,12 +40,22 @@ class _LinearFn(torch.autograd.Function):
         if ctx.relu:
             dy = dy * (y > 0).to(dy.dtype)
         dx = dw = db = None
+        n, m = dy.size(1), dy.size(0)
         if ctx.needs_input_grad[0]:
             # dx[M,K] = dy[M,N] @ W[N,K]  -> TN form needs W^T [K,N] K-major: small matrices, transpose once
-            dx = ext.gemm_tn(dy, weight.t().contiguous(), None, False)
-            count_launch()
+            if n % 8 == 0:
+                dx = ext.gemm_tn(dy, weight.t().contiguous(), None, False)
+                count_launch()
+            else:      # reduction dim (e.g. 10 classes) is not a TMA-legal row pitch: zero-pad it to a multiple of 8
+                pad = (-n) % 8
+                dx = ext.gemm_tn(torch.nn.functional.pad(dy, (0, pad)), torch.nn.functional.pad(weight.t(), (0, pad)).contiguous(), None, False)
+                count_launch()
         if ctx.needs_input_grad[1]:
-            dw = ext.gemm_tn(dy.t().contiguous(), x.t().contiguous(), None, False)   # [N,M] @ [K,M]^T
+            if m % 8 == 0:
+                dw = ext.gemm_tn(dy.t().contiguous(), x.t().contiguous(), None, False)   # [N,M] @ [K,M]^T
+            else:
+                pad = (-m) % 8
+                dw = ext.gemm_tn(torch.nn.functional.pad(dy.t(), (0, pad)).contiguous(), torch.nn.functional.pad(x.t(), (0, pad)).contiguous(), None, False)
             count_launch()
         if ctx.has_bias and ctx.needs_input_grad[2]:
             db = dy.float().sum(0).to(dy.dtype)

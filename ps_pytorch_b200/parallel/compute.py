@@ -30,6 +30,8 @@ class WorkerCompute:
                  zero_grads_in_step: bool = True):
         self.device = torch.device(device)
         self.dtype = dtype
+        if self.device.type == "cuda":
+            torch.backends.cudnn.benchmark = True     # library-path convolutions: let cuDNN pick by measurement
         self.channels_last = (self.device.type == "cuda") if channels_last is None else channels_last
         self.network = network.to(self.device).to(dtype)
         if self.channels_last:

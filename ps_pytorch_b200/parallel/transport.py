@@ -172,8 +172,6 @@ class GlooTransport(Transport):
         self.compress = compress
         self.group = group
         self._step_t = torch.zeros(2, dtype=torch.int64)
-        self._kill_req = None
-        self._kill_buf = torch.zeros(1, dtype=torch.int64)
         self._pending = []     # stale receives still in flight: (work, buffer)
         self._local_push: Optional[torch.Tensor] = None   # colocated worker's gradient
         self._send_reqs = []
@@ -261,10 +259,17 @@ class GlooTransport(Transport):
         optimizer.step(grads=avg)
         self._local_push = None
 
+    def _store(self):
+        from torch.distributed.distributed_c10d import _get_default_store
+        return _get_default_store()
+
     def ps_signal_kill(self, ranks, step):
+        """C10: the kill signal is a key in the rendezvous store (the reference polls MPI tag 77 with Iprobe,
+        ``resnet_split.py:513-520``; gloo has no probe, and a blocked receive would outlive the step)."""
+        st = self._store()
         for r in ranks:
             if r != 0:
-                self._send_reqs.append(dist.isend(torch.tensor([step], dtype=torch.int64), dst=r, tag=TAG_KILL))
+                st.set("psb_kill_r%d" % r, str(int(step)))
 
     # -- worker -------------------------------------------------------------------------------------------
     def worker_fetch(self, weights, timeout_s=0.0):
@@ -303,22 +308,9 @@ class GlooTransport(Transport):
     def worker_poll_kill(self, step):
         if self.rank == 0:
             return False
-        if self._kill_req is None:
-            import threading
-            self._kill_flag = threading.Event()
-
-            def _wait():
-                try:
-                    dist.irecv(self._kill_buf, src=0, tag=TAG_KILL).wait()
-                    self._kill_flag.set()
-                except Exception:
-                    pass
-            self._kill_req = threading.Thread(target=_wait, daemon=True)
-            self._kill_req.start()
-        if self._kill_flag.is_set():
-            s = int(self._kill_buf[0])
-            self._kill_req = None
-            return s == step
+        st, key = self._store(), "psb_kill_r%d" % self.rank
+        if st.check([key]):
+            return int(st.get(key)) == step
         return False
 
     def worker_send_buffers(self, step, flat):

@@ -94,7 +94,7 @@ class BatchLoader:
 
     def __init__(self, dataset: TensorDataset, batch_size: int, shuffle: bool, augment: bool, seed: int = 0,
                  drop_last: bool = False, pin: bool = False, out_dtype: torch.dtype = torch.float32,
-                 channels_last: bool = False):
+                 channels_last: bool = False, prefetch: int = 2):
         self.dataset, self.batch_size, self.shuffle, self.augment = dataset, batch_size, shuffle, augment
         self.drop_last, self.out_dtype, self.channels_last = drop_last, out_dtype, channels_last
         self.gen = torch.Generator().manual_seed(seed)
@@ -104,6 +104,13 @@ class BatchLoader:
         self.pin = pin and torch.cuda.is_available()
         self._bufs = None
         self._flip = 0
+        self.prefetch = prefetch
+        self._nbuf = max(2, prefetch + 2)
+        try:
+            from ..ops import host_ext
+            self._native = host_ext.get() if out_dtype == torch.float32 else None
+        except Exception:
+            self._native = None
 
     def __len__(self):
         n = len(self.dataset)
@@ -117,11 +124,33 @@ class BatchLoader:
             mk = lambda: (torch.empty(b, c, h, w, dtype=self.out_dtype).contiguous(
                 memory_format=torch.channels_last if self.channels_last else torch.contiguous_format).pin_memory(),
                 torch.empty(b, dtype=torch.int64).pin_memory())
-            self._bufs = [mk(), mk()]
-        self._flip ^= 1
+            self._bufs = [mk() for _ in range(self._nbuf)]
+        self._flip = (self._flip + 1) % self._nbuf
         return self._bufs[self._flip]
 
+    def _make_batch_native(self, idx: torch.Tensor):
+        """One multi-threaded C++ pass: gather + reflect-pad crop + flip + normalise into the (pinned) output buffer."""
+        b = idx.numel()
+        c, h, w = self.dataset.images.shape[1:]
+        out = self._out_buffers(b)
+        if out is None:
+            x = torch.empty(b, c, h, w, dtype=torch.float32)
+            if self.channels_last:
+                x = x.contiguous(memory_format=torch.channels_last)
+            out = (x, torch.empty(b, dtype=torch.int64))
+        dx = dy = fl = None
+        if self.augment:
+            dx = torch.randint(0, 9, (b,), generator=self.gen)
+            dy = torch.randint(0, 9, (b,), generator=self.gen)
+            fl = torch.rand(b, generator=self.gen) < 0.5
+        self._native.assemble_batch(self.dataset.images, idx.contiguous(), out[0], self.mean.view(-1).contiguous(),
+                                    self.inv_std.view(-1).contiguous(), dx, dy, fl)
+        torch.index_select(self.dataset.labels, 0, idx, out=out[1])
+        return out
+
     def make_batch(self, idx: torch.Tensor):
+        if self._native is not None:
+            return self._make_batch_native(idx)
         x = self.dataset.images[idx]
         y = self.dataset.labels[idx]
         b, c, h, w = x.shape
@@ -151,9 +180,40 @@ class BatchLoader:
     def __iter__(self):
         n = len(self.dataset)
         order = torch.randperm(n, generator=self.gen) if self.shuffle else torch.arange(n)
-        for i in range(len(self)):
-            idx = order[i * self.batch_size:(i + 1) * self.batch_size]
-            yield self.make_batch(idx)
+        nb = len(self)
+        if self.prefetch <= 0 or nb <= 1:
+            for i in range(nb):
+                yield self.make_batch(order[i * self.batch_size:(i + 1) * self.batch_size])
+        else:
+            # background producer: batches are assembled (GIL released inside the C++ pass) while the step runs
+            import queue
+            import threading
+            q: "queue.Queue" = queue.Queue(maxsize=self.prefetch)
+            stop = threading.Event()
+
+            def produce():
+                try:
+                    for i in range(nb):
+                        if stop.is_set():
+                            return
+                        q.put(self.make_batch(order[i * self.batch_size:(i + 1) * self.batch_size]))
+                    q.put(None)
+                except Exception as e:  # noqa: BLE001
+                    q.put(e)
+            th = threading.Thread(target=produce, daemon=True)
+            th.start()
+            try:
+                while True:
+                    item = q.get()
+                    if item is None:
+                        break
+                    if isinstance(item, Exception):
+                        raise item
+                    yield item
+            finally:
+                stop.set()
+                while not q.empty():
+                    q.get_nowait()
         self.dataset.epochs_completed += 1
 
     # reference API ---------------------------------------------------------------------------------------

@@ -330,22 +330,30 @@ def test_tc_conv_autograd_matches_cudnn(ext):
 
 
 def test_resnet18_step_sm100_vs_library(ext):
-    """One full training step through the sm100 layers must track the library (cuDNN/ATen) path."""
+    """One full training step through the sm100 layers: its gradient must be as close to an fp32 reference of the same
+    network as the bf16 library (cuDNN/ATen) path is (bf16 activations make both noisy; neither may be worse)."""
+    import copy
     from ps_pytorch_b200 import nn as pnn
     from ps_pytorch_b200.models import build_model
     torch.manual_seed(0)
-    m = build_model("ResNet18", 10).cuda().to(torch.bfloat16).to(memory_format=torch.channels_last)
-    x = torch.randn(64, 3, 32, 32, device="cuda").to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
-    y = torch.randint(0, 10, (64,), device="cuda")
+    m32 = build_model("ResNet18", 10).cuda().to(memory_format=torch.channels_last)
+    m = copy.deepcopy(m32).to(torch.bfloat16)
+    with torch.no_grad():                       # identical (bf16-representable) weights in both
+        for p32, p in zip(m32.parameters(), m.parameters()):
+            p32.copy_(p.float())
+    x = torch.randn(128, 3, 32, 32, device="cuda").to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
+    y = torch.randint(0, 10, (128,), device="cuda")
     crit = pnn.CrossEntropyLoss()
+    with pnn.backend("library"):
+        l32 = crit(m32(x.float()), y); l32.backward()
+    ref = torch.cat([p.grad.flatten() for p in m32.parameters()])
     out = {}
     for be in ("library", "sm100"):
         m.zero_grad()
         with pnn.backend(be):
             loss = crit(m(x), y)
             loss.backward()
-        out[be] = (loss.item(), torch.cat([p.grad.float().flatten() for p in m.parameters()]))
-    assert abs(out["sm100"][0] - out["library"][0]) < 0.05
-    a, b = out["sm100"][1], out["library"][1]
-    cos = torch.nn.functional.cosine_similarity(a, b, dim=0).item()
-    assert cos > 0.98, cos
+        g = torch.cat([p.grad.float().flatten() for p in m.parameters()])
+        out[be] = (loss.item(), torch.nn.functional.cosine_similarity(g, ref, dim=0).item())
+    assert abs(out["sm100"][0] - l32.item()) < 0.05, (out, l32.item())
+    assert out["sm100"][1] > 0.9 and out["sm100"][1] > out["library"][1] - 0.02, out

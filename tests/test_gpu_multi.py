@@ -1,0 +1,70 @@
+"""Multi-GPU transport tests (2+ B200s): the NVLink tier must produce the update the gloo tier / a single-process
+fp32 reference produces, in both topologies, with bf16 / fp8 wires, with and without multicast."""
+import os
+import subprocess
+import sys
+
+import pytest
+import torch
+
+pytestmark = [pytest.mark.gpu, pytest.mark.multigpu]
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _run(nprocs, out, extra, env_extra=None, timeout=300):
+    cmd = [sys.executable, "-m", "ps_pytorch_b200.launch", "-n", str(nprocs), "--timeout", str(timeout - 30),
+           os.path.join(ROOT, "tests", "mp_job.py"), "--out", out, "--transport", "nvl", "--device", "cuda", "--dtype", "bf16"] + extra
+    env = dict(os.environ, PYTHONPATH=ROOT)
+    env.update(env_extra or {})
+    r = subprocess.run(cmd, cwd=ROOT, env=env, capture_output=True, text=True, timeout=timeout)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+    return torch.load(out)
+
+
+def _reference(nworkers, steps, bs, network):
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from test_distributed_cpu import _reference as ref
+    return ref(nworkers, steps, bs, network)
+
+
+def _check(res, ref, init, tol_cos=0.97):
+    # compare the *update* (w - w0): bf16 compute makes element-wise equality meaningless, direction must agree
+    d_res = torch.cat([(a - i).flatten() for a, i in zip(res["w"], init)])
+    d_ref = torch.cat([(b - i).flatten() for b, i in zip(ref, init)])
+    cos = torch.nn.functional.cosine_similarity(d_res, d_ref, dim=0).item()
+    rel = ((d_res - d_ref).norm() / d_ref.norm()).item()
+    assert cos > tol_cos, (cos, rel)
+    return cos, rel
+
+
+def _init(network):
+    from ps_pytorch_b200.models import build_model
+    torch.manual_seed(7)
+    return [p.detach().clone() for p in build_model(network, 10).parameters()]
+
+
+@pytest.mark.parametrize("topology,wire,mc", [("ps", "bf16", "1"), ("ps", "fp8", "1"), ("ps", "bf16", "0"), ("sharded", "bf16", "1")])
+def test_nvl_two_gpus_matches_reference(tmp_path, topology, wire, mc):
+    n = min(torch.cuda.device_count(), 2)
+    res = _run(n, str(tmp_path / "w.pt"), ["--steps", "3", "--network", "LeNet", "--bs", "64", "--topology", topology,
+                                           "--grad-dtype", wire, "--colocate", "1", "--backend", "library"],
+               env_extra={"PSB200_MULTICAST": mc})
+    assert res["workers"] == n
+    ref = _reference(n, 3, 64, "LeNet")
+    _check(res, ref, _init("LeNet"), 0.97 if wire != "fp8" else 0.93)
+
+
+def test_nvl_reference_topology_pure_ps(tmp_path):
+    """--no-colocate: rank 0 only serves (the reference's topology)."""
+    n = min(torch.cuda.device_count(), 2)
+    res = _run(n, str(tmp_path / "w.pt"), ["--steps", "3", "--network", "LeNet", "--bs", "64", "--colocate", "0", "--backend", "library"])
+    assert res["workers"] == n - 1
+    _check(res, _reference(n - 1, 3, 64, "LeNet"), _init("LeNet"))
+
+
+def test_nvl_resnet18_sm100_graph(tmp_path):
+    n = min(torch.cuda.device_count(), 2)
+    res = _run(n, str(tmp_path / "w.pt"), ["--steps", "2", "--network", "ResNet18", "--bs", "32", "--colocate", "1", "--graph", "1",
+                                           "--backend", "sm100", "--overlap", "1"])
+    assert res["workers"] == n and all(torch.isfinite(w).all() for w in res["w"])
+    assert len(res["losses"]) == 2 and all(l == l for l in res["losses"])
