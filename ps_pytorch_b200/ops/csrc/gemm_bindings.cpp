@@ -5,7 +5,8 @@
 
 namespace psb {
 const char* tc_gemm_tn(const void*, const void*, void*, const void*, int, int, int, int, cudaStream_t);
-const char* tc_conv_fprop(const void*, const void*, void*, const void*, int, int, int, int, int, int, int, int, int, int, cudaStream_t);
+const char* tc_conv_fprop(const void*, const void*, void*, const void*, const void*, int, int, int, int, int, int, int, int, int, int, cudaStream_t);
+void tc_set_conv_algo(int);
 int tc_check_error();
 
 static const void* opt_ptr(const c10::optional<at::Tensor>& t, int64_t n) {
@@ -27,7 +28,8 @@ at::Tensor gemm_tn(at::Tensor x, at::Tensor w, c10::optional<at::Tensor> bias, b
 }
 
 // x: [NB,Cin,H,W] channels_last; w: [Cout,Cin,R,S] channels_last (physically [Cout][R][S][Cin]); returns channels_last y
-at::Tensor conv_fprop(at::Tensor x, at::Tensor w, c10::optional<at::Tensor> bias, int64_t stride, int64_t pad, bool relu) {
+at::Tensor conv_fprop(at::Tensor x, at::Tensor w, c10::optional<at::Tensor> bias, int64_t stride, int64_t pad, bool relu,
+                      c10::optional<at::Tensor> residual) {
     TORCH_CHECK(x.is_cuda() && x.scalar_type() == at::kBFloat16 && w.scalar_type() == at::kBFloat16 && x.dim() == 4 && w.dim() == 4);
     TORCH_CHECK(x.is_contiguous(at::MemoryFormat::ChannelsLast), "x must be NHWC");
     TORCH_CHECK(w.is_contiguous(at::MemoryFormat::ChannelsLast), "w must be [Cout][R][S][Cin]");
@@ -35,7 +37,13 @@ at::Tensor conv_fprop(at::Tensor x, at::Tensor w, c10::optional<at::Tensor> bias
     TORCH_CHECK(w.size(1) == Cin);
     const int Ho = (H + 2 * pad - R) / stride + 1, Wo = (W + 2 * pad - S) / stride + 1;
     at::Tensor y = at::empty({NB, Cout, Ho, Wo}, x.options().memory_format(at::MemoryFormat::ChannelsLast));
-    const char* e = tc_conv_fprop(x.data_ptr(), w.data_ptr(), y.data_ptr(), opt_ptr(bias, Cout), NB, H, W, Cin, Cout, R, S, (int)stride, (int)pad, relu,
+    const void* rp = nullptr;
+    if (residual.has_value()) {
+        TORCH_CHECK(residual->scalar_type() == at::kBFloat16 && residual->sizes() == y.sizes() && residual->is_contiguous(at::MemoryFormat::ChannelsLast),
+                    "residual must be an NHWC bf16 tensor of the output shape");
+        rp = residual->data_ptr();
+    }
+    const char* e = tc_conv_fprop(x.data_ptr(), w.data_ptr(), y.data_ptr(), opt_ptr(bias, Cout), rp, NB, H, W, Cin, Cout, R, S, (int)stride, (int)pad, relu,
                                   at::cuda::getCurrentCUDAStream());
     TORCH_CHECK(e == nullptr, "tc_conv_fprop: ", e);
     return y;
@@ -57,7 +65,9 @@ int64_t tc_error() { return tc_check_error(); }
 
 void bind_gemm(pybind11::module_& m) {
     m.def("gemm_tn", &psb::gemm_tn);
-    m.def("conv_fprop", &psb::conv_fprop);
+    m.def("conv_fprop", &psb::conv_fprop, pybind11::arg("x"), pybind11::arg("w"), pybind11::arg("bias"), pybind11::arg("stride"), pybind11::arg("pad"),
+          pybind11::arg("relu"), pybind11::arg("residual") = c10::optional<at::Tensor>());
+    m.def("tc_set_conv_algo", &psb::tc_set_conv_algo);
     m.def("conv_unsupported_reason", &psb::conv_unsupported_reason);
     m.def("tc_error", &psb::tc_error);
 }

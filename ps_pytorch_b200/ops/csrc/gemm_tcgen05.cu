@@ -42,7 +42,9 @@ struct TcParams {
     int Hout, Wout, NB, stride, pad, S, cblocks;
     int BW, BH, BNI, tiles_w, tiles_h;
     const __nv_bfloat16* bias;
+    const __nv_bfloat16* residual;      // optional [M,N] tensor added in the epilogue (dgrad + skip-gradient fusion)
     int relu;
+    int R, halo_w, a_stage_bytes;       // halo kernel: filter rows, halo box width, bytes per A stage
     __nv_bfloat16* C;
     int* err;                          // set to 1 if a barrier wait timed out (protocol bug), never hang
 };
@@ -55,6 +57,61 @@ template <int BN> struct TcCfg {
     static constexpr int kTmemCols = 2 * BN;                      // two accumulator stages (power of two: 128 / 256)
     static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
 };
+
+// TMEM accumulator quarter -> (+bias) (+residual) (ReLU) -> bf16 -> global.  Thread `lane` of warp quarter q owns one output row.
+template <int BN>
+__device__ __forceinline__ void epilogue_tile(const TcParams& p, uint32_t tmem_base, int acc, int q, int lane, long long out_row, int nt) {
+    const bool vec_ok = (p.N % 8) == 0;
+    __nv_bfloat16* crow = p.C + out_row * (long long)p.N + (long long)nt * BN;
+    const __nv_bfloat16* rrow = p.residual ? p.residual + out_row * (long long)p.N + (long long)nt * BN : nullptr;
+#pragma unroll 1
+    for (int c0 = 0; c0 < BN; c0 += 32) {
+        uint32_t v[32];
+        tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + c0), v);
+        tmem_ld_wait();
+        const int col0 = nt * BN + c0;
+        if (out_row >= 0 && col0 < p.N) {
+            float f[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
+            if (p.bias) {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) if (col0 + j < p.N) f[j] += __bfloat162float(p.bias[col0 + j]);
+            }
+            const bool full = vec_ok && col0 + 32 <= p.N;
+            if (rrow) {
+                if (full) {
+#pragma unroll
+                    for (int j = 0; j < 32; j += 8) {
+                        const uint4 rv = *reinterpret_cast<const uint4*>(rrow + c0 + j);
+                        const uint32_t w[4] = {rv.x, rv.y, rv.z, rv.w};
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) { f[j + 2 * k] += __uint_as_float(w[k] << 16); f[j + 2 * k + 1] += __uint_as_float(w[k] & 0xffff0000u); }
+                    }
+                } else {
+                    for (int j = 0; j < 32; ++j) if (col0 + j < p.N) f[j] += __bfloat162float(rrow[c0 + j]);
+                }
+            }
+            if (p.relu) {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.f);
+            }
+            if (full) {
+#pragma unroll
+                for (int j = 0; j < 32; j += 8) {
+                    uint4 o;
+                    __nv_bfloat162 h0 = __floats2bfloat162_rn(f[j], f[j + 1]), h1 = __floats2bfloat162_rn(f[j + 2], f[j + 3]);
+                    __nv_bfloat162 h2 = __floats2bfloat162_rn(f[j + 4], f[j + 5]), h3 = __floats2bfloat162_rn(f[j + 6], f[j + 7]);
+                    o.x = *reinterpret_cast<uint32_t*>(&h0); o.y = *reinterpret_cast<uint32_t*>(&h1);
+                    o.z = *reinterpret_cast<uint32_t*>(&h2); o.w = *reinterpret_cast<uint32_t*>(&h3);
+                    *reinterpret_cast<uint4*>(crow + c0 + j) = o;
+                }
+            } else {
+                for (int j = 0; j < 32; ++j) if (col0 + j < p.N) crow[c0 + j] = __float2bfloat16_rn(f[j]);
+            }
+        }
+    }
+}
 
 template <int BN>
 __global__ void __launch_bounds__(kThreads, 1)
@@ -141,7 +198,6 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         // ===================================================== epilogue (4 warps, one TMEM lane quarter each)
         const int q = warp & 3;
         int acc = 0; uint32_t acc_phase = 0;
-        const bool vec_ok = (p.N % 8) == 0;
         for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
             const int mt = tile / p.n_tiles_n, nt = tile % p.n_tiles_n;
             const int row_in_tile = q * 32 + lane;
@@ -157,40 +213,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
             }
             if (!mbar_wait(tmem_full + acc, acc_phase)) { if (lane == 0) *p.err = 4; return; }
             tc_fence_after();
-            __nv_bfloat16* crow = p.C + out_row * (long long)p.N + (long long)nt * BN;
-#pragma unroll 1
-            for (int c0 = 0; c0 < BN; c0 += 32) {
-                uint32_t v[32];
-                tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + c0), v);
-                tmem_ld_wait();
-                const int col0 = nt * BN + c0;
-                if (out_row >= 0 && col0 < p.N) {
-                    float f[32];
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
-                    if (p.bias) {
-#pragma unroll
-                        for (int j = 0; j < 32; ++j) if (col0 + j < p.N) f[j] += __bfloat162float(p.bias[col0 + j]);
-                    }
-                    if (p.relu) {
-#pragma unroll
-                        for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.f);
-                    }
-                    if (vec_ok && col0 + 32 <= p.N) {
-#pragma unroll
-                        for (int j = 0; j < 32; j += 8) {
-                            uint4 o;
-                            __nv_bfloat162 h0 = __floats2bfloat162_rn(f[j], f[j + 1]), h1 = __floats2bfloat162_rn(f[j + 2], f[j + 3]);
-                            __nv_bfloat162 h2 = __floats2bfloat162_rn(f[j + 4], f[j + 5]), h3 = __floats2bfloat162_rn(f[j + 6], f[j + 7]);
-                            o.x = *reinterpret_cast<uint32_t*>(&h0); o.y = *reinterpret_cast<uint32_t*>(&h1);
-                            o.z = *reinterpret_cast<uint32_t*>(&h2); o.w = *reinterpret_cast<uint32_t*>(&h3);
-                            *reinterpret_cast<uint4*>(crow + c0 + j) = o;
-                        }
-                    } else {
-                        for (int j = 0; j < 32; ++j) if (col0 + j < p.N) crow[c0 + j] = __float2bfloat16_rn(f[j]);
-                    }
-                }
-            }
+            epilogue_tile<BN>(p, tmem_base, acc, q, lane, out_row, nt);
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(tmem_empty + acc);
@@ -198,6 +221,133 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         }
     }
     // ---- teardown
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    if (warp == 2) tmem_dealloc(tmem_base, Cfg::kTmemCols);
+}
+
+// ===================================================================================================================
+// Halo variant for stride-1 RxS convolutions on feature maps with W >= 16, H >= 8.
+//
+// The per-tap kernel above re-fetches the A tile from L2 once per filter tap (9x for 3x3); measured on B200 it is
+// bound by L2->SM bandwidth (1.2 GB of smem fills per ResNet layer at ~12 TB/s ~ 100 us, profiles/run3_conv.md).
+// Here a tile is 8 rows x 16 columns of ONE image and, per 64-channel block, the input patch with its halo is loaded
+// ONCE as a single TMA box of (64 ch, 16 rows, 16+S-1 columns) with H as the fast pixel dimension, so the smem buffer
+// is [column][row][64 ch]: 128-byte rows, 16 rows (2048 B) per image column.  With the GEMM rows ordered m = bw*8 + bh,
+// the A operand of filter tap (r,s) is the *shifted window* that starts at byte ((s*16 + r) * 128) of that buffer:
+// 8 consecutive rows form one UMMA core group, groups are 2048 B apart (SBO), and because the window starts off the
+// 1024-byte swizzle pattern boundary the descriptor carries base_offset = r.  A traffic drops from R*S*16 KB to
+// (16+S-1)*2 KB per (tile, channel block): 4x less for 3x3.  B (weights) streams per (tap, channel block) as before.
+template <int BN> struct HaloCfg {
+    static constexpr int kAStages = 2;
+    static constexpr int kBStages = BN == 64 ? 10 : 6;
+    static constexpr int kBBytes = BN * BK * 2;
+    static constexpr int kTmemCols = 2 * BN;
+};
+
+template <int BN>
+__global__ void __launch_bounds__(kThreads, 1)
+tc_conv_halo_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, const TcParams p) {
+    using Cfg = HaloCfg<BN>;
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* smem_a = smem;
+    uint8_t* smem_b = smem + Cfg::kAStages * p.a_stage_bytes;
+    uint64_t* a_full = reinterpret_cast<uint64_t*>(smem_b + Cfg::kBStages * Cfg::kBBytes);
+    uint64_t* a_empty = a_full + Cfg::kAStages;
+    uint64_t* b_full = a_empty + Cfg::kAStages;
+    uint64_t* b_empty = b_full + Cfg::kBStages;
+    uint64_t* tmem_full = b_empty + Cfg::kBStages;
+    uint64_t* tmem_empty = tmem_full + 2;
+    uint32_t* tmem_base_smem = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (warp == 0 && lane == 0) { prefetch_tmap(&tmap_a); prefetch_tmap(&tmap_b); }
+    if (warp == 1 && lane == 0) {
+        for (int s = 0; s < Cfg::kAStages; ++s) { mbar_init(a_full + s, 1); mbar_init(a_empty + s, 1); }
+        for (int s = 0; s < Cfg::kBStages; ++s) { mbar_init(b_full + s, 1); mbar_init(b_empty + s, 1); }
+        for (int s = 0; s < 2; ++s) { mbar_init(tmem_full + s, 1); mbar_init(tmem_empty + s, 4); }
+        fence_barrier_init();
+    }
+    if (warp == 2) tmem_alloc(tmem_base_smem, Cfg::kTmemCols);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_base_smem;
+    const int n_tiles = p.n_tiles_m * p.n_tiles_n;
+    const int taps = p.R * p.S;
+    const int Cin = p.cblocks * BK;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            int as = 0; uint32_t aph = 0; int bs = 0; uint32_t bph = 0;
+            for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+                const int mt = tile / p.n_tiles_n, nt = tile % p.n_tiles_n;
+                const int tw = mt % p.tiles_w, th = (mt / p.tiles_w) % p.tiles_h, n = mt / (p.tiles_w * p.tiles_h);
+                for (int cb = 0; cb < p.cblocks; ++cb) {
+                    if (!mbar_wait(a_empty + as, aph ^ 1)) { *p.err = 11; return; }
+                    mbar_arrive_expect_tx(a_full + as, p.a_stage_bytes);
+                    // tensor map dims are (C, H, W, N): H is the fast pixel dimension of the smem image
+                    tma_load_4d(smem_a + as * p.a_stage_bytes, &tmap_a, a_full + as, cb * BK, th * 8 - p.pad, tw * 16 - p.pad, n);
+                    if (++as == Cfg::kAStages) { as = 0; aph ^= 1; }
+                    for (int tap = 0; tap < taps; ++tap) {
+                        if (!mbar_wait(b_empty + bs, bph ^ 1)) { *p.err = 12; return; }
+                        mbar_arrive_expect_tx(b_full + bs, Cfg::kBBytes);
+                        tma_load_2d(smem_b + bs * Cfg::kBBytes, &tmap_b, b_full + bs, tap * Cin + cb * BK, nt * BN);
+                        if (++bs == Cfg::kBStages) { bs = 0; bph ^= 1; }
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            constexpr uint32_t idesc = umma_idesc_bf16(BM, BN, 0, 0);
+            int as = 0; uint32_t aph = 0; int bs = 0; uint32_t bph = 0; int acc = 0; uint32_t acc_phase = 0;
+            for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+                if (!mbar_wait(tmem_empty + acc, acc_phase ^ 1)) { *p.err = 13; return; }
+                tc_fence_after();
+                const uint32_t tmem_d = tmem_base + acc * BN;
+                for (int cb = 0; cb < p.cblocks; ++cb) {
+                    if (!mbar_wait(a_full + as, aph)) { *p.err = 14; return; }
+                    const uint32_t sa0 = smem_u32(smem_a + as * p.a_stage_bytes);
+                    for (int tap = 0; tap < taps; ++tap) {
+                        if (!mbar_wait(b_full + bs, bph)) { *p.err = 15; return; }
+                        tc_fence_after();
+                        const int r = tap / p.S, s = tap % p.S;
+                        const uint32_t sa = sa0 + (uint32_t)((s * 16 + r) * 128);
+                        const uint32_t sb = smem_u32(smem_b + bs * Cfg::kBBytes);
+#pragma unroll
+                        for (int k = 0; k < BK / 16; ++k)
+                            tc_mma_bf16(tmem_d, umma_desc_k_sw128_off(sa + k * 32, 2048), umma_desc_k_sw128(sb + k * 32), idesc, (cb | tap | k) != 0);
+                        tc_commit(b_empty + bs);
+                        if (++bs == Cfg::kBStages) { bs = 0; bph ^= 1; }
+                    }
+                    tc_commit(a_empty + as);
+                    if (++as == Cfg::kAStages) { as = 0; aph ^= 1; }
+                }
+                tc_commit(tmem_full + acc);
+                if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+            }
+        }
+    } else if (warp >= kEpiWarp0) {
+        const int q = warp & 3;
+        int acc = 0; uint32_t acc_phase = 0;
+        for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+            const int mt = tile / p.n_tiles_n, nt = tile % p.n_tiles_n;
+            const int tw = mt % p.tiles_w, th = (mt / p.tiles_w) % p.tiles_h, n = mt / (p.tiles_w * p.tiles_h);
+            const int m = q * 32 + lane;                       // GEMM row: m = bw*8 + bh
+            const int h = th * 8 + (m & 7), w = tw * 16 + (m >> 3);
+            const long long out_row = (h < p.Hout && w < p.Wout) ? ((long long)n * p.Hout + h) * p.Wout + w : -1;
+            if (!mbar_wait(tmem_full + acc, acc_phase)) { if (lane == 0) *p.err = 16; return; }
+            tc_fence_after();
+            epilogue_tile<BN>(p, tmem_base, acc, q, lane, out_row, nt);
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(tmem_empty + acc);
+            if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+        }
+    }
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -263,6 +413,25 @@ static const char* launch(const CUtensorMap& ta, const CUtensorMap& tb, const Tc
     return cudaGetLastError() == cudaSuccess ? nullptr : "kernel launch failed";
 }
 
+template <int BN>
+static const char* launch_halo(const CUtensorMap& ta, const CUtensorMap& tb, const TcParams& p, cudaStream_t stream) {
+    using Cfg = HaloCfg<BN>;
+    const int smem_bytes = Cfg::kAStages * p.a_stage_bytes + Cfg::kBStages * Cfg::kBBytes + 1024 + 512;
+    if (smem_bytes > 227 * 1024) return "halo tile does not fit in shared memory";
+    static int attr = 0;
+    if (attr < smem_bytes) {
+        if (cudaFuncSetAttribute(tc_conv_halo_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes) != cudaSuccess) return "cannot raise dynamic smem";
+        attr = smem_bytes;
+    }
+    const int tiles = p.n_tiles_m * p.n_tiles_n;
+    const int grid = tiles < num_sms() ? tiles : num_sms();
+    tc_conv_halo_kernel<BN><<<grid, kThreads, smem_bytes, stream>>>(ta, tb, p);
+    return cudaGetLastError() == cudaSuccess ? nullptr : "kernel launch failed";
+}
+
+static int g_conv_algo = -1;     // -1 auto, 0 per-tap, 1 halo
+void tc_set_conv_algo(int a) { g_conv_algo = a; }
+
 // C[M,N] = A[M,K] B[N,K]^T ; lda/ldb = K (dense rows)
 const char* tc_gemm_tn(const void* A, const void* B, void* C, const void* bias, int M, int N, int K, int relu, cudaStream_t stream) {
     if (K % 8) return "K must be a multiple of 8";
@@ -281,11 +450,33 @@ const char* tc_gemm_tn(const void* A, const void* B, void* C, const void* bias, 
 }
 
 // Y[NB,Hout,Wout,Cout] = conv(X[NB,Hin,Win,Cin], Wt[Cout][R][S][Cin]), NHWC bf16
-const char* tc_conv_fprop(const void* X, const void* Wt, void* Y, const void* bias, int NB, int Hin, int Win, int Cin, int Cout,
+const char* tc_conv_fprop(const void* X, const void* Wt, void* Y, const void* bias, const void* residual, int NB, int Hin, int Win, int Cin, int Cout,
                           int R, int S, int stride, int pad, int relu, cudaStream_t stream) {
     if (Cin % 64) return "Cin must be a multiple of 64";
     if (Cout % 8) return "Cout must be a multiple of 8";
     const int Hout = (Hin + 2 * pad - R) / stride + 1, Wout = (Win + 2 * pad - S) / stride + 1;
+    const bool halo_ok = stride == 1 && R * S > 1 && R <= 8 && Wout >= 16 && Hout >= 8 && (16 + S - 1) <= 256;
+    if ((g_conv_algo == 1 || (g_conv_algo == -1 && halo_ok)) && halo_ok) {
+        const int BN = Cout <= 64 ? 64 : 128;
+        CUtensorMap ta, tb;
+        // dims (C, H, W, N): strides in bytes for H, W, N
+        uint64_t da[4] = {(uint64_t)Cin, (uint64_t)Hin, (uint64_t)Win, (uint64_t)NB};
+        uint64_t sa[3] = {(uint64_t)Win * Cin * 2, (uint64_t)Cin * 2, (uint64_t)Hin * Win * Cin * 2};
+        uint32_t boxa[4] = {BK, 16, (uint32_t)(16 + S - 1), 1}, esa[4] = {1, 1, 1, 1};
+        const int Ktot = R * S * Cin;
+        uint64_t db[2] = {(uint64_t)Ktot, (uint64_t)Cout}, sb[1] = {(uint64_t)Ktot * 2};
+        uint32_t boxb[2] = {BK, (uint32_t)BN}, esb[2] = {1, 1};
+        if (const char* e = make_tmap(&ta, X, 4, da, sa, boxa, esa)) return e;
+        if (const char* e = make_tmap(&tb, Wt, 2, db, sb, boxb, esb)) return e;
+        TcParams p{};
+        p.M = NB * Hout * Wout; p.N = Cout; p.num_kb = Ktot / BK; p.mode = 2;
+        p.Hout = Hout; p.Wout = Wout; p.NB = NB; p.stride = 1; p.pad = pad; p.S = S; p.R = R; p.cblocks = Cin / BK;
+        p.tiles_w = (Wout + 15) / 16; p.tiles_h = (Hout + 7) / 8;
+        p.n_tiles_m = p.tiles_w * p.tiles_h * NB; p.n_tiles_n = (Cout + BN - 1) / BN;
+        p.halo_w = 16 + S - 1; p.a_stage_bytes = p.halo_w * 16 * 128;
+        p.bias = (const __nv_bfloat16*)bias; p.residual = (const __nv_bfloat16*)residual; p.relu = relu; p.C = (__nv_bfloat16*)Y; p.err = err_word();
+        return BN == 64 ? launch_halo<64>(ta, tb, p, stream) : launch_halo<128>(ta, tb, p, stream);
+    }
     // tile rectangle: BW = largest power of two <= min(Wout,32), then rows, then images, product 128
     int BW = 1; while (BW * 2 <= Wout && BW * 2 <= 32) BW *= 2;
     int BH = 1; while (BH * 2 <= Hout && BW * BH * 2 <= 128) BH *= 2;
@@ -310,7 +501,7 @@ const char* tc_conv_fprop(const void* X, const void* Wt, void* Y, const void* bi
     p.tiles_w = (Wout + BW - 1) / BW; p.tiles_h = (Hout + BH - 1) / BH;
     const int tiles_n_img = (NB + BNI - 1) / BNI;
     p.n_tiles_m = p.tiles_w * p.tiles_h * tiles_n_img; p.n_tiles_n = (Cout + BN - 1) / BN;
-    p.bias = (const __nv_bfloat16*)bias; p.relu = relu; p.C = (__nv_bfloat16*)Y; p.err = err_word();
+    p.bias = (const __nv_bfloat16*)bias; p.residual = (const __nv_bfloat16*)residual; p.relu = relu; p.C = (__nv_bfloat16*)Y; p.err = err_word();
     return BN == 64 ? launch<64>(ta, tb, p, stream) : launch<128>(ta, tb, p, stream);
 }
 

@@ -90,6 +90,12 @@ __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.
 __device__ __forceinline__ uint64_t umma_desc_k_sw128(uint32_t saddr) {
     return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)1 << 16) | ((uint64_t)(1024 >> 4) << 32) | ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
 }
+// Same, for a tile whose first row is NOT on a 1024-byte swizzle-pattern boundary (a shifted window into a larger
+// swizzled buffer): `sbo_bytes` between 8-row groups, base_offset = (start >> 7) & 7 tells the unit the row phase.
+__device__ __forceinline__ uint64_t umma_desc_k_sw128_off(uint32_t saddr, uint32_t sbo_bytes) {
+    return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)1 << 16) | ((uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32) | ((uint64_t)1 << 46) |
+           ((uint64_t)((saddr >> 7) & 7) << 49) | ((uint64_t)2 << 61);
+}
 // MN-major operand tile, 128-byte swizzle: each K index is one 128-byte row of 64 MN-contiguous bf16; 8 K-rows per
 // 1024-byte atom (SBO = 1024); 64-element MN groups are `lbo_bytes` apart.
 __device__ __forceinline__ uint64_t umma_desc_mn_sw128(uint32_t saddr, uint32_t lbo_bytes) {

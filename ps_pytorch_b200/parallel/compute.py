@@ -149,11 +149,16 @@ class WorkerCompute:
         self._static_x, self._static_y = xs.clone(memory_format=torch.preserve_format), ys.clone()
         s = torch.cuda.Stream()
         s.wait_stream(torch.cuda.current_stream())
+        saved = [b.detach().clone() for b in self.network.buffers()]      # warm-up must not advance BN statistics
         with torch.cuda.stream(s):
             for _ in range(3):   # warm-up off-graph: cuDNN autotune, lazy inits
                 self._step_body(self._static_x, self._static_y)
         torch.cuda.current_stream().wait_stream(s)
         torch.cuda.synchronize()
+        with torch.no_grad():
+            for b, v in zip(self.network.buffers(), saved):
+                b.copy_(v)
+        self.grads.flat.zero_()                                          # ... nor leave warm-up gradients in the push source
         self.timer.resolve()
         self._graph = torch.cuda.CUDAGraph()
         self.timer = _NullTimer()

@@ -58,7 +58,7 @@ class NvlTransport(Transport):
         self.topology = topology
         self.wire = WIRE[grad_dtype]
         self.grad_dtype = grad_dtype
-        self.timeout_s = float(os.environ.get("PSB200_TIMEOUT_S", timeout_s or 30.0))
+        self.timeout_s = float(os.environ.get("PSB200_TIMEOUT_S", timeout_s or 120.0))
         self.ext = ops.require()
         T = layout.total
         self.T = T
@@ -141,8 +141,8 @@ class NvlTransport(Transport):
             return
         assert weights.flat.data_ptr() == self.arena.local_ptr + self.off_w, "PS low-precision copy must live in the arena"
         d = self._dests()
-        use_mc = self.arena.mc_ptr and len(d) == self.world
-        nfl = self.NB if self.topology == "ps" else self.world
+        use_mc = self.arena.mc_ptr and len(d) == self.world_size
+        nfl = self.NB if self.topology == "ps" else self.world_size
         self.ext.bcast(self.arena.local_ptr + self.off_w, [self._wptr(r) for r in d], (self.arena.mc_ptr + self.off_w) if use_mc else 0,
                        self.T * 2, [self._flag(r, self.F_WREADY) for r in d], nfl, self.p_psstep, 0, self.p_counters + 4 * 2 * MAXB)
         ops.count_launch()
@@ -185,7 +185,7 @@ class NvlTransport(Transport):
             wready = [self._flag(r, self.F_WREADY + 8 * self.rank) for r in self._dests()]
         take = min(P, (k + 1) if strict_reference else k)
         d = self._dests()
-        use_mc = bool(self.arena.mc_ptr) and len(d) == self.world
+        use_mc = bool(self.arena.mc_ptr) and len(d) == self.world_size
         if kind == 0:
             s0, s1, s2 = fs["buf"], None, None
         else:
@@ -217,7 +217,7 @@ class NvlTransport(Transport):
     # ---- worker side -----------------------------------------------------------------------------------------------------
     def worker_fetch(self, weights, timeout_s=0.0):
         """Enqueue the device-side wait for this step's weights; the host does not block."""
-        n = self.NB if self.topology == "ps" else self.world
+        n = self.NB if self.topology == "ps" else self.world_size
         self.ext.wait_flag(self.arena.local_ptr + self.off_flags + self.F_WREADY, n, self.p_wstep, self.p_err, self.timeout_s)
         ops.count_launch()
         self._host_wstep += 1

@@ -298,13 +298,18 @@ def test_tc_gemm(ext, M, N, K, bias, relu):
     (8, 64, 32, 32, 64, 3, 1, 1), (4, 64, 16, 16, 128, 3, 1, 1), (16, 128, 8, 8, 128, 3, 1, 1), (32, 256, 4, 4, 512, 3, 1, 1),
     (64, 512, 2, 2, 512, 3, 1, 1), (3, 64, 32, 32, 64, 1, 1, 0), (5, 128, 16, 16, 256, 1, 1, 0), (2, 64, 56, 56, 64, 3, 1, 1),
     (8, 64, 32, 32, 128, 3, 2, 1), (8, 64, 32, 32, 128, 1, 2, 0), (4, 128, 16, 16, 256, 3, 2, 1), (2, 64, 7, 7, 64, 3, 1, 1)])
-def test_tc_conv_fprop(ext, shape):
+@pytest.mark.parametrize("algo", [0, 1])
+def test_tc_conv_fprop(ext, shape, algo):
+    """algo 0 = per-tap implicit GEMM, 1 = halo (shifted-window descriptors; silently falls back to per-tap when the
+    shape is not eligible, which is what the dispatcher does in production)."""
     NB, Cin, H, W, Cout, R, st, pad = shape
+    ext.tc_set_conv_algo(algo)
     torch.manual_seed(0)
     x = (torch.randn(NB, Cin, H, W, device="cuda") * 0.5).to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
     w = (torch.randn(Cout, Cin, R, R, device="cuda") * (1.0 / math.sqrt(Cin * R * R))).to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
     y = ext.conv_fprop(x, w, None, st, pad, False)
     torch.cuda.synchronize()
+    ext.tc_set_conv_algo(-1)
     assert ext.tc_error() == 0
     ref = F.conv2d(x.float(), w.float(), None, st, pad)
     assert y.shape == ref.shape
@@ -357,3 +362,13 @@ def test_resnet18_step_sm100_vs_library(ext):
         out[be] = (loss.item(), torch.nn.functional.cosine_similarity(g, ref, dim=0).item())
     assert abs(out["sm100"][0] - l32.item()) < 0.05, (out, l32.item())
     assert out["sm100"][1] > 0.9 and out["sm100"][1] > out["library"][1] - 0.02, out
+
+
+def test_tc_conv_residual_epilogue(ext):
+    x = (torch.randn(4, 64, 16, 16, device="cuda") * 0.5).to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
+    w = (torch.randn(128, 64, 3, 3, device="cuda") / 24).to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
+    r = torch.randn(4, 128, 16, 16, device="cuda").to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
+    b = torch.randn(128, device="cuda").to(torch.bfloat16)
+    y = ext.conv_fprop(x, w, b, 1, 1, True, r)
+    ref = F.relu(F.conv2d(x.float(), w.float(), b.float(), 1, 1) + r.float())
+    assert (y.float() - ref).abs().max().item() < 0.05
