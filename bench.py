@@ -26,6 +26,14 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 
+def _tc_conv():
+    try:
+        from ps_pytorch_b200.ops import conv as C
+        return C.tc_conv_enabled()
+    except Exception:
+        return False
+
+
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -211,6 +219,7 @@ def main():
                           "grad_wire": a.grad_dtype, "optimizer": a.optimizer + " momentum 0.9, fused in the PS kernel", "backend": a.backend,
                           "transport": job.comm.name + ":" + getattr(getattr(job.comm, "arena", None), "backend", "-"),
                           "cuda_graph": not a.no_graph,
+                          "conv": "tcgen05 implicit-GEMM (ours)" if _tc_conv() else "cuDNN (library); all other layers + PS kernels ours",
                           "l2": "inputs rotate over 8 distinct pinned host batches; per-step activation working set (~3 GB) >> 126 MB L2"},
                "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "wall_ms_per_step": wall_ms / a.steps,
                "final_loss": float(lt[0])}

@@ -27,8 +27,8 @@ class _Features(tnn.Sequential):
         while i < len(mods):
             m = mods[i]
             nxt = mods[i + 1] if i + 1 < len(mods) else None
-            if isinstance(m, nn.BatchNorm2d) and isinstance(nxt, tnn.ReLU):
-                x = m(x, relu=True)
+            if isinstance(m, (nn.BatchNorm2d, nn.Conv2d)) and isinstance(nxt, tnn.ReLU):
+                x = m(x, relu=True)          # BN+ReLU in one pass / bias+ReLU in the conv epilogue
                 i += 2
             else:
                 x = m(x)

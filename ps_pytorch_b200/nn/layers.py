@@ -19,14 +19,16 @@ from .backend import use_sm100, note_fallback
 
 
 class Conv2d(nn.Conv2d):
-    def forward(self, x):
+    def forward(self, x, relu: bool = False):
+        """``relu=True`` fuses bias + ReLU into the convolution epilogue (VGG's conv→ReLU pairs)."""
         if use_sm100(x):
             from ..ops import conv as _conv
             why = _conv.unsupported_reason(x, self.weight, self.stride, self.padding, self.dilation, self.groups)
             if why is None:
-                return _conv.conv2d(x, self.weight, self.bias, self.stride, self.padding)
+                return _conv.conv2d(x, self.weight, self.bias, self.stride, self.padding, relu)
             note_fallback("conv2d", why)
-        return F.conv2d(x, self.weight, self.bias, self.stride, self.padding, self.dilation, self.groups)
+        y = F.conv2d(x, self.weight, self.bias, self.stride, self.padding, self.dilation, self.groups)
+        return F.relu(y) if relu else y
 
 
 class Linear(nn.Linear):

@@ -12,12 +12,24 @@ import torch
 from . import count_launch, require
 from ..nn.backend import note_fallback
 
-_ENABLED = os.environ.get("PSB200_TC_CONV", "1") != "0"
+# Measured on B200 (profiles/run4_conv_microbench.md) the per-tap tcgen05 kernel reaches 0.38-0.76 PFLOP/s where cuDNN's
+# sm100 kernels reach 0.75-1.34, so the *default* convolution path is the library one and the hand-written kernel is opt-in
+# (PSB200_TC_CONV=1 / set_tc_conv(True)) until it wins; every other layer of the sm100 backend is ours regardless.
+_ENABLED = os.environ.get("PSB200_TC_CONV", "0") != "0"
+
+
+def set_tc_conv(on: bool) -> None:
+    global _ENABLED
+    _ENABLED = bool(on)
+
+
+def tc_conv_enabled() -> bool:
+    return _ENABLED
 
 
 def unsupported_reason(x, weight, stride, padding, dilation, groups):
     if not _ENABLED:
-        return "disabled by PSB200_TC_CONV=0"
+        return "tcgen05 conv is opt-in (PSB200_TC_CONV=1); cuDNN is faster today"
     ext = require()
     if not hasattr(ext, "conv_fprop"):
         return "tcgen05 implicit-GEMM conv not built"
@@ -35,20 +47,23 @@ def _krsc(w):
 
 class _ConvFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, x, weight, bias, stride, pad):
+    def forward(ctx, x, weight, bias, stride, pad, relu):
         ext = require()
         x = x.contiguous(memory_format=torch.channels_last)
-        y = ext.conv_fprop(x, _krsc(weight), bias, stride, pad, False)
+        y = ext.conv_fprop(x, _krsc(weight), bias, stride, pad, relu)
         count_launch()
-        ctx.save_for_backward(x, weight)
-        ctx.stride, ctx.pad, ctx.has_bias = stride, pad, bias is not None
+        ctx.save_for_backward(x, weight, y if relu else None)
+        ctx.stride, ctx.pad, ctx.has_bias, ctx.relu = stride, pad, bias is not None, relu
         return y
 
     @staticmethod
     def backward(ctx, dy):
-        x, weight = ctx.saved_tensors
+        x, weight, y = ctx.saved_tensors
         ext = require()
         dy = dy.contiguous(memory_format=torch.channels_last)
+        if ctx.relu:
+            dy = ext.relu_backward(dy, y)
+            count_launch()
         s, p = ctx.stride, ctx.pad
         r = weight.size(2)
         dx = dw = db = None
@@ -69,8 +84,8 @@ class _ConvFn(torch.autograd.Function):
                 dw = gw
         if ctx.has_bias and ctx.needs_input_grad[2]:
             db = dy.float().sum((0, 2, 3)).to(dy.dtype)
-        return dx, dw, db, None, None
+        return dx, dw, db, None, None, None
 
 
-def conv2d(x, weight, bias, stride, padding):
-    return _ConvFn.apply(x, weight, bias, int(stride[0]), int(padding[0]))
+def conv2d(x, weight, bias, stride, padding, relu=False):
+    return _ConvFn.apply(x, weight, bias, int(stride[0]), int(padding[0]), bool(relu))

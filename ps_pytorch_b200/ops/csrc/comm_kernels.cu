@@ -220,7 +220,7 @@ __global__ void __launch_bounds__(256) reduce_update_kernel(RUArgs a) {
                 for (int j = 0; j < 8; ++j) g[j] += f[j];
             }
             float wf[8], x0[8], x1[8], x2[8];
-            {
+            if (hp.kind != 2) {
                 uint4 p = ld_v4(a.w + i), q = ld_v4(a.w + i + 4);
                 wf[0] = __uint_as_float(p.x); wf[1] = __uint_as_float(p.y); wf[2] = __uint_as_float(p.z); wf[3] = __uint_as_float(p.w);
                 wf[4] = __uint_as_float(q.x); wf[5] = __uint_as_float(q.y); wf[6] = __uint_as_float(q.z); wf[7] = __uint_as_float(q.w);
@@ -234,7 +234,11 @@ __global__ void __launch_bounds__(256) reduce_update_kernel(RUArgs a) {
                 st_v4(ptr + i, make_uint4(__float_as_uint(o[0]), __float_as_uint(o[1]), __float_as_uint(o[2]), __float_as_uint(o[3])));
                 st_v4(ptr + i + 4, make_uint4(__float_as_uint(o[4]), __float_as_uint(o[5]), __float_as_uint(o[6]), __float_as_uint(o[7])));
             };
-            if (hp.kind == 0) {
+            if (hp.kind == 2) {
+                // all-reduce mode (DDP): no optimizer, the averaged gradient itself is stored back to every peer
+#pragma unroll
+                for (int j = 0; j < 8; ++j) wf[j] = g[j] * a.inv_div;
+            } else if (hp.kind == 0) {
                 if (hp.momentum != 0.f && !first) ldf(a.s0, x0);
 #pragma unroll
                 for (int j = 0; j < 8; ++j) wf[j] = sgd_update(wf[j], g[j] * a.inv_div, x0[j], hp, first);
@@ -247,7 +251,7 @@ __global__ void __launch_bounds__(256) reduce_update_kernel(RUArgs a) {
                 stf(a.s0, x0); stf(a.s1, x1);
                 if (a.s2) stf(a.s2, x2);
             }
-            stf(a.w, wf);
+            if (hp.kind != 2) stf(a.w, wf);
             // broadcast the fresh compute copy: one multicast store through the switch, or D peer stores
             const uint4 lp = pack8(wf);
             if (a.mc_dst) {

@@ -7,6 +7,7 @@ namespace psb {
 const char* tc_gemm_tn(const void*, const void*, void*, const void*, int, int, int, int, cudaStream_t);
 const char* tc_conv_fprop(const void*, const void*, void*, const void*, const void*, int, int, int, int, int, int, int, int, int, int, cudaStream_t);
 void tc_set_conv_algo(int);
+void tc_set_halo_desc_mode(int);
 int tc_check_error();
 
 static const void* opt_ptr(const c10::optional<at::Tensor>& t, int64_t n) {
@@ -68,6 +69,7 @@ void bind_gemm(pybind11::module_& m) {
     m.def("conv_fprop", &psb::conv_fprop, pybind11::arg("x"), pybind11::arg("w"), pybind11::arg("bias"), pybind11::arg("stride"), pybind11::arg("pad"),
           pybind11::arg("relu"), pybind11::arg("residual") = c10::optional<at::Tensor>());
     m.def("tc_set_conv_algo", &psb::tc_set_conv_algo);
+    m.def("tc_set_halo_desc_mode", &psb::tc_set_halo_desc_mode);
     m.def("conv_unsupported_reason", &psb::conv_unsupported_reason);
     m.def("tc_error", &psb::tc_error);
 }

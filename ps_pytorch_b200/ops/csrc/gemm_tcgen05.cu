@@ -45,6 +45,7 @@ struct TcParams {
     const __nv_bfloat16* residual;      // optional [M,N] tensor added in the epilogue (dgrad + skip-gradient fusion)
     int relu;
     int R, halo_w, a_stage_bytes;       // halo kernel: filter rows, halo box width, bytes per A stage
+    int desc_mode;
     __nv_bfloat16* C;
     int* err;                          // set to 1 if a barrier wait timed out (protocol bug), never hang
 };
@@ -319,7 +320,11 @@ tc_conv_halo_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                         const uint32_t sb = smem_u32(smem_b + bs * Cfg::kBBytes);
 #pragma unroll
                         for (int k = 0; k < BK / 16; ++k)
-                            tc_mma_bf16(tmem_d, umma_desc_k_sw128_off(sa + k * 32, 2048), umma_desc_k_sw128(sb + k * 32), idesc, (cb | tap | k) != 0);
+                            {
+                            uint64_t ad = umma_desc_k_sw128_off(sa + k * 32, 2048);
+                            if (p.desc_mode == 1) ad &= ~((uint64_t)7 << 49);
+                            tc_mma_bf16(tmem_d, ad, umma_desc_k_sw128(sb + k * 32), idesc, (cb | tap | k) != 0);
+                        }
                         tc_commit(b_empty + bs);
                         if (++bs == Cfg::kBStages) { bs = 0; bph ^= 1; }
                     }
@@ -429,7 +434,9 @@ static const char* launch_halo(const CUtensorMap& ta, const CUtensorMap& tb, con
     return cudaGetLastError() == cudaSuccess ? nullptr : "kernel launch failed";
 }
 
-static int g_conv_algo = -1;     // -1 auto, 0 per-tap, 1 halo
+static int g_conv_algo = -1;     // -1 auto (= per-tap until the halo variant is validated on hardware), 0 per-tap, 1 halo
+static int g_halo_desc_mode = 0;  // experiment switch: 0 = base_offset from the start address, 1 = base_offset 0
+void tc_set_halo_desc_mode(int m) { g_halo_desc_mode = m; }
 void tc_set_conv_algo(int a) { g_conv_algo = a; }
 
 // C[M,N] = A[M,K] B[N,K]^T ; lda/ldb = K (dense rows)
@@ -456,7 +463,7 @@ const char* tc_conv_fprop(const void* X, const void* Wt, void* Y, const void* bi
     if (Cout % 8) return "Cout must be a multiple of 8";
     const int Hout = (Hin + 2 * pad - R) / stride + 1, Wout = (Win + 2 * pad - S) / stride + 1;
     const bool halo_ok = stride == 1 && R * S > 1 && R <= 8 && Wout >= 16 && Hout >= 8 && (16 + S - 1) <= 256;
-    if ((g_conv_algo == 1 || (g_conv_algo == -1 && halo_ok)) && halo_ok) {
+    if (g_conv_algo == 1 && halo_ok) {
         const int BN = Cout <= 64 ? 64 : 128;
         CUtensorMap ta, tb;
         // dims (C, H, W, N): strides in bytes for H, W, N
@@ -473,7 +480,7 @@ const char* tc_conv_fprop(const void* X, const void* Wt, void* Y, const void* bi
         p.Hout = Hout; p.Wout = Wout; p.NB = NB; p.stride = 1; p.pad = pad; p.S = S; p.R = R; p.cblocks = Cin / BK;
         p.tiles_w = (Wout + 15) / 16; p.tiles_h = (Hout + 7) / 8;
         p.n_tiles_m = p.tiles_w * p.tiles_h * NB; p.n_tiles_n = (Cout + BN - 1) / BN;
-        p.halo_w = 16 + S - 1; p.a_stage_bytes = p.halo_w * 16 * 128;
+        p.halo_w = 16 + S - 1; p.a_stage_bytes = p.halo_w * 16 * 128; p.desc_mode = g_halo_desc_mode;
         p.bias = (const __nv_bfloat16*)bias; p.residual = (const __nv_bfloat16*)residual; p.relu = relu; p.C = (__nv_bfloat16*)Y; p.err = err_word();
         return BN == 64 ? launch_halo<64>(ta, tb, p, stream) : launch_halo<128>(ta, tb, p, stream);
     }

@@ -282,6 +282,40 @@ class NvlTransport(Transport):
         dst.copy_(flat.float())
         self.ext.set_word(self._flag(0, self.F_BUFS), int(step))
 
+    def gather_master(self, master: FlatBuffer) -> None:
+        """Sharded topology: every rank holds the authoritative fp32 master only for its shard.  Collective (all ranks):
+        afterwards every rank's ``master`` is complete (used by the checkpoint writer; rare, goes through gloo)."""
+        if self.topology != "sharded" or self.world_size == 1:
+            return
+        torch.cuda.synchronize(self.device)
+        for r, (lo, hi) in enumerate(self.shards):
+            t = master.flat[lo:hi].detach().cpu() if r == self.rank else torch.empty(hi - lo, dtype=torch.float32)
+            dist.broadcast(t, src=r)
+            if r != self.rank:
+                master.flat[lo:hi].copy_(t)
+
+    # ---- all-reduce (DDP) ---------------------------------------------------------------------------------------------------
+    def all_reduce_grads(self, grads: FlatBuffer):
+        """In-place mean of the gradient arenas over all ranks: raise "ready" on every peer, then each rank reduces its
+        shard from all peers (P2P loads) and stores the mean back into every peer's arena (kind = 2: no optimizer)."""
+        assert self.topology == "sharded" and grads.dtype == torch.bfloat16
+        assert grads.flat.data_ptr() == self.arena.local_ptr + self.off_grads
+        if getattr(self, "_ar_hp", None) is None:
+            self._ar_hp = self.ext.make_hp(0.0, 0.0, 0.0, 0.0, False, 0.0, 0.0, 0.0, False, 2, 0).to(self.device)
+            self._ar_w = torch.zeros(8, dtype=torch.float32, device=self.device)     # unused master pointer
+        self.worker_fetch(None)                         # previous round's stores into our arena have landed
+        self._raise_ready(self._my_slot())
+        d = self.worker_ranks
+        lo, hi = self.shards[self.rank]
+        self.ext.reduce_update([self.arena.peer_ptrs[r] + self.off_grads for r in d], [], len(d), 1.0 / len(d), 0,
+                               self.arena.local_ptr + self.off_flags + self.F_GREADY, self.p_psstep, [lo], [hi], self._ar_w, None, None, None,
+                               self._ar_hp.data_ptr(), [self.arena.peer_ptrs[r] + self.off_grads for r in d], 0,
+                               [self._flag(r, self.F_WREADY + 8 * self.rank) for r in d], self.p_counters, self.p_err, self.timeout_s, True)
+        ops.count_launch()
+        self.ext.add_step(self.p_wstep, 1)
+        # results are complete for the caller once every owner has published its shard
+        self.ext.wait_flag(self.arena.local_ptr + self.off_flags + self.F_WREADY, self.world_size, self.p_wstep, self.p_err, self.timeout_s)
+
     # ---- misc --------------------------------------------------------------------------------------------------------------
     def check_error(self):
         e = int(self.ctl[2].item())

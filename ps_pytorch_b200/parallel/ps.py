@@ -181,6 +181,10 @@ class SyncReplicasMaster_NN(object):
 
     def _save_model(self, file_path=None):
         """Single designated writer: PS master weights + BN statistics fetched from the first worker."""
+        if hasattr(self.comm, "gather_master"):
+            self.comm.gather_master(self.master)              # sharded topology: collect the other owners' shards
+            if self.comm.rank != 0:
+                return                                        # single writer
         bufs = self.comm.ps_recv_buffers(self.cur_step, self._n_buffers) if self.comm is not None else None
         if bufs is not None and bufs.numel() == self._n_buffers and self._n_buffers:
             load_buffers_flat(self.network, bufs.to(self._device))

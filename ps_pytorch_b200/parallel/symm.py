@@ -140,6 +140,20 @@ class SymmetricArena:
         t.zero_()
         self.backend = "torch-symm" + ("+mc" if self.mc_ptr else "")
 
+    def close(self):
+        """Unmap peer mappings and release the local allocation (VMM backend).  The multicast VA, if any, stays reserved."""
+        if getattr(self, "backend", "").startswith("vmm") and not getattr(self, "_closed", False):
+            torch.cuda.synchronize(self.device)
+            if dist.is_initialized():
+                dist.barrier()
+            ext = ops.require()
+            for va, h in self._imports:
+                ext.vmm_unmap(va, h, self.size)
+            if not self.mc_ptr:      # memory bound to a live multicast object must stay mapped
+                self._buf = None
+                ext.vmm_unmap(self.local_ptr, self._handle, self.size)
+            self._closed = True
+
     # ---- views ------------------------------------------------------------------------------------------------
     def view(self, offset: int, nbytes: int, dtype: torch.dtype) -> torch.Tensor:
         assert offset % 16 == 0 and offset + nbytes <= self.size

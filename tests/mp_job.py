@@ -54,6 +54,8 @@ def main():
         if l is not None and os.environ.get("PSB_DEBUG"): print("rank", rank, "step", s, float(l), flush=True)
         if l is not None:
             losses.append(float(l))
+    if job.master is not None and hasattr(job.comm, "gather_master"):
+        job.comm.gather_master(job.master.master)
     job.close()
     if job.master is not None and rank == 0:
         if a.device.startswith("cuda"):
