@@ -97,7 +97,20 @@ __device__ __forceinline__ void epilogue_tile(const TcParams& p, uint32_t tmem_b
 #pragma unroll
                 for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.f);
             }
-            if (full) {
+            if (full && (p.N % 16) == 0) {
+                // 256-bit stores (STG.E.ENL2.256): every thread writes whole 32-byte sectors of its output row
+#pragma unroll
+                for (int j = 0; j < 32; j += 16) {
+                    uint32_t o[8];
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) {
+                        __nv_bfloat162 h = __floats2bfloat162_rn(f[j + 2 * k], f[j + 2 * k + 1]);
+                        o[k] = *reinterpret_cast<uint32_t*>(&h);
+                    }
+                    asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(crow + c0 + j), "r"(o[0]), "r"(o[1]), "r"(o[2]), "r"(o[3]),
+                                 "r"(o[4]), "r"(o[5]), "r"(o[6]), "r"(o[7]) : "memory");
+                }
+            } else if (full) {
 #pragma unroll
                 for (int j = 0; j < 32; j += 8) {
                     uint4 o;
@@ -141,59 +154,60 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     const int n_tiles = p.n_tiles_m * p.n_tiles_n;
 
     if (warp == 0) {
-        // ===================================================== TMA producer
-        if (lane == 0) {
-            int stage = 0; uint32_t phase = 0;
-            for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-                const int mt = tile / p.n_tiles_n, nt = tile % p.n_tiles_n;
-                int n0 = 0, h0 = 0, w0 = 0;
-                if (p.mode == 1) {
-                    const int tw = mt % p.tiles_w, th = (mt / p.tiles_w) % p.tiles_h, tn = mt / (p.tiles_w * p.tiles_h);
-                    n0 = tn * p.BNI; h0 = th * p.BH; w0 = tw * p.BW;
-                }
-                for (int kb = 0; kb < p.num_kb; ++kb) {
-                    if (!mbar_wait(empty_bar + stage, phase ^ 1)) { *p.err = 1; return; }
-                    uint8_t* sa = smem + stage * Cfg::kStageBytes;
-                    uint8_t* sb = sa + Cfg::kABytes;
+        // ===================================================== TMA producer (whole warp runs the loop; one elected lane issues)
+        int stage = 0; uint32_t phase = 0;
+        for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+            const int mt = tile / p.n_tiles_n, nt = tile % p.n_tiles_n;
+            int n0 = 0, h0 = 0, w0 = 0;
+            if (p.mode == 1) {
+                const int tw = mt % p.tiles_w, th = (mt / p.tiles_w) % p.tiles_h, tn = mt / (p.tiles_w * p.tiles_h);
+                n0 = tn * p.BNI; h0 = th * p.BH; w0 = tw * p.BW;
+            }
+            int tap = 0, cb = 0;
+            for (int kb = 0; kb < p.num_kb; ++kb) {
+                if (!mbar_wait(empty_bar + stage, phase ^ 1)) { *p.err = 1; return; }
+                uint8_t* sa = smem + stage * Cfg::kStageBytes;
+                uint8_t* sb = sa + Cfg::kABytes;
+                if (elect_one()) {
                     mbar_arrive_expect_tx(full_bar + stage, Cfg::kStageBytes);
                     if (p.mode == 0) {
                         tma_load_2d(sa, &tmap_a, full_bar + stage, kb * BK, mt * BM);
                     } else {
-                        const int tap = kb / p.cblocks, cb = kb % p.cblocks;
-                        const int r = tap / p.S, s = tap % p.S;
+                        const int r = tap / p.S, s = tap - r * p.S;
                         tma_load_4d(sa, &tmap_a, full_bar + stage, cb * BK, w0 * p.stride + s - p.pad, h0 * p.stride + r - p.pad, n0);
                     }
                     tma_load_2d(sb, &tmap_b, full_bar + stage, kb * BK, nt * BN);
-                    if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
                 }
+                __syncwarp();
+                if (++cb == p.cblocks) { cb = 0; ++tap; }
+                if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
             }
         }
     } else if (warp == 1) {
-        // ===================================================== MMA issuer
-        if (lane == 0) {
-            constexpr uint32_t idesc = umma_idesc_bf16(BM, BN, 0, 0);
-            int stage = 0; uint32_t phase = 0; int acc = 0; uint32_t acc_phase = 0;
-            for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-                if (!mbar_wait(tmem_empty + acc, acc_phase ^ 1)) { *p.err = 2; return; }
+        // ===================================================== MMA issuer (whole warp waits; one elected lane issues)
+        constexpr uint32_t idesc = umma_idesc_bf16(BM, BN, 0, 0);
+        int stage = 0; uint32_t phase = 0; int acc = 0; uint32_t acc_phase = 0;
+        for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+            if (!mbar_wait(tmem_empty + acc, acc_phase ^ 1)) { *p.err = 2; return; }
+            tc_fence_after();
+            const uint32_t tmem_d = tmem_base + acc * BN;
+            for (int kb = 0; kb < p.num_kb; ++kb) {
+                if (!mbar_wait(full_bar + stage, phase)) { *p.err = 3; return; }
                 tc_fence_after();
-                const uint32_t tmem_d = tmem_base + acc * BN;
-                for (int kb = 0; kb < p.num_kb; ++kb) {
-                    if (!mbar_wait(full_bar + stage, phase)) { *p.err = 3; return; }
-                    tc_fence_after();
-                    const uint32_t sa = smem_u32(smem + stage * Cfg::kStageBytes);
-                    const uint32_t sb = sa + Cfg::kABytes;
+                const uint32_t sa = smem_u32(smem + stage * Cfg::kStageBytes);
+                const uint32_t sb = sa + Cfg::kABytes;
+                if (elect_one()) {
 #pragma unroll
-                    for (int k = 0; k < BK / 16; ++k) {
-                        const uint64_t ad = umma_desc_k_sw128(sa + k * 32);
-                        const uint64_t bd = umma_desc_k_sw128(sb + k * 32);
-                        tc_mma_bf16(tmem_d, ad, bd, idesc, (kb | k) != 0);
-                    }
+                    for (int k = 0; k < BK / 16; ++k)
+                        tc_mma_bf16(tmem_d, umma_desc_k_sw128(sa + k * 32), umma_desc_k_sw128(sb + k * 32), idesc, (kb | k) != 0);
                     tc_commit(empty_bar + stage);                   // smem slot reusable once these MMAs retire
-                    if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
                 }
-                tc_commit(tmem_full + acc);                          // accumulator complete -> epilogue
-                if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+                __syncwarp();
+                if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
             }
+            if (elect_one()) tc_commit(tmem_full + acc);             // accumulator complete -> epilogue
+            __syncwarp();
+            if (++acc == 2) { acc = 0; acc_phase ^= 1; }
         }
     } else if (warp >= kEpiWarp0) {
         // ===================================================== epilogue (4 warps, one TMEM lane quarter each)
@@ -240,10 +254,13 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
 // 8 consecutive rows form one UMMA core group, groups are 2048 B apart (SBO), and because the window starts off the
 // 1024-byte swizzle pattern boundary the descriptor carries base_offset = r.  A traffic drops from R*S*16 KB to
 // (16+S-1)*2 KB per (tile, channel block): 4x less for 3x3.  B (weights) streams per (tap, channel block) as before.
+// Weights stream one filter ROW per TMA: a 3-D box (64 k, BN out-channels, S taps) = S consecutive K-major B tiles, so the
+// producer issues R+1 bulk copies per channel block instead of R*S+1 and the MMA warp waits on R barriers (the first
+// version issued one 8-16 KB copy per tap and the MMA warp spent a third of its time waiting on them, profiles/run7_*.md).
 template <int BN> struct HaloCfg {
     static constexpr int kAStages = 2;
-    static constexpr int kBStages = BN == 64 ? 10 : 6;
-    static constexpr int kBBytes = BN * BK * 2;
+    static constexpr int kBStages = BN == 64 ? 4 : 3;
+    static constexpr int kBTapBytes = BN * BK * 2;
     static constexpr int kTmemCols = 2 * BN;
 };
 
@@ -255,7 +272,8 @@ tc_conv_halo_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint8_t* smem_a = smem;
     uint8_t* smem_b = smem + Cfg::kAStages * p.a_stage_bytes;
-    uint64_t* a_full = reinterpret_cast<uint64_t*>(smem_b + Cfg::kBStages * Cfg::kBBytes);
+    const int b_stage_bytes = p.S * Cfg::kBTapBytes;
+    uint64_t* a_full = reinterpret_cast<uint64_t*>(smem_b + Cfg::kBStages * b_stage_bytes);
     uint64_t* a_empty = a_full + Cfg::kAStages;
     uint64_t* b_full = a_empty + Cfg::kAStages;
     uint64_t* b_empty = b_full + Cfg::kBStages;
@@ -277,63 +295,67 @@ tc_conv_halo_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     tc_fence_after();
     const uint32_t tmem_base = *tmem_base_smem;
     const int n_tiles = p.n_tiles_m * p.n_tiles_n;
-    const int taps = p.R * p.S;
-    const int Cin = p.cblocks * BK;
 
     if (warp == 0) {
-        if (lane == 0) {
-            int as = 0; uint32_t aph = 0; int bs = 0; uint32_t bph = 0;
-            for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-                const int mt = tile / p.n_tiles_n, nt = tile % p.n_tiles_n;
-                const int tw = mt % p.tiles_w, th = (mt / p.tiles_w) % p.tiles_h, n = mt / (p.tiles_w * p.tiles_h);
-                for (int cb = 0; cb < p.cblocks; ++cb) {
-                    if (!mbar_wait(a_empty + as, aph ^ 1)) { *p.err = 11; return; }
+        int as = 0; uint32_t aph = 0; int bs = 0; uint32_t bph = 0;
+        for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+            const int mt = tile / p.n_tiles_n, nt = tile % p.n_tiles_n;
+            const int tw = mt % p.tiles_w, th = (mt / p.tiles_w) % p.tiles_h, n = mt / (p.tiles_w * p.tiles_h);
+            for (int cb = 0; cb < p.cblocks; ++cb) {
+                if (!mbar_wait(a_empty + as, aph ^ 1)) { *p.err = 11; return; }
+                if (elect_one()) {
                     mbar_arrive_expect_tx(a_full + as, p.a_stage_bytes);
                     // tensor map dims are (C, H, W, N): H is the fast pixel dimension of the smem image
                     tma_load_4d(smem_a + as * p.a_stage_bytes, &tmap_a, a_full + as, cb * BK, th * 8 - p.pad, tw * 16 - p.pad, n);
-                    if (++as == Cfg::kAStages) { as = 0; aph ^= 1; }
-                    for (int tap = 0; tap < taps; ++tap) {
-                        if (!mbar_wait(b_empty + bs, bph ^ 1)) { *p.err = 12; return; }
-                        mbar_arrive_expect_tx(b_full + bs, Cfg::kBBytes);
-                        tma_load_2d(smem_b + bs * Cfg::kBBytes, &tmap_b, b_full + bs, tap * Cin + cb * BK, nt * BN);
-                        if (++bs == Cfg::kBStages) { bs = 0; bph ^= 1; }
+                }
+                __syncwarp();
+                if (++as == Cfg::kAStages) { as = 0; aph ^= 1; }
+                for (int r = 0; r < p.R; ++r) {
+                    if (!mbar_wait(b_empty + bs, bph ^ 1)) { *p.err = 12; return; }
+                    if (elect_one()) {
+                        mbar_arrive_expect_tx(b_full + bs, b_stage_bytes);
+                        tma_load_3d(smem_b + bs * b_stage_bytes, &tmap_b, b_full + bs, cb * BK, nt * BN, r * p.S);
                     }
+                    __syncwarp();
+                    if (++bs == Cfg::kBStages) { bs = 0; bph ^= 1; }
                 }
             }
         }
     } else if (warp == 1) {
-        if (lane == 0) {
-            constexpr uint32_t idesc = umma_idesc_bf16(BM, BN, 0, 0);
-            int as = 0; uint32_t aph = 0; int bs = 0; uint32_t bph = 0; int acc = 0; uint32_t acc_phase = 0;
-            for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-                if (!mbar_wait(tmem_empty + acc, acc_phase ^ 1)) { *p.err = 13; return; }
-                tc_fence_after();
-                const uint32_t tmem_d = tmem_base + acc * BN;
-                for (int cb = 0; cb < p.cblocks; ++cb) {
-                    if (!mbar_wait(a_full + as, aph)) { *p.err = 14; return; }
-                    const uint32_t sa0 = smem_u32(smem_a + as * p.a_stage_bytes);
-                    for (int tap = 0; tap < taps; ++tap) {
-                        if (!mbar_wait(b_full + bs, bph)) { *p.err = 15; return; }
-                        tc_fence_after();
-                        const int r = tap / p.S, s = tap % p.S;
-                        const uint32_t sa = sa0 + (uint32_t)((s * 16 + r) * 128);
-                        const uint32_t sb = smem_u32(smem_b + bs * Cfg::kBBytes);
+        constexpr uint32_t idesc = umma_idesc_bf16(BM, BN, 0, 0);
+        int as = 0; uint32_t aph = 0; int bs = 0; uint32_t bph = 0; int acc = 0; uint32_t acc_phase = 0;
+        for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+            if (!mbar_wait(tmem_empty + acc, acc_phase ^ 1)) { *p.err = 13; return; }
+            tc_fence_after();
+            const uint32_t tmem_d = tmem_base + acc * BN;
+            for (int cb = 0; cb < p.cblocks; ++cb) {
+                if (!mbar_wait(a_full + as, aph)) { *p.err = 14; return; }
+                const uint32_t sa0 = smem_u32(smem_a + as * p.a_stage_bytes);
+                for (int r = 0; r < p.R; ++r) {
+                    if (!mbar_wait(b_full + bs, bph)) { *p.err = 15; return; }
+                    tc_fence_after();
+                    const uint32_t sb0 = smem_u32(smem_b + bs * b_stage_bytes);
+                    if (elect_one()) {
+                        for (int s = 0; s < p.S; ++s) {
+                            // shifted window: the swizzle XOR is a function of the absolute smem address, so base_offset stays 0
+                            const uint32_t sa = sa0 + (uint32_t)((s * 16 + r) * 128);
+                            const uint32_t sb = sb0 + (uint32_t)(s * Cfg::kBTapBytes);
 #pragma unroll
-                        for (int k = 0; k < BK / 16; ++k)
-                            {
-                            uint64_t ad = umma_desc_k_sw128_off(sa + k * 32, 2048);
-                            if (p.desc_mode == 1) ad &= ~((uint64_t)7 << 49);
-                            tc_mma_bf16(tmem_d, ad, umma_desc_k_sw128(sb + k * 32), idesc, (cb | tap | k) != 0);
+                            for (int k = 0; k < BK / 16; ++k)
+                                tc_mma_bf16(tmem_d, umma_desc_k_sw128_sbo(sa + k * 32, 2048), umma_desc_k_sw128(sb + k * 32), idesc, (cb | r | s | k) != 0);
                         }
                         tc_commit(b_empty + bs);
-                        if (++bs == Cfg::kBStages) { bs = 0; bph ^= 1; }
                     }
-                    tc_commit(a_empty + as);
-                    if (++as == Cfg::kAStages) { as = 0; aph ^= 1; }
+                    __syncwarp();
+                    if (++bs == Cfg::kBStages) { bs = 0; bph ^= 1; }
                 }
-                tc_commit(tmem_full + acc);
-                if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+                if (elect_one()) tc_commit(a_empty + as);
+                __syncwarp();
+                if (++as == Cfg::kAStages) { as = 0; aph ^= 1; }
             }
+            if (elect_one()) tc_commit(tmem_full + acc);
+            __syncwarp();
+            if (++acc == 2) { acc = 0; acc_phase ^= 1; }
         }
     } else if (warp >= kEpiWarp0) {
         const int q = warp & 3;
@@ -421,7 +443,7 @@ static const char* launch(const CUtensorMap& ta, const CUtensorMap& tb, const Tc
 template <int BN>
 static const char* launch_halo(const CUtensorMap& ta, const CUtensorMap& tb, const TcParams& p, cudaStream_t stream) {
     using Cfg = HaloCfg<BN>;
-    const int smem_bytes = Cfg::kAStages * p.a_stage_bytes + Cfg::kBStages * Cfg::kBBytes + 1024 + 512;
+    const int smem_bytes = Cfg::kAStages * p.a_stage_bytes + Cfg::kBStages * p.S * Cfg::kBTapBytes + 1024 + 512;
     if (smem_bytes > 227 * 1024) return "halo tile does not fit in shared memory";
     static int attr = 0;
     if (attr < smem_bytes) {
@@ -435,8 +457,7 @@ static const char* launch_halo(const CUtensorMap& ta, const CUtensorMap& tb, con
 }
 
 static int g_conv_algo = -1;     // -1 auto (= per-tap until the halo variant is validated on hardware), 0 per-tap, 1 halo
-static int g_halo_desc_mode = 0;  // experiment switch: 0 = base_offset from the start address, 1 = base_offset 0
-void tc_set_halo_desc_mode(int m) { g_halo_desc_mode = m; }
+void tc_set_halo_desc_mode(int) {}   // kept for scripts/conv_one.py; the base_offset experiment is settled (always 0)
 void tc_set_conv_algo(int a) { g_conv_algo = a; }
 
 // C[M,N] = A[M,K] B[N,K]^T ; lda/ldb = K (dense rows)
@@ -471,16 +492,17 @@ const char* tc_conv_fprop(const void* X, const void* Wt, void* Y, const void* bi
         uint64_t sa[3] = {(uint64_t)Win * Cin * 2, (uint64_t)Cin * 2, (uint64_t)Hin * Win * Cin * 2};
         uint32_t boxa[4] = {BK, 16, (uint32_t)(16 + S - 1), 1}, esa[4] = {1, 1, 1, 1};
         const int Ktot = R * S * Cin;
-        uint64_t db[2] = {(uint64_t)Ktot, (uint64_t)Cout}, sb[1] = {(uint64_t)Ktot * 2};
-        uint32_t boxb[2] = {BK, (uint32_t)BN}, esb[2] = {1, 1};
+        // weights [Cout][R*S][Cin] as a 3-D tensor (Cin, Cout, taps): one box = S taps of one filter row
+        uint64_t db[3] = {(uint64_t)Cin, (uint64_t)Cout, (uint64_t)(R * S)}, sb[2] = {(uint64_t)Ktot * 2, (uint64_t)Cin * 2};
+        uint32_t boxb[3] = {BK, (uint32_t)BN, (uint32_t)S}, esb[3] = {1, 1, 1};
         if (const char* e = make_tmap(&ta, X, 4, da, sa, boxa, esa)) return e;
-        if (const char* e = make_tmap(&tb, Wt, 2, db, sb, boxb, esb)) return e;
+        if (const char* e = make_tmap(&tb, Wt, 3, db, sb, boxb, esb)) return e;
         TcParams p{};
         p.M = NB * Hout * Wout; p.N = Cout; p.num_kb = Ktot / BK; p.mode = 2;
         p.Hout = Hout; p.Wout = Wout; p.NB = NB; p.stride = 1; p.pad = pad; p.S = S; p.R = R; p.cblocks = Cin / BK;
         p.tiles_w = (Wout + 15) / 16; p.tiles_h = (Hout + 7) / 8;
         p.n_tiles_m = p.tiles_w * p.tiles_h * NB; p.n_tiles_n = (Cout + BN - 1) / BN;
-        p.halo_w = 16 + S - 1; p.a_stage_bytes = p.halo_w * 16 * 128; p.desc_mode = g_halo_desc_mode;
+        p.halo_w = 16 + S - 1; p.a_stage_bytes = p.halo_w * 16 * 128;
         p.bias = (const __nv_bfloat16*)bias; p.residual = (const __nv_bfloat16*)residual; p.relu = relu; p.C = (__nv_bfloat16*)Y; p.err = err_word();
         return BN == 64 ? launch_halo<64>(ta, tb, p, stream) : launch_halo<128>(ta, tb, p, stream);
     }

@@ -13,6 +13,15 @@ namespace psb { namespace tc {
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
+// One lane of a converged warp, chosen by the hardware.  Unlike `lane == 0` (a divergent branch, after which ptxas must
+// move every uniform-datapath operand of UTCHMMA / UTMALDG through ELECT / R2UR loops -- measured: ~230 SASS instructions
+// per K-block in the MMA issue loop, profiles/run5_conv_ncu.md), code under elect.sync keeps its operands in uniform registers.
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+    return pred != 0;
+}
+
 // ---- mbarrier ---------------------------------------------------------------------------------------------------
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
@@ -37,6 +46,7 @@ __device__ __forceinline__ bool mbar_wait(uint64_t* bar, uint32_t parity) {
     unsigned long long t0, t1;
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
     for (;;) {
+#pragma unroll 1
         for (int it = 0; it < 64; ++it)
             if (mbar_try_wait(bar, parity)) return true;
         asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
@@ -51,6 +61,10 @@ __device__ __forceinline__ void prefetch_tmap(const CUtensorMap* m) {
 __device__ __forceinline__ void tma_load_2d(void* smem, const CUtensorMap* m, uint64_t* bar, int c0, int c1) {
     asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
                  ::"r"(smem_u32(smem)), "l"(m), "r"(smem_u32(bar)), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(void* smem, const CUtensorMap* m, uint64_t* bar, int c0, int c1, int c2) {
+    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+                 ::"r"(smem_u32(smem)), "l"(m), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2) : "memory");
 }
 __device__ __forceinline__ void tma_load_4d(void* smem, const CUtensorMap* m, uint64_t* bar, int c0, int c1, int c2, int c3) {
     asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
@@ -91,10 +105,12 @@ __device__ __forceinline__ uint64_t umma_desc_k_sw128(uint32_t saddr) {
     return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)1 << 16) | ((uint64_t)(1024 >> 4) << 32) | ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
 }
 // Same, for a tile whose first row is NOT on a 1024-byte swizzle-pattern boundary (a shifted window into a larger
-// swizzled buffer): `sbo_bytes` between 8-row groups, base_offset = (start >> 7) & 7 tells the unit the row phase.
-__device__ __forceinline__ uint64_t umma_desc_k_sw128_off(uint32_t saddr, uint32_t sbo_bytes) {
+// swizzled buffer): `sbo_bytes` between 8-row groups.  base_offset stays 0: measured on B200, the swizzle XOR is taken from
+// absolute smem address bits [7,10), so a window that starts r rows into the pattern needs no phase hint (setting
+// base_offset = r produced wrong products for every r != 0).
+__device__ __forceinline__ uint64_t umma_desc_k_sw128_sbo(uint32_t saddr, uint32_t sbo_bytes) {
     return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)1 << 16) | ((uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32) | ((uint64_t)1 << 46) |
-           ((uint64_t)((saddr >> 7) & 7) << 49) | ((uint64_t)2 << 61);
+           ((uint64_t)2 << 61);
 }
 // MN-major operand tile, 128-byte swizzle: each K index is one 128-byte row of 64 MN-contiguous bf16; 8 K-rows per
 // 1024-byte atom (SBO = 1024); 64-element MN groups are `lbo_bytes` apart.

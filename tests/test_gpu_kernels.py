@@ -298,7 +298,7 @@ def test_tc_gemm(ext, M, N, K, bias, relu):
     (8, 64, 32, 32, 64, 3, 1, 1), (4, 64, 16, 16, 128, 3, 1, 1), (16, 128, 8, 8, 128, 3, 1, 1), (32, 256, 4, 4, 512, 3, 1, 1),
     (64, 512, 2, 2, 512, 3, 1, 1), (3, 64, 32, 32, 64, 1, 1, 0), (5, 128, 16, 16, 256, 1, 1, 0), (2, 64, 56, 56, 64, 3, 1, 1),
     (8, 64, 32, 32, 128, 3, 2, 1), (8, 64, 32, 32, 128, 1, 2, 0), (4, 128, 16, 16, 256, 3, 2, 1), (2, 64, 7, 7, 64, 3, 1, 1)])
-@pytest.mark.parametrize("algo", [0, pytest.param(1, marks=pytest.mark.xfail(reason="halo descriptors not validated yet", strict=False))])
+@pytest.mark.parametrize("algo", [0, 1])
 def test_tc_conv_fprop(ext, shape, algo):
     """algo 0 = per-tap implicit GEMM, 1 = halo (shifted-window descriptors; silently falls back to per-tap when the
     shape is not eligible, which is what the dispatcher does in production)."""
