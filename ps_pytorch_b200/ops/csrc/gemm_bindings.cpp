@@ -8,6 +8,8 @@ const char* tc_gemm_tn(const void*, const void*, void*, const void*, int, int, i
 const char* tc_conv_fprop(const void*, const void*, void*, const void*, const void*, int, int, int, int, int, int, int, int, int, int, cudaStream_t);
 void tc_set_conv_algo(int);
 void tc_set_halo_desc_mode(int);
+void tc_set_halo_cluster(int);
+void tc_set_halo_resident(int);
 int tc_check_error();
 
 static const void* opt_ptr(const c10::optional<at::Tensor>& t, int64_t n) {
@@ -70,6 +72,8 @@ void bind_gemm(pybind11::module_& m) {
           pybind11::arg("relu"), pybind11::arg("residual") = c10::optional<at::Tensor>());
     m.def("tc_set_conv_algo", &psb::tc_set_conv_algo);
     m.def("tc_set_halo_desc_mode", &psb::tc_set_halo_desc_mode);
+    m.def("tc_set_halo_cluster", &psb::tc_set_halo_cluster);
+    m.def("tc_set_halo_resident", &psb::tc_set_halo_resident);
     m.def("conv_unsupported_reason", &psb::conv_unsupported_reason);
     m.def("tc_error", &psb::tc_error);
 }

@@ -45,6 +45,7 @@ struct TcParams {
     const __nv_bfloat16* residual;      // optional [M,N] tensor added in the epilogue (dgrad + skip-gradient fusion)
     int relu;
     int R, halo_w, a_stage_bytes;       // halo kernel: filter rows, halo box width, bytes per A stage
+    int b_resident, a_stages;           // weight-stationary mode: all R filter rows of B stay in smem for the whole kernel
     int desc_mode;
     __nv_bfloat16* C;
     int* err;                          // set to 1 if a barrier wait timed out (protocol bug), never hang
@@ -247,16 +248,19 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
 //
 // The per-tap kernel above re-fetches the A tile from L2 once per filter tap (9x for 3x3); measured on B200 it is
 // bound by L2->SM bandwidth (1.2 GB of smem fills per ResNet layer at ~12 TB/s ~ 100 us, profiles/run3_conv.md).
-// Here a tile is 8 rows x 16 columns of ONE image and, per 64-channel block, the input patch with its halo is loaded
-// ONCE as a single TMA box of (64 ch, 16 rows, 16+S-1 columns) with H as the fast pixel dimension, so the smem buffer
-// is [column][row][64 ch]: 128-byte rows, 16 rows (2048 B) per image column.  With the GEMM rows ordered m = bw*8 + bh,
-// the A operand of filter tap (r,s) is the *shifted window* that starts at byte ((s*16 + r) * 128) of that buffer:
-// 8 consecutive rows form one UMMA core group, groups are 2048 B apart (SBO), and because the window starts off the
+// Here a tile is 16 rows x 8 columns of ONE image and, per 64-channel block, the input patch with its halo is loaded
+// ONCE as a single TMA box of (64 ch, 16 columns, 16+R-1 rows) (the 8+S-1 needed columns padded to a 16-pixel pitch), so
+// the smem buffer is [row][column][64 ch]: 128-byte pixels, 16 pixels (2048 B) per image row, and every box row is a
+// contiguous 2 KB run in global memory (a first version used H as the fast dimension: 288 scattered 128-byte pieces per
+// box throttled the TMA unit to ~10 B/cycle/SM).  With the GEMM rows ordered m = bh*8 + bw,
+// the A operand of filter tap (r,s) is the *shifted window* that starts at byte ((r*16 + s) * 128) of that buffer:
+// 8 consecutive pixels form one UMMA core group, groups are 2048 B apart (SBO), and because the window starts off the
 // 1024-byte swizzle pattern boundary the descriptor carries base_offset = r.  A traffic drops from R*S*16 KB to
 // (16+S-1)*2 KB per (tile, channel block): 4x less for 3x3.  B (weights) streams per (tap, channel block) as before.
 // Weights stream one filter ROW per TMA: a 3-D box (64 k, BN out-channels, S taps) = S consecutive K-major B tiles, so the
 // producer issues R+1 bulk copies per channel block instead of R*S+1 and the MMA warp waits on R barriers (the first
 // version issued one 8-16 KB copy per tap and the MMA warp spent a third of its time waiting on them, profiles/run7_*.md).
+constexpr int kMaxAStages = 4;
 template <int BN> struct HaloCfg {
     static constexpr int kAStages = 2;
     static constexpr int kBStages = BN == 64 ? 4 : 3;
@@ -264,18 +268,24 @@ template <int BN> struct HaloCfg {
     static constexpr int kTmemCols = 2 * BN;
 };
 
-template <int BN>
+// CL = cluster size (1 or 2).  With CL = 2 the two CTAs of a cluster work on neighbouring M tiles of the same N tile and
+// share the weight stream: each filter-row stage is fetched from L2 by ONE of them (alternating) and delivered to both
+// through TMA multicast; a stage is recycled when both CTAs' MMAs have retired (multicast tcgen05.commit on both
+// "empty" barriers, count 2).  Halves the dominant L2->SM term of the 64-channel layers.
+template <int BN, int CL>
 __global__ void __launch_bounds__(kThreads, 1)
 tc_conv_halo_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, const TcParams p) {
     using Cfg = HaloCfg<BN>;
+    const uint32_t crank = CL > 1 ? cluster_ctarank() : 0;
+    constexpr uint16_t kMask = (uint16_t)((1u << CL) - 1);
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint8_t* smem_a = smem;
-    uint8_t* smem_b = smem + Cfg::kAStages * p.a_stage_bytes;
+    uint8_t* smem_b = smem + p.a_stages * p.a_stage_bytes;
     const int b_stage_bytes = p.S * Cfg::kBTapBytes;
     uint64_t* a_full = reinterpret_cast<uint64_t*>(smem_b + Cfg::kBStages * b_stage_bytes);
-    uint64_t* a_empty = a_full + Cfg::kAStages;
-    uint64_t* b_full = a_empty + Cfg::kAStages;
+    uint64_t* a_empty = a_full + kMaxAStages;
+    uint64_t* b_full = a_empty + kMaxAStages;
     uint64_t* b_empty = b_full + Cfg::kBStages;
     uint64_t* tmem_full = b_empty + Cfg::kBStages;
     uint64_t* tmem_empty = tmem_full + 2;
@@ -284,37 +294,44 @@ tc_conv_halo_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (warp == 0 && lane == 0) { prefetch_tmap(&tmap_a); prefetch_tmap(&tmap_b); }
     if (warp == 1 && lane == 0) {
-        for (int s = 0; s < Cfg::kAStages; ++s) { mbar_init(a_full + s, 1); mbar_init(a_empty + s, 1); }
-        for (int s = 0; s < Cfg::kBStages; ++s) { mbar_init(b_full + s, 1); mbar_init(b_empty + s, 1); }
+        for (int s = 0; s < p.a_stages; ++s) { mbar_init(a_full + s, 1); mbar_init(a_empty + s, 1); }
+        for (int s = 0; s < Cfg::kBStages; ++s) { mbar_init(b_full + s, 1); mbar_init(b_empty + s, CL); }
         for (int s = 0; s < 2; ++s) { mbar_init(tmem_full + s, 1); mbar_init(tmem_empty + s, 4); }
         fence_barrier_init();
     }
     if (warp == 2) tmem_alloc(tmem_base_smem, Cfg::kTmemCols);
     tc_fence_before();
     __syncthreads();
+    if (CL > 1) cluster_sync_all();          // peers' barriers must exist before any multicast copy / commit targets them
     tc_fence_after();
     const uint32_t tmem_base = *tmem_base_smem;
+    // tile order: n-tile slowest, m-tiles fastest, so the CTAs of a cluster (consecutive blockIdx) get neighbouring M tiles of
+    // the same N tile.  Every CTA runs the same number of iterations (ghost tiles past the end fetch zeros and store nothing).
     const int n_tiles = p.n_tiles_m * p.n_tiles_n;
+    const int n_iters = (n_tiles + gridDim.x - 1) / gridDim.x;
 
     if (warp == 0) {
-        int as = 0; uint32_t aph = 0; int bs = 0; uint32_t bph = 0;
-        for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-            const int mt = tile / p.n_tiles_n, nt = tile % p.n_tiles_n;
-            const int tw = mt % p.tiles_w, th = (mt / p.tiles_w) % p.tiles_h, n = mt / (p.tiles_w * p.tiles_h);
+        int as = 0; uint32_t aph = 0; int bs = 0; uint32_t bph = 0; uint32_t bcount = 0;
+        for (int it = 0; it < n_iters; ++it) {
+            const int tile = it * gridDim.x + blockIdx.x;
+            const bool ghost = tile >= n_tiles;
+            const int nt = ghost ? (n_tiles - 1) / p.n_tiles_m : tile / p.n_tiles_m, mt = ghost ? 0 : tile % p.n_tiles_m;
+            const int tw = mt % p.tiles_w, th = (mt / p.tiles_w) % p.tiles_h, n = ghost ? p.NB : mt / (p.tiles_w * p.tiles_h);
             for (int cb = 0; cb < p.cblocks; ++cb) {
                 if (!mbar_wait(a_empty + as, aph ^ 1)) { *p.err = 11; return; }
                 if (elect_one()) {
                     mbar_arrive_expect_tx(a_full + as, p.a_stage_bytes);
-                    // tensor map dims are (C, H, W, N): H is the fast pixel dimension of the smem image
-                    tma_load_4d(smem_a + as * p.a_stage_bytes, &tmap_a, a_full + as, cb * BK, th * 8 - p.pad, tw * 16 - p.pad, n);
+                    tma_load_4d(smem_a + as * p.a_stage_bytes, &tmap_a, a_full + as, cb * BK, tw * 8 - p.pad, th * 16 - p.pad, n);
                 }
                 __syncwarp();
-                if (++as == Cfg::kAStages) { as = 0; aph ^= 1; }
-                for (int r = 0; r < p.R; ++r) {
+                if (++as == p.a_stages) { as = 0; aph ^= 1; }
+                if (p.b_resident && it > 0) continue;          // weights were loaded once (stage r = filter row r) and stay
+                for (int r = 0; r < p.R; ++r, ++bcount) {
                     if (!mbar_wait(b_empty + bs, bph ^ 1)) { *p.err = 12; return; }
                     if (elect_one()) {
                         mbar_arrive_expect_tx(b_full + bs, b_stage_bytes);
-                        tma_load_3d(smem_b + bs * b_stage_bytes, &tmap_b, b_full + bs, cb * BK, nt * BN, r * p.S);
+                        if (CL == 1) tma_load_3d(smem_b + bs * b_stage_bytes, &tmap_b, b_full + bs, cb * BK, nt * BN, r * p.S);
+                        else if ((bcount % CL) == crank) tma_load_3d_mcast(smem_b + bs * b_stage_bytes, &tmap_b, b_full + bs, cb * BK, nt * BN, r * p.S, kMask);
                     }
                     __syncwarp();
                     if (++bs == Cfg::kBStages) { bs = 0; bph ^= 1; }
@@ -324,7 +341,7 @@ tc_conv_halo_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     } else if (warp == 1) {
         constexpr uint32_t idesc = umma_idesc_bf16(BM, BN, 0, 0);
         int as = 0; uint32_t aph = 0; int bs = 0; uint32_t bph = 0; int acc = 0; uint32_t acc_phase = 0;
-        for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        for (int it = 0; it < n_iters; ++it) {
             if (!mbar_wait(tmem_empty + acc, acc_phase ^ 1)) { *p.err = 13; return; }
             tc_fence_after();
             const uint32_t tmem_d = tmem_base + acc * BN;
@@ -332,26 +349,27 @@ tc_conv_halo_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                 if (!mbar_wait(a_full + as, aph)) { *p.err = 14; return; }
                 const uint32_t sa0 = smem_u32(smem_a + as * p.a_stage_bytes);
                 for (int r = 0; r < p.R; ++r) {
+                    if (p.b_resident) { bs = r; bph = 0; }      // stage r holds filter row r for the whole kernel (phase 0 stays complete)
                     if (!mbar_wait(b_full + bs, bph)) { *p.err = 15; return; }
                     tc_fence_after();
                     const uint32_t sb0 = smem_u32(smem_b + bs * b_stage_bytes);
                     if (elect_one()) {
                         for (int s = 0; s < p.S; ++s) {
                             // shifted window: the swizzle XOR is a function of the absolute smem address, so base_offset stays 0
-                            const uint32_t sa = sa0 + (uint32_t)((s * 16 + r) * 128);
+                            const uint32_t sa = sa0 + (uint32_t)((r * 16 + s) * 128);
                             const uint32_t sb = sb0 + (uint32_t)(s * Cfg::kBTapBytes);
 #pragma unroll
                             for (int k = 0; k < BK / 16; ++k)
                                 tc_mma_bf16(tmem_d, umma_desc_k_sw128_sbo(sa + k * 32, 2048), umma_desc_k_sw128(sb + k * 32), idesc, (cb | r | s | k) != 0);
                         }
-                        tc_commit(b_empty + bs);
+                        if (!p.b_resident) { if (CL == 1) tc_commit(b_empty + bs); else tc_commit_mcast(b_empty + bs, kMask); }
                     }
                     __syncwarp();
-                    if (++bs == Cfg::kBStages) { bs = 0; bph ^= 1; }
+                    if (!p.b_resident && ++bs == Cfg::kBStages) { bs = 0; bph ^= 1; }
                 }
                 if (elect_one()) tc_commit(a_empty + as);
                 __syncwarp();
-                if (++as == Cfg::kAStages) { as = 0; aph ^= 1; }
+                if (++as == p.a_stages) { as = 0; aph ^= 1; }
             }
             if (elect_one()) tc_commit(tmem_full + acc);
             __syncwarp();
@@ -360,12 +378,14 @@ tc_conv_halo_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     } else if (warp >= kEpiWarp0) {
         const int q = warp & 3;
         int acc = 0; uint32_t acc_phase = 0;
-        for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-            const int mt = tile / p.n_tiles_n, nt = tile % p.n_tiles_n;
+        for (int it = 0; it < n_iters; ++it) {
+            const int tile = it * gridDim.x + blockIdx.x;
+            const bool ghost = tile >= n_tiles;
+            const int nt = ghost ? 0 : tile / p.n_tiles_m, mt = ghost ? 0 : tile % p.n_tiles_m;
             const int tw = mt % p.tiles_w, th = (mt / p.tiles_w) % p.tiles_h, n = mt / (p.tiles_w * p.tiles_h);
-            const int m = q * 32 + lane;                       // GEMM row: m = bw*8 + bh
-            const int h = th * 8 + (m & 7), w = tw * 16 + (m >> 3);
-            const long long out_row = (h < p.Hout && w < p.Wout) ? ((long long)n * p.Hout + h) * p.Wout + w : -1;
+            const int m = q * 32 + lane;                       // GEMM row: m = bh*8 + bw
+            const int h = th * 16 + (m >> 3), w = tw * 8 + (m & 7);
+            const long long out_row = (!ghost && h < p.Hout && w < p.Wout) ? ((long long)n * p.Hout + h) * p.Wout + w : -1;
             if (!mbar_wait(tmem_full + acc, acc_phase)) { if (lane == 0) *p.err = 16; return; }
             tc_fence_after();
             epilogue_tile<BN>(p, tmem_base, acc, q, lane, out_row, nt);
@@ -377,6 +397,7 @@ tc_conv_halo_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     }
     tc_fence_before();
     __syncthreads();
+    if (CL > 1) cluster_sync_all();          // no CTA may exit while a peer can still multicast into it
     tc_fence_after();
     if (warp == 2) tmem_dealloc(tmem_base, Cfg::kTmemCols);
 }
@@ -440,20 +461,32 @@ static const char* launch(const CUtensorMap& ta, const CUtensorMap& tb, const Tc
     return cudaGetLastError() == cudaSuccess ? nullptr : "kernel launch failed";
 }
 
-template <int BN>
+static int g_halo_resident = 1;
+void tc_set_halo_resident(int r) { g_halo_resident = r; }
+static int g_halo_cluster = 2;
+void tc_set_halo_cluster(int c) { g_halo_cluster = c == 2 ? 2 : 1; }
+
+template <int BN, int CL>
 static const char* launch_halo(const CUtensorMap& ta, const CUtensorMap& tb, const TcParams& p, cudaStream_t stream) {
     using Cfg = HaloCfg<BN>;
-    const int smem_bytes = Cfg::kAStages * p.a_stage_bytes + Cfg::kBStages * p.S * Cfg::kBTapBytes + 1024 + 512;
+    const int smem_bytes = p.a_stages * p.a_stage_bytes + Cfg::kBStages * p.S * Cfg::kBTapBytes + 1024 + 512;
     if (smem_bytes > 227 * 1024) return "halo tile does not fit in shared memory";
     static int attr = 0;
     if (attr < smem_bytes) {
-        if (cudaFuncSetAttribute(tc_conv_halo_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes) != cudaSuccess) return "cannot raise dynamic smem";
+        if (cudaFuncSetAttribute(tc_conv_halo_kernel<BN, CL>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes) != cudaSuccess) return "cannot raise dynamic smem";
         attr = smem_bytes;
     }
     const int tiles = p.n_tiles_m * p.n_tiles_n;
-    const int grid = tiles < num_sms() ? tiles : num_sms();
-    tc_conv_halo_kernel<BN><<<grid, kThreads, smem_bytes, stream>>>(ta, tb, p);
-    return cudaGetLastError() == cudaSuccess ? nullptr : "kernel launch failed";
+    int grid = tiles < num_sms() ? tiles : num_sms();
+    grid = (grid + CL - 1) / CL * CL;
+    if (grid > num_sms()) grid -= CL;
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(grid); cfg.blockDim = dim3(kThreads); cfg.dynamicSmemBytes = smem_bytes; cfg.stream = stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = CL; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, tc_conv_halo_kernel<BN, CL>, ta, tb, p) == cudaSuccess ? nullptr : "kernel launch failed";
 }
 
 static int g_conv_algo = -1;     // -1 auto (= per-tap until the halo variant is validated on hardware), 0 per-tap, 1 halo
@@ -483,14 +516,13 @@ const char* tc_conv_fprop(const void* X, const void* Wt, void* Y, const void* bi
     if (Cin % 64) return "Cin must be a multiple of 64";
     if (Cout % 8) return "Cout must be a multiple of 8";
     const int Hout = (Hin + 2 * pad - R) / stride + 1, Wout = (Win + 2 * pad - S) / stride + 1;
-    const bool halo_ok = stride == 1 && R * S > 1 && R <= 8 && Wout >= 16 && Hout >= 8 && (16 + S - 1) <= 256;
+    const bool halo_ok = stride == 1 && R * S > 1 && S <= 8 && Wout >= 8 && Hout >= 16 && (16 + R - 1) <= 256;
     if (g_conv_algo == 1 && halo_ok) {
         const int BN = Cout <= 64 ? 64 : 128;
         CUtensorMap ta, tb;
-        // dims (C, H, W, N): strides in bytes for H, W, N
-        uint64_t da[4] = {(uint64_t)Cin, (uint64_t)Hin, (uint64_t)Win, (uint64_t)NB};
-        uint64_t sa[3] = {(uint64_t)Win * Cin * 2, (uint64_t)Cin * 2, (uint64_t)Hin * Win * Cin * 2};
-        uint32_t boxa[4] = {BK, 16, (uint32_t)(16 + S - 1), 1}, esa[4] = {1, 1, 1, 1};
+        uint64_t da[4] = {(uint64_t)Cin, (uint64_t)Win, (uint64_t)Hin, (uint64_t)NB};
+        uint64_t sa[3] = {(uint64_t)Cin * 2, (uint64_t)Win * Cin * 2, (uint64_t)Hin * Win * Cin * 2};
+        uint32_t boxa[4] = {BK, 16, (uint32_t)(16 + R - 1), 1}, esa[4] = {1, 1, 1, 1};
         const int Ktot = R * S * Cin;
         // weights [Cout][R*S][Cin] as a 3-D tensor (Cin, Cout, taps): one box = S taps of one filter row
         uint64_t db[3] = {(uint64_t)Cin, (uint64_t)Cout, (uint64_t)(R * S)}, sb[2] = {(uint64_t)Ktot * 2, (uint64_t)Cin * 2};
@@ -500,11 +532,16 @@ const char* tc_conv_fprop(const void* X, const void* Wt, void* Y, const void* bi
         TcParams p{};
         p.M = NB * Hout * Wout; p.N = Cout; p.num_kb = Ktot / BK; p.mode = 2;
         p.Hout = Hout; p.Wout = Wout; p.NB = NB; p.stride = 1; p.pad = pad; p.S = S; p.R = R; p.cblocks = Cin / BK;
-        p.tiles_w = (Wout + 15) / 16; p.tiles_h = (Hout + 7) / 8;
+        p.tiles_w = (Wout + 7) / 8; p.tiles_h = (Hout + 15) / 16;
         p.n_tiles_m = p.tiles_w * p.tiles_h * NB; p.n_tiles_n = (Cout + BN - 1) / BN;
-        p.halo_w = 16 + S - 1; p.a_stage_bytes = p.halo_w * 16 * 128;
+        p.halo_w = 16; p.a_stage_bytes = (16 + R - 1) * 16 * 128;
+        // weight-stationary: with one channel block and one N tile the R filter-row stages hold ALL the weights this CTA ever needs
+        p.b_resident = (g_halo_resident && p.cblocks == 1 && p.n_tiles_n == 1 && R <= HaloCfg<64>::kBStages && BN == 64) ? 1 : 0;
+        p.a_stages = 2;
+        if (p.b_resident && 3 * p.a_stage_bytes + HaloCfg<64>::kBStages * S * HaloCfg<64>::kBTapBytes + 2048 <= 227 * 1024) p.a_stages = 3;
         p.bias = (const __nv_bfloat16*)bias; p.residual = (const __nv_bfloat16*)residual; p.relu = relu; p.C = (__nv_bfloat16*)Y; p.err = err_word();
-        return BN == 64 ? launch_halo<64>(ta, tb, p, stream) : launch_halo<128>(ta, tb, p, stream);
+        if (g_halo_cluster == 2 && (p.n_tiles_m % 2) == 0 && !p.b_resident) return BN == 64 ? launch_halo<64, 2>(ta, tb, p, stream) : launch_halo<128, 2>(ta, tb, p, stream);
+        return BN == 64 ? launch_halo<64, 1>(ta, tb, p, stream) : launch_halo<128, 1>(ta, tb, p, stream);
     }
     // tile rectangle: BW = largest power of two <= min(Wout,32), then rows, then images, product 128
     int BW = 1; while (BW * 2 <= Wout && BW * 2 <= 32) BW *= 2;

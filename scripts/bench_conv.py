@@ -43,8 +43,9 @@ for (Cin, H, W, Cout, R, st, pad) in SHAPES:
     ref = F.conv2d(x, w, None, st, pad)
     res = {"shape": [Cin, H, W, Cout, R, st, pad], "gflop": flops / 1e9}
     res["cudnn_us"] = timeit(lambda: F.conv2d(x, w, None, st, pad))
-    for name, algo in (("tap", 0), ("halo", 1)):
+    for name, algo, cl in (("tap", 0, 1), ("halo", 1, 1), ("halo2", 1, 2)):
         ext.tc_set_conv_algo(algo)
+        ext.tc_set_halo_cluster(cl)
         try:
             y = ext.conv_fprop(x, w, None, st, pad, False)
             torch.cuda.synchronize()
@@ -55,7 +56,7 @@ for (Cin, H, W, Cout, R, st, pad) in SHAPES:
         except Exception as e:  # noqa: BLE001
             res[name + "_err"] = repr(e)[:200]
     ext.tc_set_conv_algo(-1)
-    for k in ("cudnn_us", "tap_us", "halo_us"):
+    for k in ("cudnn_us", "tap_us", "halo_us", "halo2_us"):
         if k in res:
             res[k.replace("_us", "_pflops")] = flops / res[k] / 1e9
     rows.append(res)

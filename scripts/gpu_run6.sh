@@ -5,6 +5,6 @@ timeout 600 python scripts/bench_conv.py > gpurun_out/bench_conv.log 2>&1; pytho
 import json
 for l in open('gpurun_out/bench_conv.log'):
     if l.startswith('{'):
-        r=json.loads(l); print(r['shape'], 'cudnn %.1f tap %.1f halo %.1f us | err tap %s halo %s' % (r['cudnn_us'], r.get('tap_us',-1), r.get('halo_us',-1), r.get('tap_maxerr'), r.get('halo_maxerr')))
+        r=json.loads(l); print(r['shape'], 'cudnn %.1f tap %.1f halo %.1f halo2 %.1f us | err tap %s halo %s halo2 %s %s' % (r['cudnn_us'], r.get('tap_us',-1), r.get('halo_us',-1), r.get('halo2_us',-1), r.get('tap_maxerr'), r.get('halo_maxerr'), r.get('halo2_maxerr'), r.get('halo2_err','')))
 PY
 PSB200_TC_CONV=1 timeout 300 python bench.py --gpus 1 --steps 30 --warmup 5 --backend sm100 > gpurun_out/bench_sm100_tc.log 2>&1; tail -1 gpurun_out/bench_sm100_tc.log | cut -c1-330

@@ -298,12 +298,13 @@ def test_tc_gemm(ext, M, N, K, bias, relu):
     (8, 64, 32, 32, 64, 3, 1, 1), (4, 64, 16, 16, 128, 3, 1, 1), (16, 128, 8, 8, 128, 3, 1, 1), (32, 256, 4, 4, 512, 3, 1, 1),
     (64, 512, 2, 2, 512, 3, 1, 1), (3, 64, 32, 32, 64, 1, 1, 0), (5, 128, 16, 16, 256, 1, 1, 0), (2, 64, 56, 56, 64, 3, 1, 1),
     (8, 64, 32, 32, 128, 3, 2, 1), (8, 64, 32, 32, 128, 1, 2, 0), (4, 128, 16, 16, 256, 3, 2, 1), (2, 64, 7, 7, 64, 3, 1, 1)])
-@pytest.mark.parametrize("algo", [0, 1])
+@pytest.mark.parametrize("algo", [0, 1, 2])
 def test_tc_conv_fprop(ext, shape, algo):
     """algo 0 = per-tap implicit GEMM, 1 = halo (shifted-window descriptors; silently falls back to per-tap when the
     shape is not eligible, which is what the dispatcher does in production)."""
     NB, Cin, H, W, Cout, R, st, pad = shape
-    ext.tc_set_conv_algo(algo)
+    ext.tc_set_conv_algo(min(algo, 1))            # 2 = halo with the 2-CTA weight-multicast cluster
+    ext.tc_set_halo_cluster(2 if algo == 2 else 1)
     torch.manual_seed(0)
     x = (torch.randn(NB, Cin, H, W, device="cuda") * 0.5).to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
     w = (torch.randn(Cout, Cin, R, R, device="cuda") * (1.0 / math.sqrt(Cin * R * R))).to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
