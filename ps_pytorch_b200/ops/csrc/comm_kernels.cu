@@ -65,67 +65,66 @@ struct PushArgs {
     int mode, src_fp32, zero_src;
 };
 
-__device__ __forceinline__ void load32(const PushArgs& a, long long i, float* f) {
-    if (a.src_fp32) {
-        const float* s = reinterpret_cast<const float*>(a.src) + i;
-#pragma unroll
-        for (int k = 0; k < 8; ++k) {
-            uint4 v = ld_nc_v4(s + 4 * k);
-            f[4 * k] = __uint_as_float(v.x); f[4 * k + 1] = __uint_as_float(v.y);
-            f[4 * k + 2] = __uint_as_float(v.z); f[4 * k + 3] = __uint_as_float(v.w);
-        }
-    } else {
-        const __nv_bfloat16* s = reinterpret_cast<const __nv_bfloat16*>(a.src) + i;
-#pragma unroll
-        for (int k = 0; k < 4; ++k) unpack8(ld_nc_v4(s + 8 * k), f + 8 * k);
-    }
-}
-
+// Work decomposition: one warp-iteration covers 1024 consecutive elements as 4 rows of 32 x 8-element vectors, lane l taking
+// vector (row*32 + l).  Every load/store instruction of a warp therefore touches ONE contiguous 512-byte (bf16), 256-byte
+// (fp8) or 1-KB (fp32) span: NVLink packets are full-sized.  (The first version gave each thread 32 consecutive elements;
+// its peer stores were 16-byte pieces 64 bytes apart and the 8-GPU incast reached only 183 GB/s, profiles/run_n8.md.)
 __global__ void __launch_bounds__(256) push_kernel(PushArgs a) {
     const int lane = threadIdx.x & 31;
-    const long long nthreads = (long long)gridDim.x * blockDim.x;
-    const long long t0 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long nwarps = (long long)gridDim.x * (blockDim.x >> 5);
+    const long long warp0 = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const uint4 zero = make_uint4(0, 0, 0, 0);
-    for (long long i = a.lo + t0 * 32; i < a.hi; i += nthreads * 32) {
-        float f[32];
-        load32(a, i, f);
-        if (a.zero_src) {   // next backward accumulates into a clean arena: saves a separate 2-4 B/param memset pass
-            if (a.src_fp32) { float* s = (float*)a.src + i;
+    for (long long base = a.lo + warp0 * 1024; base < a.hi; base += nwarps * 1024) {
+        float f[4][8];
+        bool ok[4];
 #pragma unroll
-                for (int k = 0; k < 8; ++k) st_v4(s + 4 * k, zero);
-            } else { __nv_bfloat16* s = (__nv_bfloat16*)a.src + i;
+        for (int k = 0; k < 4; ++k) {                       // 4 independent 16/32-byte loads in flight per lane
+            const long long i = base + (long long)(k * 32 + lane) * 8;
+            ok[k] = i < a.hi;
+            if (ok[k]) {
+                if (a.src_fp32) {
+                    const float* sp = reinterpret_cast<const float*>(a.src) + i;
+                    const uint4 x = ld_nc_v4(sp), y = ld_nc_v4(sp + 4);
+                    f[k][0] = __uint_as_float(x.x); f[k][1] = __uint_as_float(x.y); f[k][2] = __uint_as_float(x.z); f[k][3] = __uint_as_float(x.w);
+                    f[k][4] = __uint_as_float(y.x); f[k][5] = __uint_as_float(y.y); f[k][6] = __uint_as_float(y.z); f[k][7] = __uint_as_float(y.w);
+                } else {
+                    unpack8(ld_nc_v4(reinterpret_cast<const __nv_bfloat16*>(a.src) + i), f[k]);
+                }
+            } else {
 #pragma unroll
-                for (int k = 0; k < 4; ++k) st_v4(s + 8 * k, zero);
+                for (int j = 0; j < 8; ++j) f[k][j] = 0.f;
             }
         }
-        if (a.mode == WIRE_BF16) {
-            __nv_bfloat16* d = reinterpret_cast<__nv_bfloat16*>(a.dst) + i;
 #pragma unroll
-            for (int k = 0; k < 4; ++k) st_na_v4(d + 8 * k, pack8(f + 8 * k));
-        } else if (a.mode == WIRE_FP32) {
-            float* d = reinterpret_cast<float*>(a.dst) + i;
+        for (int k = 0; k < 4; ++k) {
+            const long long i = base + (long long)(k * 32 + lane) * 8;
+            if (a.zero_src && ok[k]) {   // next backward accumulates into a clean arena: saves a separate memset pass
+                if (a.src_fp32) { float* sp = (float*)a.src + i; st_v4(sp, zero); st_v4(sp + 4, zero); }
+                else st_v4((__nv_bfloat16*)a.src + i, zero);
+            }
+            if (a.mode == WIRE_BF16) {
+                if (ok[k]) st_na_v4(reinterpret_cast<__nv_bfloat16*>(a.dst) + i, pack8(f[k]));
+            } else if (a.mode == WIRE_FP32) {
+                if (ok[k]) {
+                    float* d = reinterpret_cast<float*>(a.dst) + i;
+                    st_na_v4(d, make_uint4(__float_as_uint(f[k][0]), __float_as_uint(f[k][1]), __float_as_uint(f[k][2]), __float_as_uint(f[k][3])));
+                    st_na_v4(d + 4, make_uint4(__float_as_uint(f[k][4]), __float_as_uint(f[k][5]), __float_as_uint(f[k][6]), __float_as_uint(f[k][7])));
+                }
+            } else {
+                // one 32-element quantisation block = 4 neighbouring lanes of this row
+                float amax = 0.f;
 #pragma unroll
-            for (int k = 0; k < 8; ++k)
-                st_na_v4(d + 4 * k, make_uint4(__float_as_uint(f[4 * k]), __float_as_uint(f[4 * k + 1]), __float_as_uint(f[4 * k + 2]), __float_as_uint(f[4 * k + 3])));
-        } else {
-            float amax = 0.f;
-#pragma unroll
-            for (int k = 0; k < 32; ++k) amax = fmaxf(amax, fabsf(f[k]));
-            const int e = e8m0_exponent(amax);
-            const float inv = exp2i(-e);
-            uint8_t* d = reinterpret_cast<uint8_t*>(a.dst) + i;
-            st_na_v4(d, make_uint4(quant4(f[0], f[1], f[2], f[3], inv), quant4(f[4], f[5], f[6], f[7], inv),
-                                   quant4(f[8], f[9], f[10], f[11], inv), quant4(f[12], f[13], f[14], f[15], inv)));
-            st_na_v4(d + 16, make_uint4(quant4(f[16], f[17], f[18], f[19], inv), quant4(f[20], f[21], f[22], f[23], inv),
-                                        quant4(f[24], f[25], f[26], f[27], inv), quant4(f[28], f[29], f[30], f[31], inv)));
-            // gather 4 neighbouring lanes' scale bytes into one 32-bit peer store (the whole warp is in this iteration:
-            // ranges are multiples of 32*32 elements per warp only when aligned, so guard with the active mask)
-            const unsigned act = __activemask();
-            const uint32_t sb = (uint32_t)(e + 127);
-            const int base = (lane & ~3);
-            uint32_t w = __shfl_sync(act, sb, base) | (__shfl_sync(act, sb, base + 1) << 8) |
-                         (__shfl_sync(act, sb, base + 2) << 16) | (__shfl_sync(act, sb, base + 3) << 24);
-            if ((lane & 3) == 0) *reinterpret_cast<volatile uint32_t*>(a.dst_scale + i / 32) = w;
+                for (int j = 0; j < 8; ++j) amax = fmaxf(amax, fabsf(f[k][j]));
+                amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, 1));
+                amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, 2));
+                const int e = e8m0_exponent(amax);
+                const float inv = exp2i(-e);
+                if (ok[k]) {
+                    const uint32_t q0 = quant4(f[k][0], f[k][1], f[k][2], f[k][3], inv), q1 = quant4(f[k][4], f[k][5], f[k][6], f[k][7], inv);
+                    asm volatile("st.global.L1::no_allocate.v2.u32 [%0], {%1,%2};" ::"l"(reinterpret_cast<uint8_t*>(a.dst) + i), "r"(q0), "r"(q1) : "memory");
+                    if ((lane & 3) == 0) a.dst_scale[i / 32] = (uint8_t)(e + 127);
+                }
+            }
         }
     }
     // publish: every CTA fences its peer stores; the last CTA to arrive releases the flag with this worker's step id
@@ -211,13 +210,18 @@ __global__ void __launch_bounds__(256) reduce_update_kernel(RUArgs a) {
         if (mask == 0) return;                     // timed out: error word is set, host raises
         for (long long i = a.lo[b] + ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 8; i < a.hi[b]; i += stride) {
             float g[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-#pragma unroll 1
-            for (int k = 0; k < a.P; ++k) {
-                if (!(mask >> k & 1)) continue;
-                float f[8];
-                load_src8(a, k, i, f);
+            {
+                // issue every selected source's load before the first add: up to 8 independent 16-byte P2P/HBM loads in flight
+                float fs[kMaxPeers][8];
 #pragma unroll
-                for (int j = 0; j < 8; ++j) g[j] += f[j];
+                for (int k = 0; k < kMaxPeers; ++k)
+                    if (k < a.P && (mask >> k & 1)) load_src8(a, k, i, fs[k]);
+#pragma unroll
+                for (int k = 0; k < kMaxPeers; ++k)
+                    if (k < a.P && (mask >> k & 1)) {
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) g[j] += fs[k][j];
+                    }
             }
             float wf[8], x0[8], x1[8], x2[8];
             if (hp.kind != 2) {
