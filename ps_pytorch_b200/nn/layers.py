@@ -62,7 +62,7 @@ class BatchNorm2d(nn.BatchNorm2d):
             if why is None:
                 return _norm.batch_norm(x, self, residual, relu)
             note_fallback("batch_norm", why)
-        if self.training and self.track_running_stats and self.num_batches_tracked is not None:
+        if self.training and self.track_running_stats and self.num_batches_tracked is not None and not getattr(self, "external_counter", False):
             self.num_batches_tracked.add_(1)
         w, b = self.weight, self.bias
         rm, rv = self.running_mean, self.running_var

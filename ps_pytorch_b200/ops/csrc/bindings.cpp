@@ -17,8 +17,8 @@ at::Tensor make_hp(double, double, double, double, bool, double, double, double,
 int64_t hp_steps(at::Tensor);
 // bn_kernels.cu
 std::vector<at::Tensor> bn_forward(at::Tensor, c10::optional<at::Tensor>, c10::optional<at::Tensor>, c10::optional<at::Tensor>, c10::optional<at::Tensor>,
-                                   c10::optional<at::Tensor>, bool, double, double, bool);
-std::vector<at::Tensor> bn_backward(at::Tensor, at::Tensor, at::Tensor, c10::optional<at::Tensor>, at::Tensor, at::Tensor, bool, bool);
+                                   c10::optional<at::Tensor>, bool, double, double, bool, c10::optional<at::Tensor>);
+std::vector<at::Tensor> bn_backward(at::Tensor, at::Tensor, at::Tensor, c10::optional<at::Tensor>, at::Tensor, at::Tensor, bool, bool, c10::optional<at::Tensor>);
 // elementwise.cu
 at::Tensor relu_forward(at::Tensor);
 at::Tensor relu_backward(at::Tensor, at::Tensor);

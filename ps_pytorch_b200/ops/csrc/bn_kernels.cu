@@ -19,9 +19,78 @@ namespace psb {
 
 constexpr int kBnThreads = 256;
 
+
+// ---- fused "last CTA finalizes" variants -----------------------------------------------------------------------------
+// The stand-alone finalize kernels above cost one more launch + drain (~3-5 us inside a CUDA graph) per BN pass; with 40
+// passes per ResNet-18 step that is ~0.15 ms.  In the fused variants every CTA adds its per-channel partial sums to a
+// 2*C-float accumulator with fp32 atomics (RED), takes a ticket, and the last CTA to arrive finalizes from the accumulator and
+// leaves accumulator + ticket zeroed for the next call (self-cleaning persistent workspace owned by the layer).
+// Summation order across CTAs is not fixed, so results can differ in the last bit between runs;
+// PSB200_BN_DETERMINISTIC=1 selects the two-kernel, fixed-order path.
+struct BnFwdFin {
+    const __nv_bfloat16* x_row0; const void* gamma; const void* beta; float* running_mean; float* running_var;
+    float momentum, eps; float *mean, *invstd, *coef_a, *coef_b; int p_bf16;
+};
+struct BnBwdFin {
+    const void* gamma; const float* invstd; void* dgamma; void* dbeta; float *c1, *c2, *c3; int p_bf16;
+};
+
+__device__ __forceinline__ bool last_cta_ticket(float* ws, int C) {
+    __shared__ int s_last;
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const unsigned t = atomicAdd(reinterpret_cast<unsigned*>(ws + 2 * C), 1u);
+        s_last = (t == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (s_last) __threadfence();
+    return s_last != 0;
+}
+
+__device__ __forceinline__ void fwd_finalize_from_acc(float* ws, int C, long long M, const BnFwdFin& f) {
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+        const float s = __ldcg(ws + c), q = __ldcg(ws + C + c);
+        ws[c] = 0.f; ws[C + c] = 0.f;
+        const float inv_m = 1.f / (float)M;
+        const float dm = s * inv_m;
+        const float mu = __bfloat162float(f.x_row0[c]) + dm;
+        const float var = fmaxf(q * inv_m - dm * dm, 0.f);
+        const float is = rsqrtf(var + f.eps);
+        f.mean[c] = mu; f.invstd[c] = is;
+        float ga = 1.f, be = 0.f;
+        if (f.gamma) ga = f.p_bf16 ? __bfloat162float(((const __nv_bfloat16*)f.gamma)[c]) : ((const float*)f.gamma)[c];
+        if (f.beta) be = f.p_bf16 ? __bfloat162float(((const __nv_bfloat16*)f.beta)[c]) : ((const float*)f.beta)[c];
+        f.coef_a[c] = ga * is;
+        f.coef_b[c] = be - mu * ga * is;
+        if (f.running_mean) {
+            const float unbiased = M > 1 ? var * (float)M / (float)(M - 1) : var;
+            f.running_mean[c] = (1.f - f.momentum) * f.running_mean[c] + f.momentum * mu;
+            f.running_var[c] = (1.f - f.momentum) * f.running_var[c] + f.momentum * unbiased;
+        }
+    }
+    if (threadIdx.x == 0) *reinterpret_cast<unsigned*>(ws + 2 * C) = 0u;
+}
+
+__device__ __forceinline__ void bwd_finalize_from_acc(float* ws, int C, long long M, const BnBwdFin& f) {
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+        const float s = __ldcg(ws + c), q = __ldcg(ws + C + c);
+        ws[c] = 0.f; ws[C + c] = 0.f;
+        const float is = f.invstd[c];
+        float ga = 1.f;
+        if (f.gamma) ga = f.p_bf16 ? __bfloat162float(((const __nv_bfloat16*)f.gamma)[c]) : ((const float*)f.gamma)[c];
+        if (f.dgamma) { if (f.p_bf16) ((__nv_bfloat16*)f.dgamma)[c] = __float2bfloat16_rn(q * is); else ((float*)f.dgamma)[c] = q * is; }
+        if (f.dbeta) { if (f.p_bf16) ((__nv_bfloat16*)f.dbeta)[c] = __float2bfloat16_rn(s); else ((float*)f.dbeta)[c] = s; }
+        const float inv_m = 1.f / (float)M;
+        f.c1[c] = ga * is; f.c2[c] = s * inv_m; f.c3[c] = q * is * is * inv_m;
+    }
+    if (threadIdx.x == 0) *reinterpret_cast<unsigned*>(ws + 2 * C) = 0u;
+}
+
 // ---- forward: partial statistics --------------------------------------------------------------------------------------
 // partial[blk][0][C] = sum(x - K), partial[blk][1][C] = sum((x-K)^2), K = x[row 0]
-__global__ void __launch_bounds__(kBnThreads) bn_stats_kernel(const uint4* __restrict__ x, long long M, int LC, float* __restrict__ partial) {
+__global__ void __launch_bounds__(kBnThreads) bn_stats_kernel(const uint4* __restrict__ x, long long M, int LC, float* __restrict__ partial,
+                                                              float* ws, BnFwdFin fin) {
     extern __shared__ float sm[];                       // [kBnThreads][16]
     const int lane = threadIdx.x % LC;
     const int ty = threadIdx.x / LC;
@@ -53,10 +122,16 @@ __global__ void __launch_bounds__(kBnThreads) bn_stats_kernel(const uint4* __res
             for (int j = 0; j < 8; ++j) { s[j] += o[j]; q[j] += o[8 + j]; }
         }
         const int C = LC * 8;
-        float* ps = partial + (long long)blockIdx.x * 2 * C + lane * 8;
+        if (ws) {
 #pragma unroll
-        for (int j = 0; j < 8; ++j) { ps[j] = s[j]; ps[C + j] = q[j]; }
+            for (int j = 0; j < 8; ++j) { atomicAdd(ws + lane * 8 + j, s[j]); atomicAdd(ws + C + lane * 8 + j, q[j]); }
+        } else {
+            float* ps = partial + (long long)blockIdx.x * 2 * C + lane * 8;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) { ps[j] = s[j]; ps[C + j] = q[j]; }
+        }
     }
+    if (ws && last_cta_ticket(ws, LC * 8)) fwd_finalize_from_acc(ws, LC * 8, M, fin);
 }
 
 // one CTA per 32 channels, 8 partial-groups x 32 channels
@@ -152,7 +227,8 @@ __global__ void __launch_bounds__(kBnThreads) bn_apply_kernel(const uint4* __res
 // dy = dz * (z > 0) if RELU else dz;  partial[blk][0][C] = sum(dy), partial[blk][1][C] = sum(dy * (x - mean))
 template <bool RELU>
 __global__ void __launch_bounds__(kBnThreads) bn_bwd_reduce_kernel(const uint4* __restrict__ dz, const uint4* __restrict__ z, const uint4* __restrict__ x,
-                                                                   const float* __restrict__ mean, long long M, int LC, float* __restrict__ partial) {
+                                                                   const float* __restrict__ mean, long long M, int LC, float* __restrict__ partial,
+                                                                   float* ws, BnBwdFin fin) {
     extern __shared__ float sm[];
     const int lane = threadIdx.x % LC, ty = threadIdx.x / LC, RP = kBnThreads / LC;
     float mu[8], s[8], q[8];
@@ -186,10 +262,16 @@ __global__ void __launch_bounds__(kBnThreads) bn_bwd_reduce_kernel(const uint4* 
             for (int j = 0; j < 8; ++j) { s[j] += o[j]; q[j] += o[8 + j]; }
         }
         const int C = LC * 8;
-        float* ps = partial + (long long)blockIdx.x * 2 * C + lane * 8;
+        if (ws) {
 #pragma unroll
-        for (int j = 0; j < 8; ++j) { ps[j] = s[j]; ps[C + j] = q[j]; }
+            for (int j = 0; j < 8; ++j) { atomicAdd(ws + lane * 8 + j, s[j]); atomicAdd(ws + C + lane * 8 + j, q[j]); }
+        } else {
+            float* ps = partial + (long long)blockIdx.x * 2 * C + lane * 8;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) { ps[j] = s[j]; ps[C + j] = q[j]; }
+        }
     }
+    if (ws && last_cta_ticket(ws, LC * 8)) bwd_finalize_from_acc(ws, LC * 8, M, fin);
 }
 
 // dgamma = sum(dy*xhat) = invstd*sum(dy*(x-mean)); dbeta = sum(dy);
@@ -271,7 +353,8 @@ static void check_act(const at::Tensor& t, const char* name) {
 // returns {z, mean, invstd}
 std::vector<at::Tensor> bn_forward(at::Tensor x, c10::optional<at::Tensor> gamma, c10::optional<at::Tensor> beta,
                                    c10::optional<at::Tensor> running_mean, c10::optional<at::Tensor> running_var,
-                                   c10::optional<at::Tensor> residual, bool training, double momentum, double eps, bool relu) {
+                                   c10::optional<at::Tensor> residual, bool training, double momentum, double eps, bool relu,
+                                   c10::optional<at::Tensor> ws) {
     check_act(x, "x");
     const int C = (int)x.size(1);
     const long long M = x.numel() / C;
@@ -292,8 +375,15 @@ std::vector<at::Tensor> bn_forward(at::Tensor x, c10::optional<at::Tensor> gamma
     if (training) {
         const int RP = kBnThreads / LC;
         const int nblk = stream_grid(M, RP * 8);
+        if (ws.has_value()) {
+            TORCH_CHECK(ws->scalar_type() == at::kFloat && ws->numel() >= 2 * C + 1 && ws->is_cuda(), "bn workspace must hold 2*C+1 floats");
+            BnFwdFin fin{(const __nv_bfloat16*)x.data_ptr(), gp, bp, rm, rv, (float)momentum, (float)eps, mean.data_ptr<float>(), invstd.data_ptr<float>(),
+                         ca.data_ptr<float>(), cb.data_ptr<float>(), p_bf16 ? 1 : 0};
+            bn_stats_kernel<<<nblk, kBnThreads, kBnThreads * 16 * sizeof(float), stream>>>(xp, M, LC, nullptr, ws->data_ptr<float>(), fin);
+            C10_CUDA_KERNEL_LAUNCH_CHECK();
+        } else {
         at::Tensor partial = at::empty({nblk, 2, C}, fopt);
-        bn_stats_kernel<<<nblk, kBnThreads, kBnThreads * 16 * sizeof(float), stream>>>(xp, M, LC, partial.data_ptr<float>());
+        bn_stats_kernel<<<nblk, kBnThreads, kBnThreads * 16 * sizeof(float), stream>>>(xp, M, LC, partial.data_ptr<float>(), nullptr, BnFwdFin{});
         C10_CUDA_KERNEL_LAUNCH_CHECK();
         const int fb = (C + 31) / 32;
         if (p_bf16)
@@ -305,6 +395,7 @@ std::vector<at::Tensor> bn_forward(at::Tensor x, c10::optional<at::Tensor> gamma
                 (const float*)gp, (const float*)bp, rm, rv, (float)momentum, (float)eps, mean.data_ptr<float>(), invstd.data_ptr<float>(),
                 ca.data_ptr<float>(), cb.data_ptr<float>());
         C10_CUDA_KERNEL_LAUNCH_CHECK();
+        }
     } else {
         TORCH_CHECK(rm && rv, "bn eval needs running statistics");
         if (p_bf16) bn_eval_coef_kernel<__nv_bfloat16><<<(C + 127) / 128, 128, 0, stream>>>(C, (const __nv_bfloat16*)gp, (const __nv_bfloat16*)bp, rm, rv, (float)eps, ca.data_ptr<float>(), cb.data_ptr<float>());
@@ -326,7 +417,7 @@ std::vector<at::Tensor> bn_forward(at::Tensor x, c10::optional<at::Tensor> gamma
 
 // returns {dx, dres (or undefined), dgamma, dbeta}
 std::vector<at::Tensor> bn_backward(at::Tensor dz, at::Tensor z, at::Tensor x, c10::optional<at::Tensor> gamma, at::Tensor mean,
-                                    at::Tensor invstd, bool relu, bool has_res) {
+                                    at::Tensor invstd, bool relu, bool has_res, c10::optional<at::Tensor> ws) {
     check_act(dz, "dz"); check_act(x, "x");
     if (relu) check_act(z, "z");
     const int C = (int)x.size(1);
@@ -336,24 +427,34 @@ std::vector<at::Tensor> bn_backward(at::Tensor dz, at::Tensor z, at::Tensor x, c
     auto fopt = x.options().dtype(at::kFloat);
     const int RP = kBnThreads / LC;
     const int nblk = stream_grid(M, RP * 8);
-    at::Tensor partial = at::empty({nblk, 2, C}, fopt);
     const uint4 *dzp = (const uint4*)dz.data_ptr(), *zp = relu ? (const uint4*)z.data_ptr() : nullptr, *xp = (const uint4*)x.data_ptr();
-    if (relu) bn_bwd_reduce_kernel<true><<<nblk, kBnThreads, kBnThreads * 16 * sizeof(float), stream>>>(dzp, zp, xp, mean.data_ptr<float>(), M, LC, partial.data_ptr<float>());
-    else bn_bwd_reduce_kernel<false><<<nblk, kBnThreads, kBnThreads * 16 * sizeof(float), stream>>>(dzp, zp, xp, mean.data_ptr<float>(), M, LC, partial.data_ptr<float>());
-    C10_CUDA_KERNEL_LAUNCH_CHECK();
     at::Tensor c1 = at::empty({C}, fopt), c2 = at::empty({C}, fopt), c3 = at::empty({C}, fopt);
     at::Tensor dgamma, dbeta;
-    const int fb = (C + 31) / 32;
-    if (gamma.has_value() && gamma->scalar_type() == at::kBFloat16) {
-        dgamma = at::empty({C}, x.options()); dbeta = at::empty({C}, x.options());
-        bn_bwd_finalize_kernel<__nv_bfloat16><<<fb, 256, 0, stream>>>(partial.data_ptr<float>(), nblk, C, M, (const __nv_bfloat16*)gamma->data_ptr(), invstd.data_ptr<float>(),
-            (__nv_bfloat16*)dgamma.data_ptr(), (__nv_bfloat16*)dbeta.data_ptr(), c1.data_ptr<float>(), c2.data_ptr<float>(), c3.data_ptr<float>());
+    const bool p_bf16 = gamma.has_value() && gamma->scalar_type() == at::kBFloat16;
+    if (p_bf16) { dgamma = at::empty({C}, x.options()); dbeta = at::empty({C}, x.options()); }
+    else { dgamma = at::empty({C}, fopt); dbeta = at::empty({C}, fopt); }
+    const size_t smem = kBnThreads * 16 * sizeof(float);
+    if (ws.has_value()) {
+        TORCH_CHECK(ws->scalar_type() == at::kFloat && ws->numel() >= 2 * C + 1 && ws->is_cuda(), "bn workspace must hold 2*C+1 floats");
+        BnBwdFin fin{gamma.has_value() ? gamma->data_ptr() : nullptr, invstd.data_ptr<float>(), dgamma.data_ptr(), dbeta.data_ptr(),
+                     c1.data_ptr<float>(), c2.data_ptr<float>(), c3.data_ptr<float>(), p_bf16 ? 1 : 0};
+        if (relu) bn_bwd_reduce_kernel<true><<<nblk, kBnThreads, smem, stream>>>(dzp, zp, xp, mean.data_ptr<float>(), M, LC, nullptr, ws->data_ptr<float>(), fin);
+        else bn_bwd_reduce_kernel<false><<<nblk, kBnThreads, smem, stream>>>(dzp, zp, xp, mean.data_ptr<float>(), M, LC, nullptr, ws->data_ptr<float>(), fin);
+        C10_CUDA_KERNEL_LAUNCH_CHECK();
     } else {
-        dgamma = at::empty({C}, fopt); dbeta = at::empty({C}, fopt);
-        bn_bwd_finalize_kernel<float><<<fb, 256, 0, stream>>>(partial.data_ptr<float>(), nblk, C, M, gamma.has_value() ? gamma->data_ptr<float>() : nullptr, invstd.data_ptr<float>(),
-            dgamma.data_ptr<float>(), dbeta.data_ptr<float>(), c1.data_ptr<float>(), c2.data_ptr<float>(), c3.data_ptr<float>());
+        at::Tensor partial = at::empty({nblk, 2, C}, fopt);
+        if (relu) bn_bwd_reduce_kernel<true><<<nblk, kBnThreads, smem, stream>>>(dzp, zp, xp, mean.data_ptr<float>(), M, LC, partial.data_ptr<float>(), nullptr, BnBwdFin{});
+        else bn_bwd_reduce_kernel<false><<<nblk, kBnThreads, smem, stream>>>(dzp, zp, xp, mean.data_ptr<float>(), M, LC, partial.data_ptr<float>(), nullptr, BnBwdFin{});
+        C10_CUDA_KERNEL_LAUNCH_CHECK();
+        const int fb = (C + 31) / 32;
+        if (p_bf16)
+            bn_bwd_finalize_kernel<__nv_bfloat16><<<fb, 256, 0, stream>>>(partial.data_ptr<float>(), nblk, C, M, (const __nv_bfloat16*)gamma->data_ptr(), invstd.data_ptr<float>(),
+                (__nv_bfloat16*)dgamma.data_ptr(), (__nv_bfloat16*)dbeta.data_ptr(), c1.data_ptr<float>(), c2.data_ptr<float>(), c3.data_ptr<float>());
+        else
+            bn_bwd_finalize_kernel<float><<<fb, 256, 0, stream>>>(partial.data_ptr<float>(), nblk, C, M, gamma.has_value() ? gamma->data_ptr<float>() : nullptr, invstd.data_ptr<float>(),
+                dgamma.data_ptr<float>(), dbeta.data_ptr<float>(), c1.data_ptr<float>(), c2.data_ptr<float>(), c3.data_ptr<float>());
+        C10_CUDA_KERNEL_LAUNCH_CHECK();
     }
-    C10_CUDA_KERNEL_LAUNCH_CHECK();
     at::Tensor dx = at::empty_like(x);
     at::Tensor dres;
     if (has_res) dres = relu ? at::empty_like(x) : dz;       // without ReLU the residual gradient IS dz: no copy

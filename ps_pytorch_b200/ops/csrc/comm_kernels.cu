@@ -162,27 +162,40 @@ struct RUArgs {
     int advance_step;                     // last CTA bumps *step_ptr and hp->steps
 };
 
-__device__ __forceinline__ void load_src8(const RUArgs& a, int k, long long i, float* f) {
-    if (a.mode == WIRE_BF16) {
-        unpack8(ld_relaxed_sys_v4(reinterpret_cast<const __nv_bfloat16*>(a.src[k]) + i), f);
-    } else if (a.mode == WIRE_FP32) {
+// raw wire words of 8 elements from source k (kept packed in registers so that all K loads can be in flight at once)
+struct Raw8 { uint4 lo; uint4 hi; };        // bf16: lo only; fp32: lo+hi; fp8: lo.x,lo.y = payload, lo.z = scale byte
+template <int MODE>
+__device__ __forceinline__ void load_raw8(const RUArgs& a, int k, long long i, Raw8& r) {
+    if (MODE == WIRE_BF16) {
+        r.lo = ld_relaxed_sys_v4(reinterpret_cast<const __nv_bfloat16*>(a.src[k]) + i);
+    } else if (MODE == WIRE_FP32) {
         const float* s = reinterpret_cast<const float*>(a.src[k]) + i;
-        uint4 x = ld_relaxed_sys_v4(s), y = ld_relaxed_sys_v4(s + 4);
-        f[0] = __uint_as_float(x.x); f[1] = __uint_as_float(x.y); f[2] = __uint_as_float(x.z); f[3] = __uint_as_float(x.w);
-        f[4] = __uint_as_float(y.x); f[5] = __uint_as_float(y.y); f[6] = __uint_as_float(y.z); f[7] = __uint_as_float(y.w);
+        r.lo = ld_relaxed_sys_v4(s); r.hi = ld_relaxed_sys_v4(s + 4);
     } else {
         const uint8_t* q = reinterpret_cast<const uint8_t*>(a.src[k]) + i;
-        uint2 v;
-        asm volatile("ld.relaxed.sys.global.v2.u32 {%0,%1}, [%2];" : "=r"(v.x), "=r"(v.y) : "l"(q) : "memory");
-        uint32_t sb;
-        asm volatile("ld.relaxed.sys.global.u8 %0, [%1];" : "=r"(sb) : "l"(a.src_scale[k] + i / 32) : "memory");
-        const float sc = exp2i(max(-126, (int)sb - 127));
-        dequant4(v.x, sc, f);
-        dequant4(v.y, sc, f + 4);
+        asm volatile("ld.relaxed.sys.global.v2.u32 {%0,%1}, [%2];" : "=r"(r.lo.x), "=r"(r.lo.y) : "l"(q) : "memory");
+        asm volatile("ld.relaxed.sys.global.u8 %0, [%1];" : "=r"(r.lo.z) : "l"(a.src_scale[k] + i / 32) : "memory");
     }
 }
+template <int MODE>
+__device__ __forceinline__ void accum_raw8(const Raw8& r, float* g) {
+    float f[8];
+    if (MODE == WIRE_BF16) {
+        unpack8(r.lo, f);
+    } else if (MODE == WIRE_FP32) {
+        f[0] = __uint_as_float(r.lo.x); f[1] = __uint_as_float(r.lo.y); f[2] = __uint_as_float(r.lo.z); f[3] = __uint_as_float(r.lo.w);
+        f[4] = __uint_as_float(r.hi.x); f[5] = __uint_as_float(r.hi.y); f[6] = __uint_as_float(r.hi.z); f[7] = __uint_as_float(r.hi.w);
+    } else {
+        const float sc = exp2i(max(-126, (int)r.lo.z - 127));
+        dequant4(r.lo.x, sc, f);
+        dequant4(r.lo.y, sc, f + 4);
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) g[j] += f[j];
+}
 
-__global__ void __launch_bounds__(256) reduce_update_kernel(RUArgs a) {
+template <int MODE>
+__global__ void __launch_bounds__(256, 2) reduce_update_kernel(RUArgs a) {
     __shared__ unsigned s_mask;
     const long long step = *a.step_ptr;
     const OptHP hp = *a.hp;
@@ -211,17 +224,19 @@ __global__ void __launch_bounds__(256) reduce_update_kernel(RUArgs a) {
         for (long long i = a.lo[b] + ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 8; i < a.hi[b]; i += stride) {
             float g[8] = {0, 0, 0, 0, 0, 0, 0, 0};
             {
-                // issue every selected source's load before the first add: up to 8 independent 16-byte P2P/HBM loads in flight
-                float fs[kMaxPeers][8];
+                // issue every selected source's load before the first add: up to 8 independent P2P/HBM loads in flight per
+                // lane, held as packed wire words (4-8 registers each)
+                constexpr int kBatch = MODE == WIRE_FP32 ? 4 : kMaxPeers;
 #pragma unroll
-                for (int k = 0; k < kMaxPeers; ++k)
-                    if (k < a.P && (mask >> k & 1)) load_src8(a, k, i, fs[k]);
+                for (int k0 = 0; k0 < kMaxPeers; k0 += kBatch) {
+                    Raw8 raw[kBatch];
 #pragma unroll
-                for (int k = 0; k < kMaxPeers; ++k)
-                    if (k < a.P && (mask >> k & 1)) {
+                    for (int k = 0; k < kBatch; ++k)
+                        if (k0 + k < a.P && (mask >> (k0 + k) & 1)) load_raw8<MODE>(a, k0 + k, i, raw[k]);
 #pragma unroll
-                        for (int j = 0; j < 8; ++j) g[j] += fs[k][j];
-                    }
+                    for (int k = 0; k < kBatch; ++k)
+                        if (k0 + k < a.P && (mask >> (k0 + k) & 1)) accum_raw8<MODE>(raw[k], g);
+                }
             }
             float wf[8], x0[8], x1[8], x2[8];
             if (hp.kind != 2) {
@@ -366,7 +381,11 @@ void reduce_update(std::vector<int64_t> src, std::vector<int64_t> src_scale, int
     a.advance_step = advance_step;
     long long tot = 0;
     for (size_t b = 0; b < lo.size(); ++b) tot = std::max<long long>(tot, hi[b] - lo[b]);
-    reduce_update_kernel<<<grid_for(tot, 8), 256, 0, at::cuda::getCurrentCUDAStream()>>>(a);
+    const int grid = grid_for(tot, 8);
+    auto stream = at::cuda::getCurrentCUDAStream();
+    if (mode == WIRE_BF16) reduce_update_kernel<WIRE_BF16><<<grid, 256, 0, stream>>>(a);
+    else if (mode == WIRE_FP8) reduce_update_kernel<WIRE_FP8><<<grid, 256, 0, stream>>>(a);
+    else reduce_update_kernel<WIRE_FP32><<<grid, 256, 0, stream>>>(a);
     C10_CUDA_KERNEL_LAUNCH_CHECK();
 }
 

@@ -1,9 +1,26 @@
 """BatchNorm2d (+residual, +ReLU) autograd wrapper over ``csrc/bn_kernels.cu``."""
 from __future__ import annotations
 
+import os
+
 import torch
 
 from . import count_launch, require
+
+# Measured (profiles/run12.md): the fused last-CTA variant with fp32 atomics is SLOWER on B200 (8.19 vs 7.38 ms/step) — 592 CTAs
+# hammering 2*C addresses cost more than the extra launch — so the deterministic two-kernel path is the default.
+_DETERMINISTIC = os.environ.get("PSB200_BN_FUSED_FINALIZE", "0") == "0"
+
+
+def _workspace(module, c, device):
+    """Self-cleaning per-layer accumulator (2*C sums + ticket) for the fused stats/finalize kernels."""
+    if _DETERMINISTIC:
+        return None
+    ws = getattr(module, "_psb_ws", None)
+    if ws is None or ws.device != device or ws.numel() < 2 * c + 1:
+        ws = torch.zeros(2 * c + 1, dtype=torch.float32, device=device)
+        module._psb_ws = ws
+    return ws
 
 
 def bn_unsupported_reason(x: torch.Tensor):
@@ -20,15 +37,15 @@ def bn_unsupported_reason(x: torch.Tensor):
 
 class _BatchNormFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, x, weight, bias, residual, running_mean, running_var, training, momentum, eps, relu):
+    def forward(ctx, x, weight, bias, residual, running_mean, running_var, training, momentum, eps, relu, ws):
         ext = require()
         x = x.contiguous(memory_format=torch.channels_last)
         if residual is not None:
             residual = residual.contiguous(memory_format=torch.channels_last)
-        z, mean, invstd = ext.bn_forward(x, weight, bias, running_mean if training else running_mean,
-                                         running_var, residual, training, momentum, eps, relu)
-        count_launch(3 if training else 2)
-        ctx.relu, ctx.has_res, ctx.training = relu, residual is not None, training
+        z, mean, invstd = ext.bn_forward(x, weight, bias, running_mean, running_var, residual, training, momentum, eps, relu,
+                                         ws if training else None)
+        count_launch((2 if ws is not None else 3) if training else 2)
+        ctx.relu, ctx.has_res, ctx.training, ctx.ws = relu, residual is not None, training, ws
         ctx.save_for_backward(x, z if relu else None, weight, mean, invstd)
         return z
 
@@ -39,17 +56,17 @@ class _BatchNormFn(torch.autograd.Function):
             raise RuntimeError("bn backward in eval mode is not supported by the sm100 kernels")
         ext = require()
         dz = dz.contiguous(memory_format=torch.channels_last)
-        dx, dres, dgamma, dbeta = ext.bn_backward(dz, z if z is not None else x, x, weight, mean, invstd, ctx.relu, ctx.has_res)
-        count_launch(3)
+        dx, dres, dgamma, dbeta = ext.bn_backward(dz, z if z is not None else x, x, weight, mean, invstd, ctx.relu, ctx.has_res, ctx.ws)
+        count_launch(2 if ctx.ws is not None else 3)
         if weight is None:
             dgamma = dbeta = None
-        return dx, dgamma, dbeta, (dres if ctx.has_res else None), None, None, None, None, None, None
+        return dx, dgamma, dbeta, (dres if ctx.has_res else None), None, None, None, None, None, None, None
 
 
 def batch_norm(x, module, residual=None, relu=False):
     training = module.training or not module.track_running_stats
-    if training and module.track_running_stats and module.num_batches_tracked is not None:
+    if training and module.track_running_stats and module.num_batches_tracked is not None and not getattr(module, "external_counter", False):
         module.num_batches_tracked.add_(1)
     mom = 0.1 if module.momentum is None else module.momentum
     return _BatchNormFn.apply(x, module.weight, module.bias, residual, module.running_mean, module.running_var,
-                              training, mom, module.eps, relu)
+                              training, mom, module.eps, relu, _workspace(module, x.size(1), x.device))

@@ -106,6 +106,8 @@ class NvlTransport(Transport):
         self._hp_dev = None
         self._hp_key = None
         self._side = torch.cuda.Stream(device=self.device)
+        self._push_stream = torch.cuda.Stream(device=self.device)     # bucket pushes overlap the remaining backward
+        self._push_forked = False
         self._pushed = [False] * self.NB
         self.zeroes_grads = topology == "ps"
         torch.cuda.synchronize(self.device)
@@ -227,14 +229,23 @@ class NvlTransport(Transport):
     def _my_slot(self):
         return self.worker_slot(self.rank)
 
-    def worker_push_bucket(self, b: int, grads: FlatBuffer):
+    def worker_push_bucket(self, b: int, grads: FlatBuffer, last_bucket: bool = True):
         lo, hi = self.buckets[b]
         slot = self._my_slot()
         fp32 = grads.dtype == torch.float32
         if self.topology == "ps":
             base = self.arena.peer_ptrs[0] + self.off_slots + slot * self.slot_stride
-            self.ext.push(grads.flat.data_ptr(), fp32, base, base + self.slot_q_bytes, lo, hi,
-                          self._flag(0, self.F_GREADY + 8 * (slot * MAXB + b)), self.p_wstep, self.p_counters + 4 * (MAXB + b), self.wire, True)
+            side = self.NB > 1 and not last_bucket
+            if side:
+                # fork: the push of a finished bucket runs on a side stream while backward continues on the main one
+                # (inside a CUDA-graph capture this becomes a fork/join in the graph)
+                ev = torch.cuda.Event()
+                ev.record()
+                self._push_stream.wait_event(ev)
+                self._push_forked = True
+            with torch.cuda.stream(self._push_stream if side else torch.cuda.current_stream()):
+                self.ext.push(grads.flat.data_ptr(), fp32, base, base + self.slot_q_bytes, lo, hi,
+                              self._flag(0, self.F_GREADY + 8 * (slot * MAXB + b)), self.p_wstep, self.p_counters + 4 * (MAXB + b), self.wire, True)
             ops.count_launch()
             wbytes = {0: 2, 1: 1.03125, 2: 4}[self.wire]
             self.stats["push_bytes"] += int((hi - lo) * wbytes)
@@ -256,11 +267,16 @@ class NvlTransport(Transport):
         if hi is not None and not last:
             for b, (blo, bhi) in enumerate(self.buckets):
                 if blo >= lo and bhi <= hi and not self._pushed[b]:
-                    self.worker_push_bucket(b, grads)
+                    self.worker_push_bucket(b, grads, last_bucket=False)
             return
         for b in range(self.NB - 1, -1, -1):
             if not self._pushed[b]:
-                self.worker_push_bucket(b, grads)
+                self.worker_push_bucket(b, grads, last_bucket=True)
+        if self._push_forked:                      # join the side stream before the step counter moves on
+            ev = torch.cuda.Event()
+            ev.record(self._push_stream)
+            torch.cuda.current_stream().wait_event(ev)
+            self._push_forked = False
         self.ext.add_step(self.p_wstep, 1)
         ops.count_launch()
 
