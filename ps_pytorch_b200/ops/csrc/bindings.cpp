@@ -18,7 +18,8 @@ int64_t hp_steps(at::Tensor);
 // bn_kernels.cu
 std::vector<at::Tensor> bn_forward(at::Tensor, c10::optional<at::Tensor>, c10::optional<at::Tensor>, c10::optional<at::Tensor>, c10::optional<at::Tensor>,
                                    c10::optional<at::Tensor>, bool, double, double, bool, c10::optional<at::Tensor>);
-std::vector<at::Tensor> bn_backward(at::Tensor, at::Tensor, at::Tensor, c10::optional<at::Tensor>, at::Tensor, at::Tensor, bool, bool, c10::optional<at::Tensor>);
+std::vector<at::Tensor> bn_backward(at::Tensor, c10::optional<at::Tensor>, at::Tensor, c10::optional<at::Tensor>, at::Tensor, at::Tensor, bool, bool, c10::optional<at::Tensor>,
+                                    c10::optional<at::Tensor>, c10::optional<at::Tensor>);
 // elementwise.cu
 at::Tensor relu_forward(at::Tensor);
 at::Tensor relu_backward(at::Tensor, at::Tensor);

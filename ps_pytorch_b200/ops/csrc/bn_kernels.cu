@@ -225,29 +225,32 @@ __global__ void __launch_bounds__(kBnThreads) bn_apply_kernel(const uint4* __res
 
 // ---- backward: partial reductions ------------------------------------------------------------------------------------------
 // dy = dz * (z > 0) if RELU else dz;  partial[blk][0][C] = sum(dy), partial[blk][1][C] = sum(dy * (x - mean))
-template <bool RELU>
+// MASKX: the ReLU mask is recomputed from x (z > 0  <=>  a*x + b > 0 when there is no residual input), so the output tensor z
+// is not read at all: one of the three streamed tensors disappears from both backward passes of every BN+ReLU layer.
+template <bool RELU, bool MASKX>
 __global__ void __launch_bounds__(kBnThreads) bn_bwd_reduce_kernel(const uint4* __restrict__ dz, const uint4* __restrict__ z, const uint4* __restrict__ x,
                                                                    const float* __restrict__ mean, long long M, int LC, float* __restrict__ partial,
-                                                                   float* ws, BnBwdFin fin) {
+                                                                   float* ws, BnBwdFin fin, const float* __restrict__ coef_a, const float* __restrict__ coef_b) {
     extern __shared__ float sm[];
     const int lane = threadIdx.x % LC, ty = threadIdx.x / LC, RP = kBnThreads / LC;
-    float mu[8], s[8], q[8];
+    float mu[8], s[8], q[8], ca[8], cb[8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) { mu[j] = mean[lane * 8 + j]; s[j] = 0.f; q[j] = 0.f; }
+    for (int j = 0; j < 8; ++j) { mu[j] = mean[lane * 8 + j]; s[j] = 0.f; q[j] = 0.f; ca[j] = MASKX ? coef_a[lane * 8 + j] : 0.f; cb[j] = MASKX ? coef_b[lane * 8 + j] : 0.f; }
     const long long rstride = (long long)gridDim.x * RP;
     long long r = (long long)blockIdx.x * RP + ty;
-#define ACCB(idx) { float d[8], xx[8], zz[8]; unpack8(vd##idx, d); unpack8(vx##idx, xx); if (RELU) unpack8(vz##idx, zz); \
-        _Pragma("unroll") for (int j = 0; j < 8; ++j) { float dy = (RELU && !(zz[j] > 0.f)) ? 0.f : d[j]; s[j] += dy; q[j] = fmaf(dy, xx[j] - mu[j], q[j]); } }
+#define ACCB(idx) { float d[8], xx[8], zz[8]; unpack8(vd##idx, d); unpack8(vx##idx, xx); if (RELU && !MASKX) unpack8(vz##idx, zz); \
+        _Pragma("unroll") for (int j = 0; j < 8; ++j) { const float pre = MASKX ? fmaf(xx[j], ca[j], cb[j]) : zz[j]; \
+            float dy = (RELU && !(pre > 0.f)) ? 0.f : d[j]; s[j] += dy; q[j] = fmaf(dy, xx[j] - mu[j], q[j]); } }
     for (; r + rstride < M; r += 2 * rstride) {
         const long long i0 = r * LC + lane, i1 = (r + rstride) * LC + lane;
         uint4 vd0 = ld_nc_v4(dz + i0), vx0 = ld_nc_v4(x + i0), vd1 = ld_nc_v4(dz + i1), vx1 = ld_nc_v4(x + i1), vz0, vz1;
-        if (RELU) { vz0 = ld_nc_v4(z + i0); vz1 = ld_nc_v4(z + i1); }
+        if (RELU && !MASKX) { vz0 = ld_nc_v4(z + i0); vz1 = ld_nc_v4(z + i1); }
         ACCB(0) ACCB(1)
     }
     for (; r < M; r += rstride) {
         const long long i0 = r * LC + lane;
         uint4 vd0 = ld_nc_v4(dz + i0), vx0 = ld_nc_v4(x + i0), vz0;
-        if (RELU) vz0 = ld_nc_v4(z + i0);
+        if (RELU && !MASKX) vz0 = ld_nc_v4(z + i0);
         ACCB(0)
     }
 #undef ACCB
@@ -314,23 +317,25 @@ __global__ void __launch_bounds__(256) bn_bwd_finalize_kernel(const float* __res
     }
 }
 
-template <bool RELU, bool RES>
+template <bool RELU, bool RES, bool MASKX>
 __global__ void __launch_bounds__(kBnThreads) bn_bwd_apply_kernel(const uint4* __restrict__ dz, const uint4* __restrict__ z, const uint4* __restrict__ x,
                                                                   const float* __restrict__ mean, const float* __restrict__ c1, const float* __restrict__ c2,
                                                                   const float* __restrict__ c3, uint4* __restrict__ dx, uint4* __restrict__ dres,
-                                                                  long long nvec, int LC) {
+                                                                  long long nvec, int LC, const float* __restrict__ coef_a, const float* __restrict__ coef_b) {
     const int lane = threadIdx.x % LC;
-    float mu[8], k1[8], k2[8], k3[8];
+    float mu[8], k1[8], k2[8], k3[8], ca[8], cb[8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) { mu[j] = mean[lane * 8 + j]; k1[j] = c1[lane * 8 + j]; k2[j] = c2[lane * 8 + j]; k3[j] = c3[lane * 8 + j]; }
+    for (int j = 0; j < 8; ++j) { mu[j] = mean[lane * 8 + j]; k1[j] = c1[lane * 8 + j]; k2[j] = c2[lane * 8 + j]; k3[j] = c3[lane * 8 + j];
+                                  ca[j] = MASKX ? coef_a[lane * 8 + j] : 0.f; cb[j] = MASKX ? coef_b[lane * 8 + j] : 0.f; }
     const long long stride = (long long)gridDim.x * kBnThreads;
     for (long long i = (long long)blockIdx.x * kBnThreads + threadIdx.x; i < nvec; i += 2 * stride) {
         const bool two = i + stride < nvec;
         const long long i1 = two ? i + stride : i;
         uint4 vd0 = ld_nc_v4(dz + i), vx0 = ld_nc_v4(x + i), vd1 = ld_nc_v4(dz + i1), vx1 = ld_nc_v4(x + i1), vz0, vz1;
-        if (RELU) { vz0 = ld_nc_v4(z + i); vz1 = ld_nc_v4(z + i1); }
-#define APP(idx, off) { float d[8], xx[8], zz[8], o[8]; unpack8(vd##idx, d); unpack8(vx##idx, xx); if (RELU) unpack8(vz##idx, zz); \
-        _Pragma("unroll") for (int j = 0; j < 8; ++j) { float dy = (RELU && !(zz[j] > 0.f)) ? 0.f : d[j]; d[j] = dy; \
+        if (RELU && !MASKX) { vz0 = ld_nc_v4(z + i); vz1 = ld_nc_v4(z + i1); }
+#define APP(idx, off) { float d[8], xx[8], zz[8], o[8]; unpack8(vd##idx, d); unpack8(vx##idx, xx); if (RELU && !MASKX) unpack8(vz##idx, zz); \
+        _Pragma("unroll") for (int j = 0; j < 8; ++j) { const float pre = MASKX ? fmaf(xx[j], ca[j], cb[j]) : zz[j]; \
+            float dy = (RELU && !(pre > 0.f)) ? 0.f : d[j]; d[j] = dy; \
             o[j] = k1[j] * (dy - k2[j] - (xx[j] - mu[j]) * k3[j]); } \
         st_v4(dx + off, pack8(o)); if (RES && RELU) st_v4(dres + off, pack8(d)); }
         APP(0, i)
@@ -412,14 +417,19 @@ std::vector<at::Tensor> bn_forward(at::Tensor x, c10::optional<at::Tensor> gamma
     else if (rp) bn_apply_kernel<false, true><<<grid, kBnThreads, 0, stream>>>(xp, rp, zp, pa, pb, nvec, LC);
     else bn_apply_kernel<false, false><<<grid, kBnThreads, 0, stream>>>(xp, rp, zp, pa, pb, nvec, LC);
     C10_CUDA_KERNEL_LAUNCH_CHECK();
-    return {z, mean, invstd};
+    return {z, mean, invstd, ca, cb};
 }
 
 // returns {dx, dres (or undefined), dgamma, dbeta}
-std::vector<at::Tensor> bn_backward(at::Tensor dz, at::Tensor z, at::Tensor x, c10::optional<at::Tensor> gamma, at::Tensor mean,
-                                    at::Tensor invstd, bool relu, bool has_res, c10::optional<at::Tensor> ws) {
+std::vector<at::Tensor> bn_backward(at::Tensor dz, c10::optional<at::Tensor> z_opt, at::Tensor x, c10::optional<at::Tensor> gamma, at::Tensor mean,
+                                    at::Tensor invstd, bool relu, bool has_res, c10::optional<at::Tensor> ws,
+                                    c10::optional<at::Tensor> coef_a, c10::optional<at::Tensor> coef_b) {
     check_act(dz, "dz"); check_act(x, "x");
-    if (relu) check_act(z, "z");
+    const bool maskx = relu && !has_res && coef_a.has_value() && coef_b.has_value();
+    at::Tensor z = z_opt.has_value() ? *z_opt : x;
+    if (relu && !maskx) { TORCH_CHECK(z_opt.has_value(), "bn backward with ReLU + residual needs the saved output"); check_act(z, "z"); }
+    const float* pca = maskx ? coef_a->data_ptr<float>() : nullptr;
+    const float* pcb = maskx ? coef_b->data_ptr<float>() : nullptr;
     const int C = (int)x.size(1);
     const long long M = x.numel() / C;
     const int LC = C / 8;
@@ -427,7 +437,7 @@ std::vector<at::Tensor> bn_backward(at::Tensor dz, at::Tensor z, at::Tensor x, c
     auto fopt = x.options().dtype(at::kFloat);
     const int RP = kBnThreads / LC;
     const int nblk = stream_grid(M, RP * 8);
-    const uint4 *dzp = (const uint4*)dz.data_ptr(), *zp = relu ? (const uint4*)z.data_ptr() : nullptr, *xp = (const uint4*)x.data_ptr();
+    const uint4 *dzp = (const uint4*)dz.data_ptr(), *zp = (relu && !maskx) ? (const uint4*)z.data_ptr() : nullptr, *xp = (const uint4*)x.data_ptr();
     at::Tensor c1 = at::empty({C}, fopt), c2 = at::empty({C}, fopt), c3 = at::empty({C}, fopt);
     at::Tensor dgamma, dbeta;
     const bool p_bf16 = gamma.has_value() && gamma->scalar_type() == at::kBFloat16;
@@ -438,13 +448,15 @@ std::vector<at::Tensor> bn_backward(at::Tensor dz, at::Tensor z, at::Tensor x, c
         TORCH_CHECK(ws->scalar_type() == at::kFloat && ws->numel() >= 2 * C + 1 && ws->is_cuda(), "bn workspace must hold 2*C+1 floats");
         BnBwdFin fin{gamma.has_value() ? gamma->data_ptr() : nullptr, invstd.data_ptr<float>(), dgamma.data_ptr(), dbeta.data_ptr(),
                      c1.data_ptr<float>(), c2.data_ptr<float>(), c3.data_ptr<float>(), p_bf16 ? 1 : 0};
-        if (relu) bn_bwd_reduce_kernel<true><<<nblk, kBnThreads, smem, stream>>>(dzp, zp, xp, mean.data_ptr<float>(), M, LC, nullptr, ws->data_ptr<float>(), fin);
-        else bn_bwd_reduce_kernel<false><<<nblk, kBnThreads, smem, stream>>>(dzp, zp, xp, mean.data_ptr<float>(), M, LC, nullptr, ws->data_ptr<float>(), fin);
+        if (maskx) bn_bwd_reduce_kernel<true, true><<<nblk, kBnThreads, smem, stream>>>(dzp, zp, xp, mean.data_ptr<float>(), M, LC, nullptr, ws->data_ptr<float>(), fin, pca, pcb);
+        else if (relu) bn_bwd_reduce_kernel<true, false><<<nblk, kBnThreads, smem, stream>>>(dzp, zp, xp, mean.data_ptr<float>(), M, LC, nullptr, ws->data_ptr<float>(), fin, pca, pcb);
+        else bn_bwd_reduce_kernel<false, false><<<nblk, kBnThreads, smem, stream>>>(dzp, zp, xp, mean.data_ptr<float>(), M, LC, nullptr, ws->data_ptr<float>(), fin, pca, pcb);
         C10_CUDA_KERNEL_LAUNCH_CHECK();
     } else {
         at::Tensor partial = at::empty({nblk, 2, C}, fopt);
-        if (relu) bn_bwd_reduce_kernel<true><<<nblk, kBnThreads, smem, stream>>>(dzp, zp, xp, mean.data_ptr<float>(), M, LC, partial.data_ptr<float>(), nullptr, BnBwdFin{});
-        else bn_bwd_reduce_kernel<false><<<nblk, kBnThreads, smem, stream>>>(dzp, zp, xp, mean.data_ptr<float>(), M, LC, partial.data_ptr<float>(), nullptr, BnBwdFin{});
+        if (maskx) bn_bwd_reduce_kernel<true, true><<<nblk, kBnThreads, smem, stream>>>(dzp, zp, xp, mean.data_ptr<float>(), M, LC, partial.data_ptr<float>(), nullptr, BnBwdFin{}, pca, pcb);
+        else if (relu) bn_bwd_reduce_kernel<true, false><<<nblk, kBnThreads, smem, stream>>>(dzp, zp, xp, mean.data_ptr<float>(), M, LC, partial.data_ptr<float>(), nullptr, BnBwdFin{}, pca, pcb);
+        else bn_bwd_reduce_kernel<false, false><<<nblk, kBnThreads, smem, stream>>>(dzp, zp, xp, mean.data_ptr<float>(), M, LC, partial.data_ptr<float>(), nullptr, BnBwdFin{}, pca, pcb);
         C10_CUDA_KERNEL_LAUNCH_CHECK();
         const int fb = (C + 31) / 32;
         if (p_bf16)
@@ -463,9 +475,10 @@ std::vector<at::Tensor> bn_backward(at::Tensor dz, at::Tensor z, at::Tensor x, c
     uint4* dxp = (uint4*)dx.data_ptr();
     uint4* drp = (has_res && relu) ? (uint4*)dres.data_ptr() : nullptr;
     const float *mp = mean.data_ptr<float>(), *p1 = c1.data_ptr<float>(), *p2 = c2.data_ptr<float>(), *p3 = c3.data_ptr<float>();
-    if (relu && has_res) bn_bwd_apply_kernel<true, true><<<grid, kBnThreads, 0, stream>>>(dzp, zp, xp, mp, p1, p2, p3, dxp, drp, nvec, LC);
-    else if (relu) bn_bwd_apply_kernel<true, false><<<grid, kBnThreads, 0, stream>>>(dzp, zp, xp, mp, p1, p2, p3, dxp, drp, nvec, LC);
-    else bn_bwd_apply_kernel<false, false><<<grid, kBnThreads, 0, stream>>>(dzp, zp, xp, mp, p1, p2, p3, dxp, drp, nvec, LC);
+    if (relu && has_res) bn_bwd_apply_kernel<true, true, false><<<grid, kBnThreads, 0, stream>>>(dzp, zp, xp, mp, p1, p2, p3, dxp, drp, nvec, LC, pca, pcb);
+    else if (maskx) bn_bwd_apply_kernel<true, false, true><<<grid, kBnThreads, 0, stream>>>(dzp, zp, xp, mp, p1, p2, p3, dxp, drp, nvec, LC, pca, pcb);
+    else if (relu) bn_bwd_apply_kernel<true, false, false><<<grid, kBnThreads, 0, stream>>>(dzp, zp, xp, mp, p1, p2, p3, dxp, drp, nvec, LC, pca, pcb);
+    else bn_bwd_apply_kernel<false, false, false><<<grid, kBnThreads, 0, stream>>>(dzp, zp, xp, mp, p1, p2, p3, dxp, drp, nvec, LC, pca, pcb);
     C10_CUDA_KERNEL_LAUNCH_CHECK();
     return {dx, dres, dgamma, dbeta};
 }

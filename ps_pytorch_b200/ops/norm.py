@@ -9,6 +9,10 @@ from . import count_launch, require
 
 # Measured (profiles/run12.md): the fused last-CTA variant with fp32 atomics is SLOWER on B200 (8.19 vs 7.38 ms/step) — 592 CTAs
 # hammering 2*C addresses cost more than the extra launch — so the deterministic two-kernel path is the default.
+# Recomputing the ReLU mask from x instead of re-reading the output z saves one streamed tensor per backward pass on paper, but
+# measured A/B on B200 (same job, 2 repeats): 7.59 ms/step with it vs 7.44 without — z is still L2-hot from the next layer's
+# wgrad and the 16 extra registers cost occupancy.  Off by default.
+_MASKX = os.environ.get("PSB200_BN_MASKX", "0") != "0"
 _DETERMINISTIC = os.environ.get("PSB200_BN_FUSED_FINALIZE", "0") == "0"
 
 
@@ -42,21 +46,23 @@ class _BatchNormFn(torch.autograd.Function):
         x = x.contiguous(memory_format=torch.channels_last)
         if residual is not None:
             residual = residual.contiguous(memory_format=torch.channels_last)
-        z, mean, invstd = ext.bn_forward(x, weight, bias, running_mean, running_var, residual, training, momentum, eps, relu,
-                                         ws if training else None)
+        z, mean, invstd, ca, cb = ext.bn_forward(x, weight, bias, running_mean, running_var, residual, training, momentum, eps, relu,
+                                                 ws if training else None)
         count_launch((2 if ws is not None else 3) if training else 2)
         ctx.relu, ctx.has_res, ctx.training, ctx.ws = relu, residual is not None, training, ws
-        ctx.save_for_backward(x, z if relu else None, weight, mean, invstd)
+        # BN+ReLU without a residual: the backward recomputes the ReLU mask from x (a*x+b > 0), so z is neither saved nor re-read
+        maskx = relu and residual is None and _MASKX
+        ctx.save_for_backward(x, z if (relu and not maskx) else None, weight, mean, invstd, ca if maskx else None, cb if maskx else None)
         return z
 
     @staticmethod
     def backward(ctx, dz):
-        x, z, weight, mean, invstd = ctx.saved_tensors
+        x, z, weight, mean, invstd, ca, cb = ctx.saved_tensors
         if not ctx.training:
             raise RuntimeError("bn backward in eval mode is not supported by the sm100 kernels")
         ext = require()
         dz = dz.contiguous(memory_format=torch.channels_last)
-        dx, dres, dgamma, dbeta = ext.bn_backward(dz, z if z is not None else x, x, weight, mean, invstd, ctx.relu, ctx.has_res, ctx.ws)
+        dx, dres, dgamma, dbeta = ext.bn_backward(dz, z, x, weight, mean, invstd, ctx.relu, ctx.has_res, ctx.ws, ca, cb)
         count_launch(2 if ctx.ws is not None else 3)
         if weight is None:
             dgamma = dbeta = None
