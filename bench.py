@@ -51,6 +51,7 @@ def parse():
     ap.add_argument("--overlap", action="store_true")
     ap.add_argument("--optimizer", type=str, default="sgd")
     ap.add_argument("--skip-e2e", action="store_true")
+    ap.add_argument("--no-stage", dest="stage", action="store_false", help="do not prefetch the next batch's H2D copy")
     return ap.parse_args()
 
 
@@ -152,6 +153,8 @@ def main():
         last = None
         for i in range(nsteps):
             last = job.step(xs[i % nb], ys[i % nb])
+            if a.stage:
+                job.stage(xs[(i + 1) % nb], ys[(i + 1) % nb])     # next batch's H2D overlaps this step
             if read_loss and last is not None:
                 last = float(last)            # D2H read of the step's result, every step
         return last

@@ -89,5 +89,10 @@ class PSJob:
             m.cur_step += 1
         return self.last_loss
 
+    def stage(self, x_host: torch.Tensor, y_host: torch.Tensor) -> None:
+        """Announce the next step's batch so its host→device copy overlaps the current step (see ``WorkerCompute.stage``)."""
+        if self.worker is not None:
+            self.worker.compute.stage(x_host, y_host)
+
     def close(self):
         self.comm.close()

@@ -27,6 +27,10 @@ class Conv2d(nn.Conv2d):
             if why is None:
                 return _conv.conv2d(x, self.weight, self.bias, self.stride, self.padding, relu)
             note_fallback("conv2d", why)
+            from ..ops import libconv as _lc
+            if _lc.enabled() and torch.is_grad_enabled() and not isinstance(self.padding, str):
+                y = _lc.conv2d(x, self.weight, self.bias, self.stride, self.padding, self.dilation, self.groups)
+                return F.relu(y) if relu else y
         y = F.conv2d(x, self.weight, self.bias, self.stride, self.padding, self.dilation, self.groups)
         return F.relu(y) if relu else y
 

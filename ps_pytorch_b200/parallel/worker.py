@@ -130,15 +130,22 @@ class DistributedWorker(object):
         total = len(train_loader.dataset)
         self._done = False
         for num_epoch in range(self.max_epochs):
-            for batch_idx, (xb, yb) in enumerate(train_loader):
-                if not self._one_step(xb, yb, num_epoch, batch_idx, total):
+            it = iter(train_loader)
+            nxt = next(it, None)
+            batch_idx = 0
+            while nxt is not None:
+                xb, yb = nxt
+                nxt = next(it, None)
+                ok = self._one_step(xb, yb, num_epoch, batch_idx, total, nxt)
+                batch_idx += 1
+                if not ok:
                     self._done = True
                     break
             if self._done:
                 break
         self._jsonl.close()
 
-    def _one_step(self, xb, yb, num_epoch=0, batch_idx=0, total=0) -> bool:
+    def _one_step(self, xb, yb, num_epoch=0, batch_idx=0, total=0, next_batch=None) -> bool:
         iter_start = time.time()
         t0 = time.time()
         self.sync_fetch_step()                                            # C1 + C2
@@ -154,6 +161,8 @@ class DistributedWorker(object):
         killed = False
         try:
             loss, logits = self.compute.train_step(xb, yb, self.cur_step)
+            if next_batch is not None and next_batch[0].is_pinned():
+                self.compute.stage(next_batch[0], next_batch[1])       # overlap the next batch's H2D with this step
         except StragglerKilled:
             killed = True
         c0 = time.time()
