@@ -27,7 +27,8 @@ class PSJob:
                  lr: float = 0.1, momentum: float = 0.9, optimizer: str = "sgd", weight_decay: float = 0.0, nesterov: bool = False,
                  transport: str = "auto", topology: str = "ps", colocate: bool = True, grad_dtype: str = "bf16", num_aggregate: Optional[int] = None,
                  overlap: bool = False, num_buckets: int = 4, cuda_graph: bool = True, backend: str = "auto", max_steps: int = 10 ** 9,
-                 eval_freq: int = 10 ** 9, train_dir: str = "output/models/", mode: str = "normal", compress: bool = False, seed: int = 1):
+                 eval_freq: int = 10 ** 9, train_dir: str = "output/models/", mode: str = "normal", compress: bool = False, seed: int = 1,
+                 comm_type: str = "Bcast"):
         self.device = torch.device(device)
         self.rank = dist.get_rank() if dist.is_initialized() else 0
         self.world = dist.get_world_size() if dist.is_initialized() else 1
@@ -48,7 +49,8 @@ class PSJob:
         else:
             from .parallel.nvl import NvlTransport
             self.comm = NvlTransport(self.layout, self.device, grad_dtype=grad_dtype, colocate=colocate,
-                                     num_buckets=num_buckets if overlap else 1, topology=topology, n_buffers=n_buf)
+                                     num_buckets=num_buckets if overlap else 1, topology=topology, n_buffers=n_buf,
+                                     pull_weights=comm_type.lower() == "async")
         self.topology = getattr(self.comm, "topology", "ps")
         P = self.comm.num_workers
         self.k = P if num_aggregate is None else max(1, min(num_aggregate, P))

@@ -277,7 +277,8 @@ __global__ void __launch_bounds__(256, 2) reduce_update_kernel(RUArgs a) {
                 multimem_st_v4(reinterpret_cast<__nv_bfloat16*>(a.mc_dst) + i, lp);
             } else {
 #pragma unroll 1
-                for (int d = 0; d < a.D; ++d) st_na_v4(reinterpret_cast<__nv_bfloat16*>(a.dst[d]) + i, lp);
+                for (int d = 0; d < a.D; ++d)
+                    if (d == 0 || a.dst[d] != a.dst[0]) st_na_v4(reinterpret_cast<__nv_bfloat16*>(a.dst[d]) + i, lp);   // pull mode lists the PS replica D times
             }
         }
         __threadfence_system();

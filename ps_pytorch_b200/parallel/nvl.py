@@ -44,7 +44,8 @@ class NvlTransport(Transport):
     fused_lowp = True            # the reduce-update kernel writes the low-precision replicas itself
 
     def __init__(self, layout: ParamLayout, device, grad_dtype: str = "bf16", colocate: bool = False, num_buckets: int = 1,
-                 topology: str = "ps", n_buffers: int = 0, timeout_s: float = None, weight_dtype: torch.dtype = torch.bfloat16):
+                 topology: str = "ps", n_buffers: int = 0, timeout_s: float = None, weight_dtype: torch.dtype = torch.bfloat16,
+                 pull_weights: bool = False):
         rank = dist.get_rank() if dist.is_initialized() else 0
         world = dist.get_world_size() if dist.is_initialized() else 1
         if world == 1:
@@ -110,6 +111,9 @@ class NvlTransport(Transport):
         self._push_forked = False
         self._pushed = [False] * self.NB
         self.zeroes_grads = topology == "ps"
+        # --comm-type Async: the PS only publishes a version; every worker PULLS the weights from the PS replica with P2P loads
+        # (the reference's point-to-point weight fetch, distributed_worker.py:201-219, which has no sender in that snapshot)
+        self.pull_weights = bool(pull_weights) and topology == "ps" and world > 1
         torch.cuda.synchronize(self.device)
 
     # ---- storage handed to the roles -------------------------------------------------------------------------------
@@ -133,6 +137,10 @@ class NvlTransport(Transport):
     def _dests(self):
         return list(self.worker_ranks)
 
+    def _weight_dests(self):
+        """Replicas the PS kernel stores into: everyone (push/multicast), or only its own when workers pull."""
+        return [0] if self.pull_weights else list(self.worker_ranks)
+
     def ps_publish(self, step, weights):
         """Step 1 / resume: copy the PS's bf16 weights (already in its W region) to every replica and release the
         ready flags.  Later steps are published by the reduce-update kernel itself."""
@@ -143,10 +151,14 @@ class NvlTransport(Transport):
             return
         assert weights.flat.data_ptr() == self.arena.local_ptr + self.off_w, "PS low-precision copy must live in the arena"
         d = self._dests()
-        use_mc = self.arena.mc_ptr and len(d) == self.world_size
+        use_mc = self.arena.mc_ptr and len(d) == self.world_size and not self.pull_weights
         nfl = self.NB if self.topology == "ps" else self.world_size
-        self.ext.bcast(self.arena.local_ptr + self.off_w, [self._wptr(r) for r in d], (self.arena.mc_ptr + self.off_w) if use_mc else 0,
-                       self.T * 2, [self._flag(r, self.F_WREADY) for r in d], nfl, self.p_psstep, 0, self.p_counters + 4 * 2 * MAXB)
+        if self.pull_weights:      # nothing to copy (the PS replica is the source of truth); just release the version flags
+            self.ext.bcast(self.arena.local_ptr + self.off_w, [self._wptr(r) for r in d], 0, 0, [self._flag(r, self.F_WREADY) for r in d], nfl,
+                           self.p_psstep, 0, self.p_counters + 4 * 2 * MAXB)
+        else:
+            self.ext.bcast(self.arena.local_ptr + self.off_w, [self._wptr(r) for r in d], (self.arena.mc_ptr + self.off_w) if use_mc else 0,
+                           self.T * 2, [self._flag(r, self.F_WREADY) for r in d], nfl, self.p_psstep, 0, self.p_counters + 4 * 2 * MAXB)
         ops.count_launch()
         self._published = step
         self.stats["bcast_bytes"] += self.T * 2
@@ -187,13 +199,13 @@ class NvlTransport(Transport):
             wready = [self._flag(r, self.F_WREADY + 8 * self.rank) for r in self._dests()]
         take = min(P, (k + 1) if strict_reference else k)
         d = self._dests()
-        use_mc = bool(self.arena.mc_ptr) and len(d) == self.world_size
+        use_mc = bool(self.arena.mc_ptr) and len(d) == self.world_size and not self.pull_weights
         if kind == 0:
             s0, s1, s2 = fs["buf"], None, None
         else:
             s0, s1, s2 = fs["m"], fs["v"], fs["vmax"]
         self.ext.reduce_update(src, scl, int(take), 1.0 / float(k), int(mode), self.arena.local_ptr + self.off_flags + self.F_GREADY,
-                               self.p_psstep, lo, hi, master.flat, s0, s1, s2, hp_ptr, [self._wptr(r) for r in d],
+                               self.p_psstep, lo, hi, master.flat, s0, s1, s2, hp_ptr, self._ru_dst(d),
                                (self.arena.mc_ptr + self.off_w) if use_mc else 0, wready, self.p_counters, self.p_err,
                                float(timeout_s or self.timeout_s), True)
         ops.count_launch()
@@ -201,6 +213,11 @@ class NvlTransport(Transport):
         self._host_psstep += 1
         self._published = step + 1
         self.stats["bcast_bytes"] += self.T * 2
+
+    def _ru_dst(self, d):
+        # the kernel walks dst[] and w_ready[] with one index: in pull mode every entry stores to the PS replica (idempotent) while
+        # each worker still gets its own version flag
+        return [self._wptr(0 if self.pull_weights else r) for r in d]
 
     def ps_signal_kill(self, ranks, step):
         for r in ranks:
@@ -222,6 +239,11 @@ class NvlTransport(Transport):
         n = self.NB if self.topology == "ps" else self.world_size
         self.ext.wait_flag(self.arena.local_ptr + self.off_flags + self.F_WREADY, n, self.p_wstep, self.p_err, self.timeout_s)
         ops.count_launch()
+        if self.pull_weights and self.rank != 0:
+            # P2P pull of the fresh weights from the PS replica into ours (no flags to release: nflags = 0)
+            self.ext.bcast(self.arena.peer_ptrs[0] + self.off_w, [self.arena.local_ptr + self.off_w], 0, self.T * 2,
+                           [self._flag(self.rank, self.F_WREADY)], 0, self.p_wstep, 0, self.p_counters + 4 * (2 * MAXB + 2))
+            ops.count_launch()
         self._host_wstep += 1
         self._pushed = [False] * self.NB
         return self._host_wstep

@@ -69,7 +69,8 @@ def make_transport(args, layout: ParamLayout, device: torch.device, world: int):
         gd = args.grad_dtype
         if gd == "auto":
             gd = "fp8" if compress else "bf16"
-        return NvlTransport(layout, device, grad_dtype=gd, colocate=args.colocate_worker, num_buckets=(args.num_buckets if args.overlap else 1))
+        return NvlTransport(layout, device, grad_dtype=gd, colocate=args.colocate_worker, num_buckets=(args.num_buckets if args.overlap else 1),
+                            pull_weights=str(args.comm_type).lower() == "async")
     raise ValueError(kind)
 
 

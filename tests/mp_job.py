@@ -33,6 +33,7 @@ def main():
     ap.add_argument("--overlap", type=int, default=0)
     ap.add_argument("--graph", type=int, default=0)
     ap.add_argument("--backend", default="auto")
+    ap.add_argument("--comm-type", default="Bcast")
     a = ap.parse_args()
     rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
     if a.device == "cuda":
@@ -44,7 +45,7 @@ def main():
     job = PSJob(network=a.network, dataset=ds, batch_size=a.bs, device=a.device, dtype=a.dtype, lr=0.05, momentum=0.9,
                 transport=a.transport, topology=a.topology, colocate=bool(a.colocate), grad_dtype=a.grad_dtype,
                 num_aggregate=(a.k or None), compress=bool(a.compress), overlap=bool(a.overlap), num_buckets=3,
-                cuda_graph=bool(a.graph), backend=a.backend, seed=7)
+                cuda_graph=bool(a.graph), backend=a.backend, seed=7, comm_type=a.comm_type)
     losses = []
     for s in range(1, a.steps + 1):
         x = y = None

@@ -100,3 +100,23 @@ def test_single_machine_cli(tmp_path):
     losses = [float(l.split("Loss: ")[1].split()[0]) for l in r.stdout.splitlines() if l.startswith("Train Epoch")]
     assert len(losses) >= 2 and losses[-1] < losses[0]
     assert "Test set: Average loss" in r.stdout
+
+
+def test_resume_from_checkpoint_sidecar(tmp_path):
+    """Train 6 steps (checkpoints + .opt sidecars at 3 and 6), then --resume to step 9: the PS restarts at step 7 with the
+    saved momentum, and the result equals an uninterrupted 9-step run (the reference has no resume at all)."""
+    env = dict(os.environ, PYTHONPATH=ROOT, OMP_NUM_THREADS="2")
+    base = [sys.executable, "-m", "ps_pytorch_b200.launch", "-n", "2", "--timeout", "200", os.path.join(ROOT, "src", "distributed_nn.py"),
+            "--network", "LeNet", "--dataset", "MNIST", "--batch-size", "32", "--lr", "0.05", "--momentum", "0.9", "--num-aggregate", "1",
+            "--eval-freq", "3", "--compress-grad", "None", "--seed", "3"]
+    da, db = str(tmp_path / "a") + "/", str(tmp_path / "b") + "/"
+    os.makedirs(da); os.makedirs(db)
+    r = subprocess.run(base + ["--max-steps", "9", "--train-dir", da], cwd=ROOT, env=env, capture_output=True, text=True, timeout=240)
+    assert r.returncode == 0, r.stderr[-2000:]
+    r = subprocess.run(base + ["--max-steps", "6", "--train-dir", db], cwd=ROOT, env=env, capture_output=True, text=True, timeout=240)
+    assert r.returncode == 0, r.stderr[-2000:]
+    r = subprocess.run(base + ["--max-steps", "9", "--train-dir", db, "--resume", "true"], cwd=ROOT, env=env, capture_output=True, text=True, timeout=240)
+    assert r.returncode == 0, r.stderr[-2000:]
+    assert "resumed from step 6" in r.stdout + r.stderr
+    assert "Master node is entering step: 7" in r.stdout + r.stderr and "entering step: 6\n" not in r.stdout + r.stderr
+    assert os.path.isfile(db + "model_step_9")

@@ -68,3 +68,63 @@ def test_nvl_resnet18_sm100_graph(tmp_path):
                                            "--backend", "sm100", "--overlap", "1"])
     assert res["workers"] == n and all(torch.isfinite(w).all() for w in res["w"])
     assert len(res["losses"]) == 2 and all(l == l for l in res["losses"])
+
+
+@pytest.mark.parametrize("topology,mode", [("ps", "push"), ("ps", "pull"), ("sharded", "push")])
+def test_flag_protocol_litmus(topology, mode):
+    """300 exact-arithmetic push/reduce/broadcast cycles: any stale read or missed flag is an exact mismatch."""
+    n = min(torch.cuda.device_count(), 4)
+    cmd = [sys.executable, "-m", "ps_pytorch_b200.launch", "-n", str(n), "--timeout", "200", os.path.join(ROOT, "tests", "mp_litmus.py"), topology, "300", mode]
+    r = subprocess.run(cmd, cwd=ROOT, env=dict(os.environ, PYTHONPATH=ROOT), capture_output=True, text=True, timeout=260)
+    assert r.returncode == 0 and "mismatches 0" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
+
+
+def test_nvl_async_pull_matches_reference(tmp_path):
+    """--comm-type Async: workers pull the weights from the PS replica instead of receiving a broadcast."""
+    n = min(torch.cuda.device_count(), 2)
+    res = _run(n, str(tmp_path / "w.pt"), ["--steps", "3", "--network", "LeNet", "--bs", "64", "--colocate", "1", "--backend", "library", "--comm-type", "Async"])
+    _check(res, _reference(n, 3, 64, "LeNet"), _init("LeNet"))
+
+
+DDP_SCRIPT = r'''
+import os, sys, torch, torch.distributed as dist
+sys.path.insert(0, %r)
+from ps_pytorch_b200.models import build_model
+from ps_pytorch_b200.parallel.ddp import DistributedDataParallel
+r, w = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+torch.cuda.set_device(int(os.environ["LOCAL_RANK"]))
+dist.init_process_group("gloo", rank=r, world_size=w)
+torch.manual_seed(100 + r)
+dev = torch.device("cuda", int(os.environ["LOCAL_RANK"]))
+ddp = DistributedDataParallel(build_model("ResNet18", 10).to(torch.bfloat16), dev)
+ok = True
+for it in range(3):
+    g = torch.Generator().manual_seed(5 + r + 10 * it)
+    x = torch.randn(16, 3, 32, 32, generator=g).to(dev).to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
+    y = torch.randint(0, 10, (16,), generator=g).to(dev)
+    ddp.zero_grad()
+    torch.nn.functional.cross_entropy(ddp(x).float(), y).backward()
+    local = ddp.grads.flat.float().clone()
+    ddp.sync_gradients()
+    torch.cuda.synchronize()
+    # reference: gloo all-reduce of the local gradients
+    ref = local.cpu(); dist.all_reduce(ref); ref /= w
+    got = ddp.grads.flat.float().cpu()
+    err = (got - ref).abs().max().item() / max(1e-6, ref.abs().max().item())
+    ok = ok and err < 2e-2
+    with torch.no_grad():
+        ddp.weights.flat.add_(ddp.grads.flat, alpha=-0.01)
+ddp._nvl.check_error()
+t = torch.tensor([0 if ok else 1]); dist.all_reduce(t)
+if r == 0: print("DDP_OK" if int(t[0]) == 0 else "DDP_BAD")
+dist.barrier()
+'''
+
+
+def test_ddp_allreduce_kernel(tmp_path):
+    n = min(torch.cuda.device_count(), 4)
+    script = tmp_path / "ddp_gpu.py"
+    script.write_text(DDP_SCRIPT % ROOT)
+    r = subprocess.run([sys.executable, "-m", "ps_pytorch_b200.launch", "-n", str(n), "--timeout", "200", str(script)],
+                       cwd=ROOT, env=dict(os.environ, PYTHONPATH=ROOT), capture_output=True, text=True, timeout=260)
+    assert r.returncode == 0 and "DDP_OK" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
