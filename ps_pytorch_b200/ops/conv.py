@@ -1,8 +1,9 @@
-"""Convolutions on the tcgen05 implicit-GEMM kernel (``csrc/gemm_tcgen05.cu``).
+"""Convolutions on the tcgen05 implicit-GEMM kernels (``csrc/gemm_tcgen05.cu``).
 
-Forward (fprop) and the data gradient of stride-1 convolutions run on the hand-written kernel; the weight gradient and the
-data gradient of strided convolutions currently go through cuDNN (``torch.ops.aten.convolution_backward``) — logged
-once per process by ``note_fallback``."""
+Forward (fprop: per-tap / halo / weight-stationary variants), the data gradient of stride-1 convolutions (the same kernels on
+flipped+transposed weights) and the weight gradient (MN-major operands, split-K with fp32 vector reductions) run on the
+hand-written kernels; only the data gradient of *strided* convolutions still goes through cuDNN
+(``torch.ops.aten.convolution_backward``), logged once per process by ``note_fallback``."""
 from __future__ import annotations
 
 import os
@@ -40,6 +41,18 @@ def unsupported_reason(x, weight, stride, padding, dilation, groups):
     return r or None
 
 
+_scratch = {}
+
+
+def _wgrad_scratch(weight):
+    """Persistent, self-cleaning fp32 accumulation buffer for the split-K weight gradient of this weight shape."""
+    key = (weight.device, tuple(weight.shape))
+    buf = _scratch.get(key)
+    if buf is None:
+        buf = _scratch[key] = torch.zeros(weight.numel(), dtype=torch.float32, device=weight.device)
+    return buf
+
+
 def _krsc(w):
     """[Cout,Cin,R,S] logical -> physically [Cout][R][S][Cin] (no copy for channels-last parameters)."""
     return w if w.is_contiguous(memory_format=torch.channels_last) else w.contiguous(memory_format=torch.channels_last)
@@ -74,8 +87,12 @@ class _ConvFn(torch.autograd.Function):
             dx = ext.conv_fprop(dy, wt, None, 1, r - 1 - p, False)
             count_launch()
             need_dx = False
+        if need_dw and weight.size(0) % 64 == 0 and weight.size(1) % 64 == 0:
+            dw = ext.conv_wgrad(dy, x, _wgrad_scratch(weight), r, weight.size(3), s, p)
+            count_launch(2)
+            need_dw = False
         if need_dx or need_dw:
-            note_fallback("conv2d.backward", "weight gradient / strided data gradient use cuDNN")
+            note_fallback("conv2d.backward", "strided data gradient uses cuDNN")
             gi, gw, _ = torch.ops.aten.convolution_backward(dy, x, weight, None, (s, s), (p, p), (1, 1), False, (0, 0), 1,
                                                             (need_dx, need_dw, False))
             if need_dx:

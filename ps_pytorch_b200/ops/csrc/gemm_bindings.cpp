@@ -11,6 +11,7 @@ void tc_set_halo_desc_mode(int);
 void tc_set_halo_cluster(int);
 void tc_set_halo_resident(int);
 int tc_check_error();
+const char* tc_conv_wgrad(const void*, const void*, void*, float*, int, int, int, int, int, int, int, int, int, cudaStream_t);
 
 static const void* opt_ptr(const c10::optional<at::Tensor>& t, int64_t n) {
     if (!t.has_value()) return nullptr;
@@ -52,6 +53,20 @@ at::Tensor conv_fprop(at::Tensor x, at::Tensor w, c10::optional<at::Tensor> bias
     return y;
 }
 
+// dW [Cout,Cin,R,S] channels_last (physically [Cout][R][S][Cin]) from dy (NHWC) and x (NHWC).  `scratch` is a persistent fp32 buffer of
+// Cout*R*S*Cin floats that must be zero on entry and is left zeroed.
+at::Tensor conv_wgrad(at::Tensor dy, at::Tensor x, at::Tensor scratch, int64_t R, int64_t S, int64_t stride, int64_t pad) {
+    TORCH_CHECK(dy.is_cuda() && dy.scalar_type() == at::kBFloat16 && x.scalar_type() == at::kBFloat16 && dy.dim() == 4 && x.dim() == 4);
+    TORCH_CHECK(dy.is_contiguous(at::MemoryFormat::ChannelsLast) && x.is_contiguous(at::MemoryFormat::ChannelsLast), "dy and x must be NHWC");
+    const int NB = x.size(0), Cin = x.size(1), H = x.size(2), W = x.size(3), Cout = dy.size(1);
+    TORCH_CHECK(scratch.scalar_type() == at::kFloat && scratch.is_contiguous() && scratch.numel() >= (int64_t)Cout * R * S * Cin);
+    at::Tensor dw = at::empty({Cout, Cin, R, S}, x.options().memory_format(at::MemoryFormat::ChannelsLast));
+    const char* e = tc_conv_wgrad(dy.data_ptr(), x.data_ptr(), dw.data_ptr(), scratch.data_ptr<float>(), NB, H, W, Cin, Cout, (int)R, (int)S, (int)stride, (int)pad,
+                                  at::cuda::getCurrentCUDAStream());
+    TORCH_CHECK(e == nullptr, "tc_conv_wgrad: ", e);
+    return dw;
+}
+
 std::string conv_unsupported_reason(std::vector<int64_t> xs, std::vector<int64_t> ws, std::vector<int64_t> stride, std::vector<int64_t> pad,
                                     std::vector<int64_t> dil, int64_t groups, bool bf16) {
     if (!bf16) return "needs bf16 operands";
@@ -75,5 +90,6 @@ void bind_gemm(pybind11::module_& m) {
     m.def("tc_set_halo_cluster", &psb::tc_set_halo_cluster);
     m.def("tc_set_halo_resident", &psb::tc_set_halo_resident);
     m.def("conv_unsupported_reason", &psb::conv_unsupported_reason);
+    m.def("conv_wgrad", &psb::conv_wgrad);
     m.def("tc_error", &psb::tc_error);
 }

@@ -402,6 +402,168 @@ tc_conv_halo_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     if (warp == 2) tmem_dealloc(tmem_base, Cfg::kTmemCols);
 }
 
+// ===================================================================================================================
+// Weight gradient:  dW[co][r][s][ci] = sum over output pixels p of dY[p, co] * X[p*stride + (r,s) - pad, ci]
+//
+// A GEMM whose reduction dimension is the PIXEL index, so both operands are "MN-major" for the tensor core (the channel
+// dimension — M = co for dY, N = ci for X — is the contiguous one in NHWC memory).  A K-block is a rectangle of 128 output
+// pixels; its dY tile and its tap-shifted X tile are the same kind of 4-D TMA box loads the forward kernel uses (padding and
+// stride-2 come from TMA zero-fill / element strides), landing in smem as [pixel][64 channels] 128-byte rows = the canonical
+// MN-major SWIZZLE_128B operand (8 pixel rows per 1024-byte atom = SBO, 64-channel groups one box apart = LBO).
+// Work item = (filter tap, co tile, ci tile, K split); every item accumulates 128 K-blocks worth of 128xN products in TMEM and
+// adds its partial tile into an fp32 [Cout][R*S][Cin] scratch with vector reductions (REDG.E.ADD.F32x4); a small kernel then
+// converts the scratch to the bf16 gradient and leaves it zeroed.
+struct WgParams {
+    int taps, S, stride, pad, Cin, Cout, NB, Ho, Wo;
+    int BW, BH, BNI, tiles_w, tiles_h, kb_total;
+    int co_tiles, ci_tiles, ksplit, kb_per_split, n_items;
+    float* dW32;
+    int* err;
+};
+constexpr int kWgKPix = 128;                       // pixels per K-block
+constexpr int kWgBoxBytes = kWgKPix * 128;         // one [128 pixels][64 channels] box = 16 KB
+
+template <int BN, int MM> struct WgCfg {
+    static constexpr int kGroupsA = MM / 64, kGroupsB = BN / 64;
+    static constexpr int kStageBytes = (kGroupsA + kGroupsB) * kWgBoxBytes;
+    static constexpr int kStages = (200 * 1024) / kStageBytes;
+    static constexpr int kTmemCols = 2 * BN < 32 ? 32 : 2 * BN;
+    static constexpr int kSmemBytes = kStages * kStageBytes + 1024 + 256;
+};
+
+template <int BN, int MM>
+__global__ void __launch_bounds__(kThreads, 1)
+tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmap_dy, const __grid_constant__ CUtensorMap tmap_x, const WgParams p) {
+    using Cfg = WgCfg<BN, MM>;
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + Cfg::kStages * Cfg::kStageBytes);
+    uint64_t* empty_bar = full_bar + Cfg::kStages;
+    uint64_t* tmem_full = empty_bar + Cfg::kStages;
+    uint64_t* tmem_empty = tmem_full + 2;
+    uint32_t* tmem_base_smem = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (warp == 0 && lane == 0) { prefetch_tmap(&tmap_dy); prefetch_tmap(&tmap_x); }
+    if (warp == 1 && lane == 0) {
+        for (int s = 0; s < Cfg::kStages; ++s) { mbar_init(full_bar + s, 1); mbar_init(empty_bar + s, 1); }
+        for (int s = 0; s < 2; ++s) { mbar_init(tmem_full + s, 1); mbar_init(tmem_empty + s, 4); }
+        fence_barrier_init();
+    }
+    if (warp == 2) tmem_alloc(tmem_base_smem, Cfg::kTmemCols);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_base_smem;
+
+    // item -> (tap fastest: CTAs of one wave read the same dY / X region, L2-friendly), then K split, ci tile, co tile
+    auto decode = [&](int item, int& tap, int& ks, int& nt, int& mt) {
+        tap = item % p.taps; int r = item / p.taps;
+        ks = r % p.ksplit; r /= p.ksplit;
+        nt = r % p.ci_tiles; mt = r / p.ci_tiles;
+    };
+
+    if (warp == 0) {
+        int stage = 0; uint32_t phase = 0;
+        for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
+            int tap, ks, nt, mt; decode(item, tap, ks, nt, mt);
+            const int fr = tap / p.S, fs = tap - fr * p.S;
+            const int kb0 = ks * p.kb_per_split, kb1 = min(kb0 + p.kb_per_split, p.kb_total);
+            for (int kb = kb0; kb < kb1; ++kb) {
+                const int tw = kb % p.tiles_w, th = (kb / p.tiles_w) % p.tiles_h, tn = kb / (p.tiles_w * p.tiles_h);
+                const int n0 = tn * p.BNI, h0 = th * p.BH, w0 = tw * p.BW;
+                if (!mbar_wait(empty_bar + stage, phase ^ 1)) { *p.err = 21; return; }
+                uint8_t* sa = smem + stage * Cfg::kStageBytes;
+                uint8_t* sb = sa + Cfg::kGroupsA * kWgBoxBytes;
+                if (elect_one()) {
+                    mbar_arrive_expect_tx(full_bar + stage, Cfg::kStageBytes);
+#pragma unroll
+                    for (int g = 0; g < Cfg::kGroupsA; ++g)
+                        tma_load_4d(sa + g * kWgBoxBytes, &tmap_dy, full_bar + stage, mt * MM + g * 64, w0, h0, n0);
+#pragma unroll
+                    for (int g = 0; g < Cfg::kGroupsB; ++g)
+                        tma_load_4d(sb + g * kWgBoxBytes, &tmap_x, full_bar + stage, nt * BN + g * 64, w0 * p.stride + fs - p.pad, h0 * p.stride + fr - p.pad, n0);
+                }
+                __syncwarp();
+                if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
+            }
+        }
+    } else if (warp == 1) {
+        constexpr uint32_t idesc = umma_idesc_bf16(MM, BN, 1, 1);          // both operands MN-major
+        int stage = 0; uint32_t phase = 0; int acc = 0; uint32_t acc_phase = 0;
+        for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
+            int tap, ks, nt, mt; decode(item, tap, ks, nt, mt);
+            const int kb0 = ks * p.kb_per_split, kb1 = min(kb0 + p.kb_per_split, p.kb_total);
+            if (!mbar_wait(tmem_empty + acc, acc_phase ^ 1)) { *p.err = 22; return; }
+            tc_fence_after();
+            const uint32_t tmem_d = tmem_base + acc * BN;
+            for (int kb = kb0; kb < kb1; ++kb) {
+                if (!mbar_wait(full_bar + stage, phase)) { *p.err = 23; return; }
+                tc_fence_after();
+                const uint32_t sa = smem_u32(smem + stage * Cfg::kStageBytes);
+                const uint32_t sb = sa + Cfg::kGroupsA * kWgBoxBytes;
+                if (elect_one()) {
+#pragma unroll
+                    for (int j = 0; j < kWgKPix / 16; ++j)       // 16 pixels per MMA = two 8-row atoms = 2048 bytes
+                        tc_mma_bf16(tmem_d, umma_desc_mn_sw128(sa + j * 2048, kWgBoxBytes), umma_desc_mn_sw128(sb + j * 2048, kWgBoxBytes), idesc,
+                                    (kb > kb0 || j > 0) ? 1u : 0u);
+                    tc_commit(empty_bar + stage);
+                }
+                __syncwarp();
+                if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
+            }
+            if (elect_one()) tc_commit(tmem_full + acc);
+            __syncwarp();
+            if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+        }
+    } else if (warp >= kEpiWarp0) {
+        const int q = warp & 3;
+        int acc = 0; uint32_t acc_phase = 0;
+        for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
+            int tap, ks, nt, mt; decode(item, tap, ks, nt, mt);
+            // TMEM rows: M=128 -> lane = row; M=64 -> "half sub-partition" layout: row m lives in lane (m%16) + 32*(m/16)
+            const int row = MM == 128 ? q * 32 + lane : q * 16 + lane;
+            const bool row_ok = (MM == 128 || lane < 16) && (mt * MM + row) < p.Cout;
+            const int kb0 = ks * p.kb_per_split;
+            const bool has_work = kb0 < p.kb_total;
+            if (!mbar_wait(tmem_full + acc, acc_phase)) { if (lane == 0) *p.err = 24; return; }
+            tc_fence_after();
+            float* drow = p.dW32 + ((long long)(mt * MM + row) * p.taps + tap) * p.Cin + (long long)nt * BN;
+#pragma unroll 1
+            for (int c0 = 0; c0 < BN; c0 += 32) {
+                uint32_t v[32];
+                tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + c0), v);
+                tmem_ld_wait();
+                if (row_ok && has_work) {
+#pragma unroll
+                    for (int j = 0; j < 32; j += 4)
+                        if (nt * BN + c0 + j < p.Cin)
+                            asm volatile("red.global.add.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(drow + c0 + j), "f"(__uint_as_float(v[j])), "f"(__uint_as_float(v[j + 1])),
+                                         "f"(__uint_as_float(v[j + 2])), "f"(__uint_as_float(v[j + 3])) : "memory");
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(tmem_empty + acc);
+            if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    if (warp == 2) tmem_dealloc(tmem_base, Cfg::kTmemCols);
+}
+
+// scratch fp32 -> bf16 gradient, scratch left zeroed (self-cleaning)
+__global__ void wgrad_finish_kernel(float* __restrict__ acc, __nv_bfloat16* __restrict__ out, long long n) {
+    for (long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 4; i < n; i += (long long)gridDim.x * blockDim.x * 4) {
+        float4 v = *reinterpret_cast<float4*>(acc + i);
+        *reinterpret_cast<float4*>(acc + i) = make_float4(0.f, 0.f, 0.f, 0.f);
+        __nv_bfloat162 a = __floats2bfloat162_rn(v.x, v.y), b = __floats2bfloat162_rn(v.z, v.w);
+        uint2 o; o.x = *reinterpret_cast<uint32_t*>(&a); o.y = *reinterpret_cast<uint32_t*>(&b);
+        *reinterpret_cast<uint2*>(out + i) = o;
+    }
+}
+
 // ------------------------------------------------------------------------------------------------------------------ host
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
@@ -569,6 +731,65 @@ const char* tc_conv_fprop(const void* X, const void* Wt, void* Y, const void* bi
     p.n_tiles_m = p.tiles_w * p.tiles_h * tiles_n_img; p.n_tiles_n = (Cout + BN - 1) / BN;
     p.bias = (const __nv_bfloat16*)bias; p.residual = (const __nv_bfloat16*)residual; p.relu = relu; p.C = (__nv_bfloat16*)Y; p.err = err_word();
     return BN == 64 ? launch<64>(ta, tb, p, stream) : launch<128>(ta, tb, p, stream);
+}
+
+template <int BN, int MM>
+static const char* launch_wgrad(const CUtensorMap& ta, const CUtensorMap& tb, const WgParams& p, cudaStream_t stream) {
+    using Cfg = WgCfg<BN, MM>;
+    static bool attr = false;
+    if (!attr) {
+        if (cudaFuncSetAttribute(tc_wgrad_kernel<BN, MM>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes) != cudaSuccess) return "cannot raise dynamic smem";
+        attr = true;
+    }
+    const int grid = p.n_items < num_sms() ? p.n_items : num_sms();
+    tc_wgrad_kernel<BN, MM><<<grid, kThreads, Cfg::kSmemBytes, stream>>>(ta, tb, p);
+    return cudaGetLastError() == cudaSuccess ? nullptr : "kernel launch failed";
+}
+
+// dW (bf16, [Cout][R][S][Cin]) from dY [NB,Ho,Wo,Cout] and X [NB,H,W,Cin]; scratch32 = zeroed fp32 buffer of Cout*R*S*Cin floats
+const char* tc_conv_wgrad(const void* dY, const void* X, void* dW, float* scratch32, int NB, int Hin, int Win, int Cin, int Cout, int R, int S,
+                          int stride, int pad, cudaStream_t stream) {
+    if (Cin % 64 || Cout % 64) return "Cin and Cout must be multiples of 64";
+    const int Ho = (Hin + 2 * pad - R) / stride + 1, Wo = (Win + 2 * pad - S) / stride + 1;
+    int BW = 1; while (BW * 2 <= Wo && BW * 2 <= 32) BW *= 2;
+    int BH = 1; while (BH * 2 <= Ho && BW * BH * 2 <= kWgKPix) BH *= 2;
+    const int BNI = kWgKPix / (BW * BH);
+    if ((BW - 1) * stride + 1 > 256 || (BH - 1) * stride + 1 > 256 || BNI > 256) return "pixel rectangle exceeds the TMA box limit";
+    CUtensorMap ta, tb;
+    uint64_t da[4] = {(uint64_t)Cout, (uint64_t)Wo, (uint64_t)Ho, (uint64_t)NB};
+    uint64_t sa[3] = {(uint64_t)Cout * 2, (uint64_t)Wo * Cout * 2, (uint64_t)Ho * Wo * Cout * 2};
+    uint32_t boxa[4] = {64, (uint32_t)BW, (uint32_t)BH, (uint32_t)BNI}, esa[4] = {1, 1, 1, 1};
+    uint64_t db[4] = {(uint64_t)Cin, (uint64_t)Win, (uint64_t)Hin, (uint64_t)NB};
+    uint64_t sb[3] = {(uint64_t)Cin * 2, (uint64_t)Win * Cin * 2, (uint64_t)Hin * Win * Cin * 2};
+    uint32_t boxb[4] = {64, (uint32_t)((BW - 1) * stride + 1), (uint32_t)((BH - 1) * stride + 1), (uint32_t)BNI};
+    uint32_t esb[4] = {1, (uint32_t)stride, (uint32_t)stride, 1};
+    if (const char* e = make_tmap(&ta, dY, 4, da, sa, boxa, esa)) return e;
+    if (const char* e = make_tmap(&tb, X, 4, db, sb, boxb, esb)) return e;
+    WgParams p{};
+    p.taps = R * S; p.S = S; p.stride = stride; p.pad = pad; p.Cin = Cin; p.Cout = Cout; p.NB = NB; p.Ho = Ho; p.Wo = Wo;
+    p.BW = BW; p.BH = BH; p.BNI = BNI;
+    p.tiles_w = (Wo + BW - 1) / BW; p.tiles_h = (Ho + BH - 1) / BH;
+    p.kb_total = p.tiles_w * p.tiles_h * ((NB + BNI - 1) / BNI);
+    const int MM = Cout % 128 == 0 ? 128 : 64;
+    const int BN = Cin % 128 == 0 ? 128 : 64;
+    p.co_tiles = Cout / MM; p.ci_tiles = Cin / BN;
+    const int base_items = p.taps * p.co_tiles * p.ci_tiles;
+    int ksplit = (2 * num_sms() + base_items - 1) / base_items;
+    if (ksplit < 1) ksplit = 1;
+    if (ksplit > p.kb_total) ksplit = p.kb_total;
+    p.kb_per_split = (p.kb_total + ksplit - 1) / ksplit;
+    p.ksplit = (p.kb_total + p.kb_per_split - 1) / p.kb_per_split;
+    p.n_items = base_items * p.ksplit;
+    p.dW32 = scratch32; p.err = err_word();
+    const char* e;
+    if (MM == 128 && BN == 128) e = launch_wgrad<128, 128>(ta, tb, p, stream);
+    else if (MM == 128) e = launch_wgrad<64, 128>(ta, tb, p, stream);
+    else if (BN == 128) e = launch_wgrad<128, 64>(ta, tb, p, stream);
+    else e = launch_wgrad<64, 64>(ta, tb, p, stream);
+    if (e) return e;
+    const long long n = (long long)Cout * R * S * Cin;
+    wgrad_finish_kernel<<<(int)((n / 4 + 255) / 256 < 1184 ? (n / 4 + 255) / 256 : 1184), 256, 0, stream>>>(scratch32, (__nv_bfloat16*)dW, n);
+    return cudaGetLastError() == cudaSuccess ? nullptr : "finish kernel launch failed";
 }
 
 }  // namespace psb

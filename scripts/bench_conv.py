@@ -56,6 +56,18 @@ for (Cin, H, W, Cout, R, st, pad) in SHAPES:
         except Exception as e:  # noqa: BLE001
             res[name + "_err"] = repr(e)[:200]
     ext.tc_set_conv_algo(-1)
+    # weight gradient: cuDNN vs ours
+    try:
+        dyt = (torch.randn_like(ref) * 0.1).contiguous(memory_format=torch.channels_last)
+        res["cudnn_wgrad_us"] = timeit(lambda: torch.ops.aten.convolution_backward(dyt, x, w, None, (st, st), (pad, pad), (1, 1), False, (0, 0), 1, (False, True, False)))
+        if Cin % 64 == 0 and Cout % 64 == 0:
+            scratch = torch.zeros(Cout * R * R * Cin, device="cuda")
+            g0 = torch.ops.aten.convolution_backward(dyt, x, w, None, (st, st), (pad, pad), (1, 1), False, (0, 0), 1, (False, True, False))[1]
+            g1 = ext.conv_wgrad(dyt, x, scratch, R, R, st, pad)
+            res["wgrad_maxerr"] = (g1.float() - g0.float()).abs().max().item()
+            res["wgrad_us"] = timeit(lambda: ext.conv_wgrad(dyt, x, scratch, R, R, st, pad))
+    except Exception as e:  # noqa: BLE001
+        res["wgrad_err"] = repr(e)[:200]
     for k in ("cudnn_us", "tap_us", "halo_us", "halo2_us"):
         if k in res:
             res[k.replace("_us", "_pflops")] = flops / res[k] / 1e9

@@ -376,3 +376,28 @@ def test_tc_conv_residual_epilogue(ext):
     y = ext.conv_fprop(x, w, b, 1, 1, True, r)
     ref = F.relu(F.conv2d(x.float(), w.float(), b.float(), 1, 1) + r.float())
     assert (y.float() - ref).abs().max().item() < 0.05
+
+
+@pytest.mark.parametrize("shape", [  # NB, Cin, H, W, Cout, R, stride, pad
+    (8, 128, 16, 16, 128, 3, 1, 1), (4, 64, 32, 32, 64, 3, 1, 1), (16, 256, 8, 8, 256, 3, 1, 1), (32, 512, 4, 4, 512, 3, 1, 1),
+    (8, 64, 32, 32, 128, 3, 2, 1), (8, 128, 16, 16, 256, 1, 2, 0), (4, 128, 16, 16, 64, 3, 1, 1), (3, 64, 14, 14, 64, 3, 1, 1)])
+def test_tc_conv_wgrad(ext, shape):
+    """tcgen05 weight gradient (MN-major operands, split-K + fp32 vector reductions) vs the fp32 autograd reference."""
+    NB, Cin, H, W, Cout, R, st, pad = shape
+    torch.manual_seed(0)
+    x = (torch.randn(NB, Cin, H, W, device="cuda") * 0.5).to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
+    Ho = (H + 2 * pad - R) // st + 1
+    dy = (torch.randn(NB, Cout, Ho, Ho, device="cuda") * 0.1).to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
+    scratch = torch.zeros(Cout * R * R * Cin, device="cuda")
+    dw = ext.conv_wgrad(dy, x, scratch, R, R, st, pad)
+    torch.cuda.synchronize()
+    assert ext.tc_error() == 0
+    assert scratch.abs().max().item() == 0, "scratch must be left zeroed"
+    w = torch.zeros(Cout, Cin, R, R, device="cuda", requires_grad=True)
+    F.conv2d(x.float(), w, None, st, pad).backward(dy.float())
+    ref = w.grad
+    err = (dw.float() - ref).abs().max().item()
+    assert dw.shape == ref.shape and err <= 0.02 * max(1.0, ref.abs().max().item()), (shape, err, ref.abs().max().item())
+    # second call on the same scratch (self-cleaning) gives the same answer
+    dw2 = ext.conv_wgrad(dy, x, scratch, R, R, st, pad)
+    assert (dw2.float() - dw.float()).abs().max().item() <= 0.02 * max(1.0, ref.abs().max().item())
