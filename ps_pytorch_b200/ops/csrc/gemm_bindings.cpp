@@ -10,6 +10,7 @@ void tc_set_conv_algo(int);
 void tc_set_halo_desc_mode(int);
 void tc_set_halo_cluster(int);
 void tc_set_halo_resident(int);
+void tc_set_gemm_bn(int);
 int tc_check_error();
 const char* tc_conv_wgrad(const void*, const void*, void*, float*, int, int, int, int, int, int, int, int, int, cudaStream_t);
 
@@ -89,6 +90,7 @@ void bind_gemm(pybind11::module_& m) {
     m.def("tc_set_halo_desc_mode", &psb::tc_set_halo_desc_mode);
     m.def("tc_set_halo_cluster", &psb::tc_set_halo_cluster);
     m.def("tc_set_halo_resident", &psb::tc_set_halo_resident);
+    m.def("tc_set_gemm_bn", &psb::tc_set_gemm_bn);
     m.def("conv_unsupported_reason", &psb::conv_unsupported_reason);
     m.def("conv_wgrad", &psb::conv_wgrad);
     m.def("tc_error", &psb::tc_error);

@@ -52,7 +52,7 @@ struct TcParams {
 };
 
 template <int BN> struct TcCfg {
-    static constexpr int kStages = BN == 64 ? 8 : 6;
+    static constexpr int kStages = BN == 64 ? 8 : (BN == 128 ? 6 : 4);
     static constexpr int kABytes = BM * BK * 2;
     static constexpr int kBBytes = BN * BK * 2;
     static constexpr int kStageBytes = kABytes + kBBytes;
@@ -420,21 +420,22 @@ struct WgParams {
     float* dW32;
     int* err;
 };
-constexpr int kWgKPix = 128;                       // pixels per K-block
-constexpr int kWgBoxBytes = kWgKPix * 128;         // one [128 pixels][64 channels] box = 16 KB
-
-template <int BN, int MM> struct WgCfg {
+// KP = pixels per K-block (128, or 64 for the 256-column configuration so that four stages still fit in shared memory);
+// one [KP pixels][64 channels] box = KP*128 bytes
+template <int BN, int MM, int KP> struct WgCfg {
+    static constexpr int kBoxBytes = KP * 128;
     static constexpr int kGroupsA = MM / 64, kGroupsB = BN / 64;
-    static constexpr int kStageBytes = (kGroupsA + kGroupsB) * kWgBoxBytes;
+    static constexpr int kStageBytes = (kGroupsA + kGroupsB) * kBoxBytes;
     static constexpr int kStages = (200 * 1024) / kStageBytes;
     static constexpr int kTmemCols = 2 * BN < 32 ? 32 : 2 * BN;
     static constexpr int kSmemBytes = kStages * kStageBytes + 1024 + 256;
 };
 
-template <int BN, int MM>
+template <int BN, int MM, int KP>
 __global__ void __launch_bounds__(kThreads, 1)
 tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmap_dy, const __grid_constant__ CUtensorMap tmap_x, const WgParams p) {
-    using Cfg = WgCfg<BN, MM>;
+    using Cfg = WgCfg<BN, MM, KP>;
+    constexpr int kWgBoxBytes = Cfg::kBoxBytes;
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + Cfg::kStages * Cfg::kStageBytes);
@@ -503,7 +504,7 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmap_dy, const __grid_consta
                 const uint32_t sb = sa + Cfg::kGroupsA * kWgBoxBytes;
                 if (elect_one()) {
 #pragma unroll
-                    for (int j = 0; j < kWgKPix / 16; ++j)       // 16 pixels per MMA = two 8-row atoms = 2048 bytes
+                    for (int j = 0; j < KP / 16; ++j)            // 16 pixels per MMA = two 8-row atoms = 2048 bytes
                         tc_mma_bf16(tmem_d, umma_desc_mn_sw128(sa + j * 2048, kWgBoxBytes), umma_desc_mn_sw128(sb + j * 2048, kWgBoxBytes), idesc,
                                     (kb > kb0 || j > 0) ? 1u : 0u);
                     tc_commit(empty_bar + stage);
@@ -655,10 +656,15 @@ static int g_conv_algo = -1;     // -1 auto (= per-tap until the halo variant is
 void tc_set_halo_desc_mode(int) {}   // kept for scripts/conv_one.py; the base_offset experiment is settled (always 0)
 void tc_set_conv_algo(int a) { g_conv_algo = a; }
 
+static int g_gemm_bn = -1;       // -1 auto, 128 / 256 force the N tile of the plain GEMM
+void tc_set_gemm_bn(int b) { g_gemm_bn = b; }
+
 // C[M,N] = A[M,K] B[N,K]^T ; lda/ldb = K (dense rows)
 const char* tc_gemm_tn(const void* A, const void* B, void* C, const void* bias, int M, int N, int K, int relu, cudaStream_t stream) {
     if (K % 8) return "K must be a multiple of 8";
-    const int BN = N <= 64 ? 64 : 128;
+    int BN = N <= 64 ? 64 : 128;
+    if (g_gemm_bn == 256 && N >= 256) BN = 256;
+    else if (g_gemm_bn == -1 && N >= 512 && ((M + BM - 1) / BM) * ((N + 255) / 256) >= num_sms()) BN = 256;   // enough tiles to fill the chip
     CUtensorMap ta, tb;
     uint64_t da[2] = {(uint64_t)K, (uint64_t)M}, sa[1] = {(uint64_t)K * 2};
     uint64_t db[2] = {(uint64_t)K, (uint64_t)N}, sb[1] = {(uint64_t)K * 2};
@@ -669,7 +675,7 @@ const char* tc_gemm_tn(const void* A, const void* B, void* C, const void* bias, 
     p.M = M; p.N = N; p.num_kb = (K + BK - 1) / BK; p.mode = 0;
     p.n_tiles_m = (M + BM - 1) / BM; p.n_tiles_n = (N + BN - 1) / BN;
     p.bias = (const __nv_bfloat16*)bias; p.relu = relu; p.C = (__nv_bfloat16*)C; p.err = err_word();
-    return BN == 64 ? launch<64>(ta, tb, p, stream) : launch<128>(ta, tb, p, stream);
+    return BN == 64 ? launch<64>(ta, tb, p, stream) : (BN == 128 ? launch<128>(ta, tb, p, stream) : launch<256>(ta, tb, p, stream));
 }
 
 // Y[NB,Hout,Wout,Cout] = conv(X[NB,Hin,Win,Cin], Wt[Cout][R][S][Cin]), NHWC bf16
@@ -710,7 +716,8 @@ const char* tc_conv_fprop(const void* X, const void* Wt, void* Y, const void* bi
     int BH = 1; while (BH * 2 <= Hout && BW * BH * 2 <= 128) BH *= 2;
     int BNI = 128 / (BW * BH);
     if (BW * stride > 256 || BH * stride > 256 || BNI > 256) return "tile rectangle exceeds the TMA box limit";
-    const int BN = Cout <= 64 ? 64 : 128;
+    // 256 accumulator columns per MMA when the layer is wide enough (+30 % tensor throughput, profiles/run20_gemm.md)
+    const int BN = Cout <= 64 ? 64 : ((Cout % 256 == 0 && g_gemm_bn != 128) ? 256 : 128);
     CUtensorMap ta, tb;
     uint64_t da[4] = {(uint64_t)Cin, (uint64_t)Win, (uint64_t)Hin, (uint64_t)NB};
     uint64_t sa[3] = {(uint64_t)Cin * 2, (uint64_t)Win * Cin * 2, (uint64_t)Hin * Win * Cin * 2};
@@ -730,19 +737,19 @@ const char* tc_conv_fprop(const void* X, const void* Wt, void* Y, const void* bi
     const int tiles_n_img = (NB + BNI - 1) / BNI;
     p.n_tiles_m = p.tiles_w * p.tiles_h * tiles_n_img; p.n_tiles_n = (Cout + BN - 1) / BN;
     p.bias = (const __nv_bfloat16*)bias; p.residual = (const __nv_bfloat16*)residual; p.relu = relu; p.C = (__nv_bfloat16*)Y; p.err = err_word();
-    return BN == 64 ? launch<64>(ta, tb, p, stream) : launch<128>(ta, tb, p, stream);
+    return BN == 64 ? launch<64>(ta, tb, p, stream) : (BN == 128 ? launch<128>(ta, tb, p, stream) : launch<256>(ta, tb, p, stream));
 }
 
-template <int BN, int MM>
+template <int BN, int MM, int KP>
 static const char* launch_wgrad(const CUtensorMap& ta, const CUtensorMap& tb, const WgParams& p, cudaStream_t stream) {
-    using Cfg = WgCfg<BN, MM>;
+    using Cfg = WgCfg<BN, MM, KP>;
     static bool attr = false;
     if (!attr) {
-        if (cudaFuncSetAttribute(tc_wgrad_kernel<BN, MM>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes) != cudaSuccess) return "cannot raise dynamic smem";
+        if (cudaFuncSetAttribute(tc_wgrad_kernel<BN, MM, KP>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes) != cudaSuccess) return "cannot raise dynamic smem";
         attr = true;
     }
     const int grid = p.n_items < num_sms() ? p.n_items : num_sms();
-    tc_wgrad_kernel<BN, MM><<<grid, kThreads, Cfg::kSmemBytes, stream>>>(ta, tb, p);
+    tc_wgrad_kernel<BN, MM, KP><<<grid, kThreads, Cfg::kSmemBytes, stream>>>(ta, tb, p);
     return cudaGetLastError() == cudaSuccess ? nullptr : "kernel launch failed";
 }
 
@@ -751,6 +758,9 @@ const char* tc_conv_wgrad(const void* dY, const void* X, void* dW, float* scratc
                           int stride, int pad, cudaStream_t stream) {
     if (Cin % 64 || Cout % 64) return "Cin and Cout must be multiples of 64";
     const int Ho = (Hin + 2 * pad - R) / stride + 1, Wo = (Win + 2 * pad - S) / stride + 1;
+    const int MM = Cout % 128 == 0 ? 128 : 64;
+    const int BN = (Cin % 256 == 0 && MM == 128) ? 256 : (Cin % 128 == 0 ? 128 : 64);     // 256-column MMAs for wide layers
+    const int kWgKPix = BN == 256 ? 64 : 128;
     int BW = 1; while (BW * 2 <= Wo && BW * 2 <= 32) BW *= 2;
     int BH = 1; while (BH * 2 <= Ho && BW * BH * 2 <= kWgKPix) BH *= 2;
     const int BNI = kWgKPix / (BW * BH);
@@ -770,8 +780,6 @@ const char* tc_conv_wgrad(const void* dY, const void* X, void* dW, float* scratc
     p.BW = BW; p.BH = BH; p.BNI = BNI;
     p.tiles_w = (Wo + BW - 1) / BW; p.tiles_h = (Ho + BH - 1) / BH;
     p.kb_total = p.tiles_w * p.tiles_h * ((NB + BNI - 1) / BNI);
-    const int MM = Cout % 128 == 0 ? 128 : 64;
-    const int BN = Cin % 128 == 0 ? 128 : 64;
     p.co_tiles = Cout / MM; p.ci_tiles = Cin / BN;
     const int base_items = p.taps * p.co_tiles * p.ci_tiles;
     int ksplit = (2 * num_sms() + base_items - 1) / base_items;
@@ -782,10 +790,11 @@ const char* tc_conv_wgrad(const void* dY, const void* X, void* dW, float* scratc
     p.n_items = base_items * p.ksplit;
     p.dW32 = scratch32; p.err = err_word();
     const char* e;
-    if (MM == 128 && BN == 128) e = launch_wgrad<128, 128>(ta, tb, p, stream);
-    else if (MM == 128) e = launch_wgrad<64, 128>(ta, tb, p, stream);
-    else if (BN == 128) e = launch_wgrad<128, 64>(ta, tb, p, stream);
-    else e = launch_wgrad<64, 64>(ta, tb, p, stream);
+    if (BN == 256) e = launch_wgrad<256, 128, 64>(ta, tb, p, stream);
+    else if (MM == 128 && BN == 128) e = launch_wgrad<128, 128, 128>(ta, tb, p, stream);
+    else if (MM == 128) e = launch_wgrad<64, 128, 128>(ta, tb, p, stream);
+    else if (BN == 128) e = launch_wgrad<128, 64, 128>(ta, tb, p, stream);
+    else e = launch_wgrad<64, 64, 128>(ta, tb, p, stream);
     if (e) return e;
     const long long n = (long long)Cout * R * S * Cin;
     wgrad_finish_kernel<<<(int)((n / 4 + 255) / 256 < 1184 ? (n / 4 + 255) / 256 : 1184), 256, 0, stream>>>(scratch32, (__nv_bfloat16*)dW, n);
