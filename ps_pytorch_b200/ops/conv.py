@@ -16,12 +16,14 @@ from ..nn.backend import note_fallback
 # Measured on B200 (profiles/run4_conv_microbench.md) the per-tap tcgen05 kernel reaches 0.38-0.76 PFLOP/s where cuDNN's
 # sm100 kernels reach 0.75-1.34, so the *default* convolution path is the library one and the hand-written kernel is opt-in
 # (PSB200_TC_CONV=1 / set_tc_conv(True)) until it wins; every other layer of the sm100 backend is ours regardless.
-_ENABLED = os.environ.get("PSB200_TC_CONV", "0") != "0"
+_MODE = os.environ.get("PSB200_TC_CONV", "0").lower()       # "0" library, "1" every supported conv, "auto" only where ours wins
+_ENABLED = _MODE != "0"
 
 
-def set_tc_conv(on: bool) -> None:
-    global _ENABLED
-    _ENABLED = bool(on)
+def set_tc_conv(on) -> None:
+    global _ENABLED, _MODE
+    _MODE = on if isinstance(on, str) else ("1" if on else "0")
+    _ENABLED = _MODE != "0"
 
 
 def tc_conv_enabled() -> bool:
@@ -36,6 +38,11 @@ def unsupported_reason(x, weight, stride, padding, dilation, groups):
         return "tcgen05 implicit-GEMM conv not built"
     if isinstance(padding, str):
         return "string padding"
+    if _MODE == "auto":
+        # measured policy (profiles/run20_gemm.md): 1x1 stride-1 convolutions with >= 256 output channels are plain GEMMs on which the
+        # 256-column tcgen05 kernel matches or beats the library
+        if not (weight.size(2) == 1 and weight.size(3) == 1 and stride[0] == 1 and weight.size(0) % 256 == 0):
+            return "auto policy keeps this shape on cuDNN"
     r = ext.conv_unsupported_reason(list(x.shape), list(weight.shape), list(stride), list(padding), list(dilation), groups,
                                     x.dtype == torch.bfloat16 and weight.dtype == torch.bfloat16)
     return r or None

@@ -28,8 +28,8 @@ def _native():
 
 def compress(t: torch.Tensor) -> torch.Tensor:
     """Lossless: tensor → uint8 blob (header: magic, codec id, itemsize, raw bytes)."""
-    raw = t.detach().contiguous().view(torch.uint8).reshape(-1)
     isz = t.element_size()
+    raw = t.detach().contiguous().reshape(-1).view(torch.uint8) if t.numel() else torch.empty(0, dtype=torch.uint8)
     nat = _native()
     if nat is not None:
         body = nat.shuffle_lz_compress(raw, isz)
@@ -45,8 +45,10 @@ def compress(t: torch.Tensor) -> torch.Tensor:
 def decompress_into(blob: torch.Tensor, out: torch.Tensor) -> torch.Tensor:
     magic, cid, isz, nraw = struct.unpack("<IIQQ", bytes(blob[:24].numpy().tobytes()))
     assert magic == _MAGIC, "corrupt payload"
-    dst = out.view(torch.uint8).reshape(-1)
+    dst = out.reshape(-1).view(torch.uint8) if out.numel() else torch.empty(0, dtype=torch.uint8)
     assert dst.numel() == nraw, (dst.numel(), nraw)
+    if nraw == 0:
+        return out
     body = blob[24:]
     if cid == 1:
         nat = _native()
