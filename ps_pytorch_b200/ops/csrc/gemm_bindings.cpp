@@ -12,6 +12,7 @@ void tc_set_halo_cluster(int);
 void tc_set_halo_resident(int);
 void tc_set_gemm_bn(int);
 int tc_check_error();
+const char* stem_wgrad_launch(const void*, const void*, void*, float*, int, int, int, int, int, cudaStream_t);
 const char* tc_conv_wgrad(const void*, const void*, void*, float*, int, int, int, int, int, int, int, int, int, cudaStream_t);
 
 static const void* opt_ptr(const c10::optional<at::Tensor>& t, int64_t n) {
@@ -68,6 +69,18 @@ at::Tensor conv_wgrad(at::Tensor dy, at::Tensor x, at::Tensor scratch, int64_t R
     return dw;
 }
 
+// weight gradient of a 3x3/s1/p1 convolution with Cin <= 3 (network stem); dy, x NHWC bf16; scratch: zeroed fp32 [Cout*9*Cin], left zeroed
+at::Tensor stem_wgrad(at::Tensor dy, at::Tensor x, at::Tensor scratch) {
+    TORCH_CHECK(dy.is_cuda() && dy.scalar_type() == at::kBFloat16 && x.scalar_type() == at::kBFloat16 && dy.dim() == 4 && x.dim() == 4);
+    TORCH_CHECK(dy.is_contiguous(at::MemoryFormat::ChannelsLast) && x.is_contiguous(at::MemoryFormat::ChannelsLast), "dy and x must be NHWC");
+    const int N = x.size(0), Cin = x.size(1), H = x.size(2), W = x.size(3), Cout = dy.size(1);
+    TORCH_CHECK(dy.size(2) == H && dy.size(3) == W && scratch.scalar_type() == at::kFloat && scratch.numel() >= (int64_t)Cout * 9 * Cin);
+    at::Tensor dw = at::empty({Cout, Cin, 3, 3}, x.options().memory_format(at::MemoryFormat::ChannelsLast));
+    const char* e = stem_wgrad_launch(dy.data_ptr(), x.data_ptr(), dw.data_ptr(), scratch.data_ptr<float>(), N, H, W, Cin, Cout, at::cuda::getCurrentCUDAStream());
+    TORCH_CHECK(e == nullptr, e);
+    return dw;
+}
+
 std::string conv_unsupported_reason(std::vector<int64_t> xs, std::vector<int64_t> ws, std::vector<int64_t> stride, std::vector<int64_t> pad,
                                     std::vector<int64_t> dil, int64_t groups, bool bf16) {
     if (!bf16) return "needs bf16 operands";
@@ -93,5 +106,6 @@ void bind_gemm(pybind11::module_& m) {
     m.def("tc_set_gemm_bn", &psb::tc_set_gemm_bn);
     m.def("conv_unsupported_reason", &psb::conv_unsupported_reason);
     m.def("conv_wgrad", &psb::conv_wgrad);
+    m.def("stem_wgrad", &psb::stem_wgrad);
     m.def("tc_error", &psb::tc_error);
 }

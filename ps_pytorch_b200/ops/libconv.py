@@ -13,6 +13,15 @@ import torch
 import torch.nn.functional as F
 
 _ENABLED = os.environ.get("PSB200_WGRAD_STREAM", "1") != "0"
+# dedicated stem kernel: correct but 199 us vs cuDNN 189 us at batch 1024 (scripts/bench_stem.py), and hidden on the side stream: opt-in
+_STEM = os.environ.get("PSB200_STEM_WGRAD", "0") != "0"
+_stem_scratch = {}
+
+
+def _stem_ok(x, weight, stride, padding, dilation, groups, dy):
+    return (_STEM and weight.size(1) <= 3 and tuple(weight.shape[2:]) == (3, 3) and tuple(stride) == (1, 1) and tuple(padding) == (1, 1)
+            and tuple(dilation) == (1, 1) and groups == 1 and weight.size(0) % 64 == 0 and x.size(2) % 8 == 0 and x.size(3) <= 32
+            and x.dtype == torch.bfloat16 and dy.dtype == torch.bfloat16 and x.is_contiguous(memory_format=torch.channels_last))
 _streams = {}
 _forked = {}
 
@@ -54,8 +63,18 @@ class _LibConvFn(torch.autograd.Function):
             side = _side(dev)
             side.wait_stream(main)                      # dy is complete on the main stream at this point
             with torch.cuda.stream(side):
-                _, dw, db = torch.ops.aten.convolution_backward(dy, x, weight, [weight.size(0)] if need_db else None, stride, padding, dilation,
-                                                                False, [0, 0], groups, [False, need_dw, need_db])
+                if need_dw and not need_db and _stem_ok(x, weight, stride, padding, dilation, groups, dy):
+                    # network stem (RGB -> 64): dedicated register-blocked kernel instead of cuDNN's generic implicit GEMM
+                    from . import count_launch, require
+                    key = (dev, tuple(weight.shape))
+                    sc = _stem_scratch.get(key)
+                    if sc is None:
+                        sc = _stem_scratch[key] = torch.zeros(weight.numel(), dtype=torch.float32, device=dev)
+                    dw = require().stem_wgrad(dy.contiguous(memory_format=torch.channels_last), x, sc)
+                    count_launch(2)
+                else:
+                    _, dw, db = torch.ops.aten.convolution_backward(dy, x, weight, [weight.size(0)] if need_db else None, stride, padding, dilation,
+                                                                    False, [0, 0], groups, [False, need_dw, need_db])
             _forked[dev] = True
             for t in (dy, x, weight):
                 t.record_stream(side)

@@ -401,3 +401,17 @@ def test_tc_conv_wgrad(ext, shape):
     # second call on the same scratch (self-cleaning) gives the same answer
     dw2 = ext.conv_wgrad(dy, x, scratch, R, R, st, pad)
     assert (dw2.float() - dw.float()).abs().max().item() <= 0.02 * max(1.0, ref.abs().max().item())
+
+
+@pytest.mark.parametrize("shape", [(8, 3, 32, 32, 64), (4, 3, 16, 16, 128), (5, 1, 8, 24, 64)])
+def test_stem_wgrad(ext, shape):
+    NB, Cin, H, W, Cout = shape
+    torch.manual_seed(0)
+    x = torch.randn(NB, Cin, H, W, device="cuda").to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
+    dy = (torch.randn(NB, Cout, H, W, device="cuda") * 0.1).to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
+    sc = torch.zeros(Cout * 9 * Cin, device="cuda")
+    dw = ext.stem_wgrad(dy, x, sc)
+    w = torch.zeros(Cout, Cin, 3, 3, device="cuda", requires_grad=True)
+    F.conv2d(x.float(), w, None, 1, 1).backward(dy.float())
+    assert sc.abs().max().item() == 0
+    assert (dw.float() - w.grad).abs().max().item() <= 0.02 * max(1.0, w.grad.abs().max().item())
