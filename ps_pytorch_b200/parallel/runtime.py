@@ -74,8 +74,67 @@ def make_transport(args, layout: ParamLayout, device: torch.device, world: int):
     raise ValueError(kind)
 
 
+def run_ddp(args):
+    """``--parallelism ddp``: every rank holds a replica, gradients are averaged by the all-reduce kernel (``ddp.py``) and every rank
+    applies the same fused flat optimizer step to its own fp32 master — the capability of the reference's vendored
+    ``DistributedDataParallel`` (``/root/reference/src/data_parallel_dist/data_parallel_dist.py:29-267``) as a runnable mode."""
+    import time
+
+    from .. import nn as pnn
+    from ..optim import build_optimizer
+    from ..utils import checkpoint as ckpt
+    from ..utils.obs import format_worker_line
+    from .arena import FlatBuffer
+    from .ddp import DistributedDataParallel
+
+    use_cuda = bool(args.enable_gpu) and not args.no_cuda and torch.cuda.is_available()
+    rank, local_rank, world = init_process_group(use_cuda)
+    device = torch.device("cuda", local_rank) if use_cuda else torch.device("cpu")
+    seed_everything(args.seed, rank)
+    if args.backend != "auto":
+        pnn.set_backend(args.backend)
+    num_classes = num_classes_for(args.dataset)
+    dtype = resolve_dtype(args.dtype, device)
+    model = build_model(args.network, num_classes).to(device=device, dtype=dtype)
+    ddp = DistributedDataParallel(model, device)
+    master = ddp.weights if dtype == torch.float32 else FlatBuffer(ddp.layout, torch.float32, device)
+    if master is not ddp.weights:
+        master.flat.copy_(ddp.weights.flat)
+    opt = build_optimizer(args.optimizer, model.parameters(), args.lr, args.momentum, weight_decay=args.weight_decay,
+                          nesterov=args.nesterov, dampening=args.dampening, amsgrad=args.amsgrad)
+    opt.attach_flat(master)
+    criterion = pnn.CrossEntropyLoss()
+    train_loader, _ = prepare_data(args, rank=rank, pin=use_cuda, out_dtype=torch.float32, channels_last=use_cuda)
+    step, losses = 1, []
+    model.train()
+    while step <= args.max_steps:
+        t0 = time.time()
+        x, y = train_loader.next_batch()
+        x = x.to(device=device, dtype=dtype, non_blocking=True)
+        y = y.to(device, non_blocking=True)
+        ddp.zero_grad()
+        loss = criterion(ddp(x), y)
+        loss.backward()
+        ddp.sync_gradients()
+        opt.step(ddp.grads.flat, out_lowp=None if master is ddp.weights else ddp.weights.flat)
+        lv = float(loss)
+        losses.append(lv)
+        if step % max(1, args.log_interval) == 0:
+            seen = (step * args.batch_size) % len(train_loader.dataset)
+            logger.info(format_worker_line(rank, step, step * args.batch_size // max(1, len(train_loader.dataset)), seen, len(train_loader.dataset),
+                                           lv, time.time() - t0, 0.0, 0.0, 0.0, 0.0))
+        if rank == 0 and args.eval_freq > 0 and step % args.eval_freq == 0:
+            ckpt.save_model(model, args.train_dir, step, master=master, optimizer=opt)
+        step += 1
+    if dist.is_initialized():
+        dist.barrier()
+    return {"ddp": ddp, "losses": losses, "master": master}
+
+
 def run_distributed(args):
     """Body of ``distributed_nn.py``: build data, roles and transport from flags, then run."""
+    if getattr(args, "parallelism", "ps") == "ddp":
+        return run_ddp(args)
     use_cuda = bool(args.enable_gpu) and not args.no_cuda and torch.cuda.is_available()
     rank, local_rank, world = init_process_group(use_cuda)
     device = torch.device("cuda", local_rank) if use_cuda else torch.device("cpu")
