@@ -107,3 +107,13 @@ def test_master_reference_api_aggregate_and_update():
         assert torch.allclose(p, b - 0.1, atol=1e-6)
     ps.meset_grad_buffer()
     assert float(ps._grad_aggregate_buffer.flat.abs().sum()) == 0.0
+
+
+def test_compression_facade_names():
+    import subprocess, sys, os
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    code = ("import numpy as np, compression as c; a=np.arange(12,dtype=np.float32).reshape(3,4); "
+            "assert (c.g_decompress(c.g_compress(a))==a).all() and (c.w_decompress(c.w_compress(a))==a).all(); "
+            "assert c._trim_msg(b'abc'+bytes([0x29])*32+b'junk')==b'abc' and c._trim_msg(b'abc')==b'abc'; print('ok')")
+    r = subprocess.run([sys.executable, "-c", code], cwd=os.path.join(root, "src"), capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0 and "ok" in r.stdout, r.stderr[-1500:]
