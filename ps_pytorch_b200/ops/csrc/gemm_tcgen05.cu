@@ -244,6 +244,125 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
 }
 
 // ===================================================================================================================
+// CTA-pair GEMM: one 256 x 256 output tile per pair of SMs (cluster of 2), tcgen05.mma.cta_group::2.
+//
+// Why: an SS-mode MMA is paced by its shared-memory operand reads, ~ (A bytes + B bytes) / 64 cycles per instruction
+// (DESIGN.md section 5).  With one CTA, 128 x 256 x 16 reads 4 KB of A + 8 KB of B = 192 cycles for 128 cycles of math.  In a
+// pair each SM reads its own 128 rows of A and only HALF of B (128 of the 256 columns; the tensor cores exchange operands
+// across the pair), 8 KB = 128 cycles: the math rate.
+//   rank r of the pair loads A rows [256 mt + 128 r, +128) and B rows [256 nt + 128 r, +128); every TMA signals the
+//   LEADER's full barrier (cta_group::2 form, barrier address mapped to rank 0); only the leader issues MMAs; tcgen05.commit
+//   multicasts the "stage free" / "accumulator ready" arrivals to both CTAs; each CTA's epilogue drains its own 128 TMEM
+//   lanes and arrives on the leader's tmem_empty barrier (8 arrivals: 4 warps x 2 CTAs).
+struct Tc2Cfg {
+    static constexpr int kStages = 6;
+    static constexpr int kABytes = BM * BK * 2;                 // 128 rows of A
+    static constexpr int kBBytes = 128 * BK * 2;                // 128 of the tile's 256 B rows
+    static constexpr int kStageBytes = kABytes + kBBytes;
+    static constexpr int kTmemCols = 512;                       // two 256-column accumulator stages
+    static constexpr int kSmemBytes = kStages * kStageBytes + 1024 + 256;
+};
+
+__global__ void __launch_bounds__(kThreads, 1)
+tc_gemm2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, const TcParams p) {
+    using Cfg = Tc2Cfg;
+    constexpr int BN2 = 256;
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + Cfg::kStages * Cfg::kStageBytes);
+    uint64_t* empty_bar = full_bar + Cfg::kStages;
+    uint64_t* tmem_full = empty_bar + Cfg::kStages;
+    uint64_t* tmem_empty = tmem_full + 2;
+    uint32_t* tmem_base_smem = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t rank = cluster_ctarank();
+    const bool leader = rank == 0;
+    if (warp == 0 && lane == 0) { prefetch_tmap(&tmap_a); prefetch_tmap(&tmap_b); }
+    if (warp == 1 && lane == 0) {
+        for (int s = 0; s < Cfg::kStages; ++s) { mbar_init(full_bar + s, 1); mbar_init(empty_bar + s, 1); }
+        for (int s = 0; s < 2; ++s) { mbar_init(tmem_full + s, 1); mbar_init(tmem_empty + s, 8); }
+        fence_barrier_init();
+    }
+    if (warp == 2) tmem_alloc2(tmem_base_smem, Cfg::kTmemCols);
+    tc_fence_before();
+    cluster_sync_all();                         // peer barriers initialised before any remote arrive / TMA signal / commit
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_base_smem;
+    const int n_tiles = p.n_tiles_m * p.n_tiles_n;
+    const int pair = blockIdx.x >> 1, n_pairs = gridDim.x >> 1;
+
+    if (warp == 0) {
+        // ===================================================== TMA producer (both CTAs)
+        int stage = 0; uint32_t phase = 0;
+        for (int tile = pair; tile < n_tiles; tile += n_pairs) {
+            const int mt = tile / p.n_tiles_n, nt = tile % p.n_tiles_n;
+            for (int kb = 0; kb < p.num_kb; ++kb) {
+                if (!mbar_wait(empty_bar + stage, phase ^ 1)) { *p.err = 1; break; }
+                uint8_t* sa = smem + stage * Cfg::kStageBytes;
+                uint8_t* sb = sa + Cfg::kABytes;
+                if (elect_one()) {
+                    const uint32_t lead_full = mapa_u32(smem_u32(full_bar + stage), 0);
+                    if (leader) mbar_arrive_expect_tx(full_bar + stage, 2 * Cfg::kStageBytes);      // both CTAs' bytes land on this barrier
+                    tma_load_2d_2sm(sa, &tmap_a, lead_full, kb * BK, mt * 256 + (int)rank * 128);
+                    tma_load_2d_2sm(sb, &tmap_b, lead_full, kb * BK, nt * BN2 + (int)rank * 128);
+                }
+                __syncwarp();
+                if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
+            }
+        }
+    } else if (warp == 1 && leader) {
+        // ===================================================== MMA issuer (leader CTA only)
+        constexpr uint32_t idesc = umma_idesc_bf16(256, BN2, 0, 0);
+        int stage = 0; uint32_t phase = 0; int acc = 0; uint32_t acc_phase = 0;
+        bool ok = true;
+        for (int tile = pair; tile < n_tiles && ok; tile += n_pairs) {
+            if (!mbar_wait(tmem_empty + acc, acc_phase ^ 1)) { *p.err = 2; break; }
+            tc_fence_after();
+            const uint32_t tmem_d = tmem_base + acc * BN2;
+            for (int kb = 0; kb < p.num_kb; ++kb) {
+                if (!mbar_wait(full_bar + stage, phase)) { *p.err = 3; ok = false; break; }
+                tc_fence_after();
+                const uint32_t sa = smem_u32(smem + stage * Cfg::kStageBytes);
+                const uint32_t sb = sa + Cfg::kABytes;
+                if (elect_one()) {
+#pragma unroll
+                    for (int k = 0; k < BK / 16; ++k)
+                        tc_mma2_bf16(tmem_d, umma_desc_k_sw128(sa + k * 32), umma_desc_k_sw128(sb + k * 32), idesc, (kb | k) != 0);
+                    tc_commit2_mcast(empty_bar + stage, 0b11);       // the stage is free in BOTH CTAs once these MMAs retire
+                }
+                __syncwarp();
+                if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
+            }
+            if (ok && elect_one()) tc_commit2_mcast(tmem_full + acc, 0b11);
+            __syncwarp();
+            if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+        }
+    } else if (warp >= kEpiWarp0) {
+        // ===================================================== epilogue (both CTAs; each drains its own 128 TMEM lanes)
+        const int q = warp & 3;
+        int acc = 0; uint32_t acc_phase = 0;
+        for (int tile = pair; tile < n_tiles; tile += n_pairs) {
+            const int mt = tile / p.n_tiles_n, nt = tile % p.n_tiles_n;
+            const int m = mt * 256 + (int)rank * 128 + q * 32 + lane;
+            const long long out_row = m < p.M ? m : -1;
+            if (!mbar_wait(tmem_full + acc, acc_phase)) { if (lane == 0) *p.err = 4; break; }
+            tc_fence_after();
+            epilogue_tile<BN2>(p, tmem_base, acc, q, lane, out_row, nt);
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_cluster(mapa_u32(smem_u32(tmem_empty + acc), 0));
+            if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+        }
+    }
+    // ---- teardown: nobody may still be signalling the peer or using TMEM
+    tc_fence_before();
+    cluster_sync_all();
+    tc_fence_after();
+    if (warp == 2) tmem_dealloc2(tmem_base, Cfg::kTmemCols);
+}
+
+// ===================================================================================================================
 // Halo variant for stride-1 RxS convolutions on feature maps with W >= 16, H >= 8.
 //
 // The per-tap kernel above re-fetches the A tile from L2 once per filter tap (9x for 3x3); measured on B200 it is
@@ -656,25 +775,47 @@ static int g_conv_algo = -1;     // -1 auto (= per-tap until the halo variant is
 void tc_set_halo_desc_mode(int) {}   // kept for scripts/conv_one.py; the base_offset experiment is settled (always 0)
 void tc_set_conv_algo(int a) { g_conv_algo = a; }
 
-static int g_gemm_bn = -1;       // -1 auto, 128 / 256 force the N tile of the plain GEMM
+static int g_gemm_bn = -1;       // -1 auto, 128 / 256 force the N tile of the plain GEMM, 2 = CTA-pair kernel (256 x 256 tiles)
 void tc_set_gemm_bn(int b) { g_gemm_bn = b; }
+
+static const char* launch_pair(const CUtensorMap& ta, const CUtensorMap& tb, const TcParams& p, cudaStream_t stream) {
+    static bool attr = false;
+    if (!attr) {
+        if (cudaFuncSetAttribute(tc_gemm2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Tc2Cfg::kSmemBytes) != cudaSuccess) return "cannot raise dynamic smem";
+        attr = true;
+    }
+    const int tiles = p.n_tiles_m * p.n_tiles_n;
+    int pairs = num_sms() / 2;
+    if (tiles < pairs) pairs = tiles;
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(2 * pairs); cfg.blockDim = dim3(kThreads); cfg.dynamicSmemBytes = Tc2Cfg::kSmemBytes; cfg.stream = stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, tc_gemm2_kernel, ta, tb, p) == cudaSuccess ? nullptr : "kernel launch failed";
+}
 
 // C[M,N] = A[M,K] B[N,K]^T ; lda/ldb = K (dense rows)
 const char* tc_gemm_tn(const void* A, const void* B, void* C, const void* bias, int M, int N, int K, int relu, cudaStream_t stream) {
     if (K % 8) return "K must be a multiple of 8";
     int BN = N <= 64 ? 64 : 128;
-    if (g_gemm_bn == 256 && N >= 256) BN = 256;
+    // CTA-pair kernel (256 x 256 tiles): forced by tc_set_gemm_bn(2); automatic when the problem fills every SM pair
+    // (measured 1.28-1.56 PF/s vs 1.12-1.53 for the 1-CTA kernel, profiles/run22_gemm_pair.md)
+    const bool pair = N >= 256 && M >= 256 && (g_gemm_bn == 2 || (g_gemm_bn == -1 && ((M + 255) / 256) * ((N + 255) / 256) >= num_sms() / 2));
+    if (pair || (g_gemm_bn == 256 && N >= 256)) BN = 256;
     else if (g_gemm_bn == -1 && N >= 512 && ((M + BM - 1) / BM) * ((N + 255) / 256) >= num_sms()) BN = 256;   // enough tiles to fill the chip
     CUtensorMap ta, tb;
     uint64_t da[2] = {(uint64_t)K, (uint64_t)M}, sa[1] = {(uint64_t)K * 2};
     uint64_t db[2] = {(uint64_t)K, (uint64_t)N}, sb[1] = {(uint64_t)K * 2};
-    uint32_t boxa[2] = {BK, BM}, boxb[2] = {BK, (uint32_t)BN}, es[2] = {1, 1};
+    uint32_t boxa[2] = {BK, BM}, boxb[2] = {BK, (uint32_t)(pair ? 128 : BN)}, es[2] = {1, 1};
     if (const char* e = make_tmap(&ta, A, 2, da, sa, boxa, es)) return e;
     if (const char* e = make_tmap(&tb, B, 2, db, sb, boxb, es)) return e;
     TcParams p{};
     p.M = M; p.N = N; p.num_kb = (K + BK - 1) / BK; p.mode = 0;
-    p.n_tiles_m = (M + BM - 1) / BM; p.n_tiles_n = (N + BN - 1) / BN;
+    p.n_tiles_m = (M + (pair ? 256 : BM) - 1) / (pair ? 256 : BM); p.n_tiles_n = (N + BN - 1) / BN;
     p.bias = (const __nv_bfloat16*)bias; p.relu = relu; p.C = (__nv_bfloat16*)C; p.err = err_word();
+    if (pair) return launch_pair(ta, tb, p, stream);
     return BN == 64 ? launch<64>(ta, tb, p, stream) : (BN == 128 ? launch<128>(ta, tb, p, stream) : launch<256>(ta, tb, p, stream));
 }
 

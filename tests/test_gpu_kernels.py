@@ -415,3 +415,22 @@ def test_stem_wgrad(ext, shape):
     F.conv2d(x.float(), w, None, 1, 1).backward(dy.float())
     assert sc.abs().max().item() == 0
     assert (dw.float() - w.grad).abs().max().item() <= 0.02 * max(1.0, w.grad.abs().max().item())
+
+
+@pytest.mark.parametrize("shape", [(256, 256, 64), (512, 768, 256), (1000, 520, 328), (2048, 1024, 512)])
+def test_tc_gemm_cta_pair(ext, shape):
+    """tcgen05.mma.cta_group::2 kernel (two SMs per 256 x 256 tile, TMA signalling the leader's barrier, multicast commits)."""
+    M, N, K = shape
+    torch.manual_seed(1)
+    x = (torch.randn(M, K, device="cuda") * 0.1).to(torch.bfloat16)
+    w = (torch.randn(N, K, device="cuda") * 0.1).to(torch.bfloat16)
+    b = torch.randn(N, device="cuda").to(torch.bfloat16)
+    ext.tc_set_gemm_bn(2)
+    try:
+        y = ext.gemm_tn(x, w, b, True).float()
+        torch.cuda.synchronize()
+    finally:
+        ext.tc_set_gemm_bn(-1)
+    assert ext.tc_error() == 0
+    ref = torch.relu(x.float() @ w.float().t() + b.float())
+    assert (y - ref).abs().max().item() <= 0.02 * max(1.0, ref.abs().max().item())
