@@ -61,6 +61,8 @@ def add_fit_args(parser: argparse.ArgumentParser, argv=None):
     parser.add_argument('--mode', type=str, default='normal', metavar='N',
                         help="normal | kill (signal-kill stragglers) | timeout (kill after --kill-threshold seconds)")
     parser.add_argument('--kill-threshold', type=float, default=7.0, metavar='KT', help='straggler timeout in seconds')
+    parser.add_argument('--topology', type=str, default='ps', choices=['ps', 'sharded'],
+                        help='ps: rank 0 is the parameter server (reference) | sharded: every rank serves 1/W of the parameters (NVLink tier only)')
     parser.add_argument('--parallelism', type=str, default='ps', choices=['ps', 'ddp'],
                         help='ps: parameter server (the reference\'s product path) | ddp: all-reduce data parallelism (its vendored DistributedDataParallel)')
     parser.add_argument('--comm-type', type=str, default='Bcast', metavar='N', help='Bcast (multicast weight push) | Async (workers pull weights)')

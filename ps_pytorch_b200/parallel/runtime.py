@@ -131,10 +131,55 @@ def run_ddp(args):
     return {"ddp": ddp, "losses": losses, "master": master}
 
 
+def run_sharded(args):
+    """``--topology sharded``: every rank is a worker and the server of 1/W of the parameter arena (the scalable form of the PS; the
+    reference pins ``n_masters`` to 1, ``/root/reference/tools/pytorch_ec2.py:26``).  All ranks run the same loop, so it is driven
+    through ``engine.PSJob`` rather than the master/worker role loops."""
+    import time
+
+    from ..engine import PSJob
+    from ..utils.obs import format_worker_line
+
+    use_cuda = bool(args.enable_gpu) and not args.no_cuda and torch.cuda.is_available()
+    if not use_cuda:
+        raise SystemExit("--topology sharded needs the NVLink tier (GPUs): shards are served by peer-memory kernels")
+    rank, local_rank, world = init_process_group(True)
+    device = torch.device("cuda", local_rank)
+    seed_everything(args.seed, rank)
+    gd = args.grad_dtype
+    if gd == "auto":
+        gd = "bf16"
+    job = PSJob(network=args.network, dataset=args.dataset, batch_size=args.batch_size, device=device, dtype=args.dtype, lr=args.lr,
+                momentum=args.momentum, optimizer=args.optimizer, weight_decay=args.weight_decay, nesterov=args.nesterov, transport="nvl",
+                topology="sharded", grad_dtype=gd, num_aggregate=None, cuda_graph=args.cuda_graph, backend=args.backend,
+                max_steps=args.max_steps, eval_freq=args.eval_freq, train_dir=args.train_dir, seed=args.seed)
+    train_loader, _ = prepare_data(args, rank=rank, pin=True, out_dtype=torch.float32, channels_last=True)
+    n = len(train_loader.dataset)
+    for step in range(1, args.max_steps + 1):
+        t0 = time.time()
+        x, y = train_loader.next_batch()
+        loss = job.step(x, y)
+        if step % max(1, args.log_interval) == 0:
+            logger.info(format_worker_line(rank, step, step * args.batch_size // max(1, n), (step * args.batch_size) % max(1, n), n, float(loss),
+                                           time.time() - t0, 0.0, 0.0, 0.0, 0.0))
+        if args.eval_freq > 0 and step % args.eval_freq == 0:
+            if rank == 0:                                # rank 0's own replica supplies the BN statistics of the checkpoint
+                job.comm.worker_send_buffers(step, job.worker.compute.buffers_flat())
+            job.master.cur_step = step
+            job.master._save_model()                     # collective: gathers the shards, rank 0 writes model_step_<step>
+            job.master.cur_step = step + 1
+    job.close()
+    if dist.is_initialized():
+        dist.barrier()
+    return {"job": job}
+
+
 def run_distributed(args):
     """Body of ``distributed_nn.py``: build data, roles and transport from flags, then run."""
     if getattr(args, "parallelism", "ps") == "ddp":
         return run_ddp(args)
+    if getattr(args, "topology", "ps") == "sharded":
+        return run_sharded(args)
     use_cuda = bool(args.enable_gpu) and not args.no_cuda and torch.cuda.is_available()
     rank, local_rank, world = init_process_group(use_cuda)
     device = torch.device("cuda", local_rank) if use_cuda else torch.device("cpu")
