@@ -20,6 +20,7 @@ std::vector<at::Tensor> bn_forward(at::Tensor, c10::optional<at::Tensor>, c10::o
                                    c10::optional<at::Tensor>, bool, double, double, bool, c10::optional<at::Tensor>);
 std::vector<at::Tensor> bn_backward(at::Tensor, c10::optional<at::Tensor>, at::Tensor, c10::optional<at::Tensor>, at::Tensor, at::Tensor, bool, bool, c10::optional<at::Tensor>,
                                     c10::optional<at::Tensor>, c10::optional<at::Tensor>);
+void bn_set_finalize_wide(int);
 // elementwise.cu
 at::Tensor relu_forward(at::Tensor);
 at::Tensor relu_backward(at::Tensor, at::Tensor);
@@ -51,7 +52,7 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
     m.def("sgd_flat", &sgd_flat); m.def("adam_flat", &adam_flat);
     m.def("push", &push); m.def("reduce_update", &reduce_update); m.def("bcast", &bcast); m.def("wait_flag", &wait_flag);
     m.def("add_step", &add_step); m.def("set_word", &set_word); m.def("make_hp", &make_hp); m.def("hp_steps", &hp_steps);
-    m.def("bn_forward", &bn_forward); m.def("bn_backward", &bn_backward);
+    m.def("bn_forward", &bn_forward); m.def("bn_backward", &bn_backward); m.def("bn_set_finalize_wide", &bn_set_finalize_wide);
     m.def("relu_forward", &relu_forward); m.def("relu_backward", &relu_backward);
     m.def("maxpool2x2_forward", &maxpool2x2_forward); m.def("maxpool2x2_backward", &maxpool2x2_backward);
     m.def("gap_forward", &gap_forward); m.def("gap_backward", &gap_backward); m.def("softmax_ce", &softmax_ce);

@@ -317,6 +317,87 @@ __global__ void __launch_bounds__(256) bn_bwd_finalize_kernel(const float* __res
     }
 }
 
+// ---- wide finalize (opt-in: bn_set_finalize_wide(1) / PSB200_BN_FINALIZE=wide) -------------------------------------------
+// profiles/run23_launch_list_final.md: the finalize kernels above cost 26-35 us each under ncu (40 launches per ResNet-18 step) because 2-16 CTAs
+// walk ~74 partial rows per thread in dependent batches.  Here one CTA owns 8 channels (one 32-byte sector of a partial row): thread
+// (g = tid / 8, cc = tid % 8) sums rows g, g+32, g+64, ... with eight predicated loads in flight per batch (3 batches for 592 rows),
+// the 32 row groups are folded through shared memory and threads 0..7 finish their channel with the same arithmetic as above.
+// Sums s (first half of a partial row) and q (second half) for channel c over all nblk rows; valid in threads with g == 0 after the call.
+__device__ __forceinline__ void wide_partial_sum(const float* __restrict__ partial, int nblk, int C, int c, float& s, float& q) {
+    __shared__ float ss[32][8], sq[32][8];
+    const int cc = threadIdx.x & 7, g = threadIdx.x >> 3;
+    float s8[8] = {0, 0, 0, 0, 0, 0, 0, 0}, q8[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    if (c < C) {
+        for (int b = g; b < nblk; b += 8 * 32) {
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const int bb = b + 32 * u;
+                if (bb < nblk) {
+                    s8[u] += __ldg(partial + (long long)bb * 2 * C + c);
+                    q8[u] += __ldg(partial + (long long)bb * 2 * C + C + c);
+                }
+            }
+        }
+    }
+    s = 0.f; q = 0.f;
+#pragma unroll
+    for (int u = 0; u < 8; ++u) { s += s8[u]; q += q8[u]; }
+    ss[g][cc] = s; sq[g][cc] = q;
+    __syncthreads();
+    if (g == 0) {
+        for (int t = 1; t < 32; ++t) { s += ss[t][cc]; q += sq[t][cc]; }
+    }
+}
+
+template <typename PT>
+__global__ void __launch_bounds__(256) bn_finalize_wide_kernel(const float* __restrict__ partial, int nblk, int C, long long M,
+                                                               const __nv_bfloat16* __restrict__ x_row0, const PT* __restrict__ gamma,
+                                                               const PT* __restrict__ beta, float* running_mean, float* running_var,
+                                                               float momentum, float eps, float* __restrict__ mean, float* __restrict__ invstd,
+                                                               float* __restrict__ coef_a, float* __restrict__ coef_b) {
+    const int c = blockIdx.x * 8 + (threadIdx.x & 7);
+    float s, q;
+    wide_partial_sum(partial, nblk, C, c, s, q);
+    if ((threadIdx.x >> 3) == 0 && c < C) {
+        const float inv_m = 1.f / (float)M;
+        const float dm = s * inv_m;
+        const float K = __bfloat162float(x_row0[c]);
+        const float mu = K + dm;
+        const float var = fmaxf(q * inv_m - dm * dm, 0.f);
+        const float is = rsqrtf(var + eps);
+        mean[c] = mu; invstd[c] = is;
+        const float ga = gamma ? to_f(gamma[c]) : 1.f, be = beta ? to_f(beta[c]) : 0.f;
+        coef_a[c] = ga * is;
+        coef_b[c] = be - mu * ga * is;
+        if (running_mean) {
+            const float unbiased = M > 1 ? var * (float)M / (float)(M - 1) : var;
+            running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * mu;
+            running_var[c] = (1.f - momentum) * running_var[c] + momentum * unbiased;
+        }
+    }
+}
+
+template <typename PT>
+__global__ void __launch_bounds__(256) bn_bwd_finalize_wide_kernel(const float* __restrict__ partial, int nblk, int C, long long M,
+                                                                   const PT* __restrict__ gamma, const float* __restrict__ invstd,
+                                                                   PT* __restrict__ dgamma, PT* __restrict__ dbeta, float* __restrict__ c1,
+                                                                   float* __restrict__ c2, float* __restrict__ c3) {
+    const int c = blockIdx.x * 8 + (threadIdx.x & 7);
+    float s, q;
+    wide_partial_sum(partial, nblk, C, c, s, q);
+    if ((threadIdx.x >> 3) == 0 && c < C) {
+        const float is = invstd[c];
+        const float ga = gamma ? to_f(gamma[c]) : 1.f;
+        if (dgamma) dgamma[c] = from_f<PT>(q * is);
+        if (dbeta) dbeta[c] = from_f<PT>(s);
+        const float inv_m = 1.f / (float)M;
+        c1[c] = ga * is; c2[c] = s * inv_m; c3[c] = q * is * is * inv_m;
+    }
+}
+
+static int g_bn_finalize_wide = 0;
+void bn_set_finalize_wide(int on) { g_bn_finalize_wide = on ? 1 : 0; }
+
 template <bool RELU, bool RES, bool MASKX>
 __global__ void __launch_bounds__(kBnThreads) bn_bwd_apply_kernel(const uint4* __restrict__ dz, const uint4* __restrict__ z, const uint4* __restrict__ x,
                                                                   const float* __restrict__ mean, const float* __restrict__ c1, const float* __restrict__ c2,
@@ -391,7 +472,15 @@ std::vector<at::Tensor> bn_forward(at::Tensor x, c10::optional<at::Tensor> gamma
         bn_stats_kernel<<<nblk, kBnThreads, kBnThreads * 16 * sizeof(float), stream>>>(xp, M, LC, partial.data_ptr<float>(), nullptr, BnFwdFin{});
         C10_CUDA_KERNEL_LAUNCH_CHECK();
         const int fb = (C + 31) / 32;
-        if (p_bf16)
+        if (g_bn_finalize_wide && p_bf16)
+            bn_finalize_wide_kernel<__nv_bfloat16><<<(C + 7) / 8, 256, 0, stream>>>(partial.data_ptr<float>(), nblk, C, M, (const __nv_bfloat16*)x.data_ptr(),
+                (const __nv_bfloat16*)gp, (const __nv_bfloat16*)bp, rm, rv, (float)momentum, (float)eps, mean.data_ptr<float>(), invstd.data_ptr<float>(),
+                ca.data_ptr<float>(), cb.data_ptr<float>());
+        else if (g_bn_finalize_wide)
+            bn_finalize_wide_kernel<float><<<(C + 7) / 8, 256, 0, stream>>>(partial.data_ptr<float>(), nblk, C, M, (const __nv_bfloat16*)x.data_ptr(),
+                (const float*)gp, (const float*)bp, rm, rv, (float)momentum, (float)eps, mean.data_ptr<float>(), invstd.data_ptr<float>(),
+                ca.data_ptr<float>(), cb.data_ptr<float>());
+        else if (p_bf16)
             bn_finalize_kernel<__nv_bfloat16><<<fb, 256, 0, stream>>>(partial.data_ptr<float>(), nblk, C, M, (const __nv_bfloat16*)x.data_ptr(),
                 (const __nv_bfloat16*)gp, (const __nv_bfloat16*)bp, rm, rv, (float)momentum, (float)eps, mean.data_ptr<float>(), invstd.data_ptr<float>(),
                 ca.data_ptr<float>(), cb.data_ptr<float>());
@@ -459,7 +548,13 @@ std::vector<at::Tensor> bn_backward(at::Tensor dz, c10::optional<at::Tensor> z_o
         else bn_bwd_reduce_kernel<false, false><<<nblk, kBnThreads, smem, stream>>>(dzp, zp, xp, mean.data_ptr<float>(), M, LC, partial.data_ptr<float>(), nullptr, BnBwdFin{}, pca, pcb);
         C10_CUDA_KERNEL_LAUNCH_CHECK();
         const int fb = (C + 31) / 32;
-        if (p_bf16)
+        if (g_bn_finalize_wide && p_bf16)
+            bn_bwd_finalize_wide_kernel<__nv_bfloat16><<<(C + 7) / 8, 256, 0, stream>>>(partial.data_ptr<float>(), nblk, C, M, (const __nv_bfloat16*)gamma->data_ptr(), invstd.data_ptr<float>(),
+                (__nv_bfloat16*)dgamma.data_ptr(), (__nv_bfloat16*)dbeta.data_ptr(), c1.data_ptr<float>(), c2.data_ptr<float>(), c3.data_ptr<float>());
+        else if (g_bn_finalize_wide)
+            bn_bwd_finalize_wide_kernel<float><<<(C + 7) / 8, 256, 0, stream>>>(partial.data_ptr<float>(), nblk, C, M, gamma.has_value() ? gamma->data_ptr<float>() : nullptr, invstd.data_ptr<float>(),
+                dgamma.data_ptr<float>(), dbeta.data_ptr<float>(), c1.data_ptr<float>(), c2.data_ptr<float>(), c3.data_ptr<float>());
+        else if (p_bf16)
             bn_bwd_finalize_kernel<__nv_bfloat16><<<fb, 256, 0, stream>>>(partial.data_ptr<float>(), nblk, C, M, (const __nv_bfloat16*)gamma->data_ptr(), invstd.data_ptr<float>(),
                 (__nv_bfloat16*)dgamma.data_ptr(), (__nv_bfloat16*)dbeta.data_ptr(), c1.data_ptr<float>(), c2.data_ptr<float>(), c3.data_ptr<float>());
         else

@@ -14,6 +14,17 @@ from . import count_launch, require
 # wgrad and the 16 extra registers cost occupancy.  Off by default.
 _MASKX = os.environ.get("PSB200_BN_MASKX", "0") != "0"
 _DETERMINISTIC = os.environ.get("PSB200_BN_FUSED_FINALIZE", "0") == "0"
+# "wide": one CTA per 8 channels in the two finalize kernels (profiles/run23_launch_list_final.md).  Written after this round's GPU budget was
+# spent: compiled and covered by an opt-in test, off by default until it has been run on hardware.
+_FINALIZE_WIDE = os.environ.get("PSB200_BN_FINALIZE", "") == "wide"
+_wide_applied = False
+
+
+def _apply_switches(ext):
+    global _wide_applied
+    if _FINALIZE_WIDE and not _wide_applied:
+        ext.bn_set_finalize_wide(1)
+        _wide_applied = True
 
 
 def _workspace(module, c, device):
@@ -43,6 +54,7 @@ class _BatchNormFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, weight, bias, residual, running_mean, running_var, training, momentum, eps, relu, ws):
         ext = require()
+        _apply_switches(ext)
         x = x.contiguous(memory_format=torch.channels_last)
         if residual is not None:
             residual = residual.contiguous(memory_format=torch.channels_last)
