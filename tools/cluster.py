@@ -98,12 +98,18 @@ def main():
     ap.add_argument("--nfs-dir", default="/mnt/psb200_shared")
     ap.add_argument("--gloo", action="store_true", help="launch: one multi-node gloo-tier job instead of independent single-box jobs")
     ap.add_argument("--nproc-per-node", type=int, default=0)
-    ap.add_argument("rest", nargs=argparse.REMAINDER)
-    a = ap.parse_args()
+    ap.add_argument("--out-dir", default=HERE, help="get_hosts: where to write hosts / hosts_alias / hosts_address")
+    ap.add_argument("rest", nargs="*", help="run_command / launch: the command or flags (put them after --)")
+    argv = sys.argv[1:]
+    tail = []
+    if "--" in argv:                                   # options may come before or after the verb; everything after -- is passed through
+        i = argv.index("--")
+        argv, tail = argv[:i], argv[i + 1:]
+    a = ap.parse_args(argv)
     nodes = read_inventory(a.inventory)
-    rest = [x for x in a.rest if x != "--"]
+    rest = list(a.rest) + tail
     if a.verb == "get_hosts":
-        return get_hosts(nodes, HERE)
+        return get_hosts(nodes, a.out_dir)
     if a.verb == "run_command":
         return show(parallel(nodes, " ".join(rest)))
     if a.verb == "status":
