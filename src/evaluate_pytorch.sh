@@ -2,8 +2,9 @@
 # Evaluator launch line of the reference (src/evaluate_pytorch.sh): polls --model-dir for model_step_<k*eval_freq>.
 cd "$(dirname "$0")"
 python distributed_evaluator.py \
---eval-batch-size=10000 \
+--eval-batch-size=${EVAL_BATCH:-10000} \
 --eval-freq=${EVAL_FREQ:-20} \
---network=ResNet18 \
---dataset=Cifar10 \
---model-dir=${TRAIN_DIR:-output/models/}
+--network=${NETWORK:-ResNet18} \
+--dataset=${DATASET:-Cifar10} \
+--model-dir=${TRAIN_DIR:-output/models/} \
+"$@"
