@@ -85,3 +85,16 @@ print('facades ok')
 """
     r = subprocess.run([sys.executable, "-c", code], cwd=os.path.join(ROOT, "src"), capture_output=True, text=True, env=ENV, timeout=300)
     assert r.returncode == 0 and "facades ok" in r.stdout, r.stdout[-1500:] + r.stderr[-3000:]
+
+
+def test_reference_launch_scripts(tmp_path):
+    """src/run_pytorch.sh -> src/evaluate_pytorch.sh, the reference's two launch lines, on a small CPU configuration."""
+    d = str(tmp_path) + "/"
+    env = dict(ENV, NPROC="3", NETWORK="LeNet", DATASET="MNIST", BATCH="32", MAX_STEPS="6", EVAL_FREQ="3", TRAIN_DIR=d, CUDA_VISIBLE_DEVICES="")
+    r = subprocess.run(["bash", os.path.join(ROOT, "src", "run_pytorch.sh")], capture_output=True, text=True, env=env, timeout=280)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert os.path.isfile(d + "model_step_3") and os.path.isfile(d + "model_step_6")
+    env["EVAL_BATCH"] = "256"
+    r = subprocess.run(["bash", os.path.join(ROOT, "src", "evaluate_pytorch.sh"), "--max-evals", "2", "--poll-seconds", "0.2"],
+                       capture_output=True, text=True, env=env, timeout=200)
+    assert r.returncode == 0 and r.stdout.count("Test set: Average loss") == 2, r.stdout[-1500:] + r.stderr[-1500:]
