@@ -5,9 +5,10 @@ cd "$(dirname "$0")"
 tune_dir=${TUNE_DIR:-./tune/}
 max_tuning_step=${MAX_TUNING_STEP:-100}
 nproc=${NPROC:-17}
+lrs=${LRS:-"0.0078125 0.015625 0.03125 0.0625 0.125 0.25 0.5"}
 mkdir -p "${tune_dir}"
 echo "Start parameter tuning ..."
-for lr in 0.0078125 0.015625 0.03125 0.0625 0.125 0.25 0.5
+for lr in ${lrs}
 do
   echo "Trial running for learning rate: ${lr}"
   python -m ps_pytorch_b200.launch -n ${nproc} distributed_nn.py \
@@ -16,7 +17,7 @@ do
   --enable-gpu=${ENABLE_GPU:-} --train-dir=${tune_dir} > ${tune_dir}lr_${lr} 2>&1
   grep "Step: ${max_tuning_step}," ${tune_dir}lr_${lr} > ${tune_dir}lr_${lr}_processing
 done
-for lr in 0.0078125 0.015625 0.03125 0.0625 0.125 0.25 0.5
+for lr in ${lrs}
 do
   echo "Logging out tunning results"
   python tiny_tuning_parser.py --tuning-dir=${tune_dir}lr_${lr}_processing --tuning-lr=${lr} --num-workers=$((nproc-1))

@@ -98,3 +98,14 @@ def test_reference_launch_scripts(tmp_path):
     r = subprocess.run(["bash", os.path.join(ROOT, "src", "evaluate_pytorch.sh"), "--max-evals", "2", "--poll-seconds", "0.2"],
                        capture_output=True, text=True, env=env, timeout=200)
     assert r.returncode == 0 and r.stdout.count("Test set: Average loss") == 2, r.stdout[-1500:] + r.stderr[-1500:]
+
+
+def test_lr_sweep_script(tmp_path):
+    """src/tune.sh: run each learning-rate candidate for a few steps, grep the last step's worker lines, average the loss per candidate."""
+    d = str(tmp_path) + "/"
+    env = dict(ENV, NPROC="3", NETWORK="LeNet", DATASET="MNIST", BATCH="16", MAX_TUNING_STEP="4", TUNE_DIR=d, LRS="0.01 0.1", CUDA_VISIBLE_DEVICES="")
+    r = subprocess.run(["bash", os.path.join(ROOT, "src", "tune.sh")], capture_output=True, text=True, env=env, timeout=280)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    lines = [l for l in r.stdout.splitlines() if l.startswith("Avged loss for lr candidate")]
+    assert len(lines) == 2 and "0.01=========>" in lines[0] and "0.1=========>" in lines[1], r.stdout[-1500:]
+    assert "Illegal Number of Workers" not in r.stdout
