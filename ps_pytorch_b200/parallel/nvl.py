@@ -20,8 +20,6 @@ from __future__ import annotations
 
 import os
 import time
-from typing import List, Optional
-
 import torch
 import torch.distributed as dist
 

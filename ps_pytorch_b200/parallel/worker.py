@@ -9,17 +9,14 @@ rebuild), and "send grads" is one push per bucket that can overlap the remaining
 from __future__ import annotations
 
 import time
-from typing import Optional
-
 import torch
 
-from .arena import ParamLayout
 from .compute import WorkerCompute, resolve_dtype
 from .transport import Transport
 from ..models import build_model
 from ..models.layerwise import LayerwiseBackwardMixin, StragglerKilled
 from ..utils import checkpoint as ckpt
-from ..utils.metrics import accuracy
+from ..utils.metrics import accuracy  # noqa: F401  (the reference defines accuracy() in this module; kept importable from here)
 from ..utils.obs import JsonlSink, format_worker_line, logger
 
 STEP_START_ = 1
