@@ -18,6 +18,8 @@ from ..nn.backend import note_fallback
 # (PSB200_TC_CONV=1 / set_tc_conv(True)) until it wins; every other layer of the sm100 backend is ours regardless.
 _MODE = os.environ.get("PSB200_TC_CONV", "0").lower()       # "0" library, "1" every supported conv, "auto" only where ours wins
 _ENABLED = _MODE != "0"
+_HALO_PAIR = os.environ.get("PSB200_TC_HALO_PAIR", "0") != "0"   # EXPERIMENTAL cta_group::2 halo kernel, not yet run on hardware
+_pair_applied = False
 
 
 def set_tc_conv(on) -> None:
@@ -36,6 +38,10 @@ def unsupported_reason(x, weight, stride, padding, dilation, groups):
     ext = require()
     if not hasattr(ext, "conv_fprop"):
         return "tcgen05 implicit-GEMM conv not built"
+    global _pair_applied
+    if _HALO_PAIR and not _pair_applied:
+        ext.tc_set_halo_pair(1)
+        _pair_applied = True
     if isinstance(padding, str):
         return "string padding"
     if _MODE == "auto":

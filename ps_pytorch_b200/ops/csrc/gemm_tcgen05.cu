@@ -522,6 +522,138 @@ tc_conv_halo_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
 }
 
 // ===================================================================================================================
+// CTA-pair halo convolution (EXPERIMENTAL: written after this round's GPU budget was spent; compiled, not yet run on hardware;
+// enabled only by tc_set_halo_pair(1) / PSB200_TC_HALO_PAIR=1).
+//
+// Same tile geometry and shifted-window A descriptors as tc_conv_halo_kernel, with the pair mechanics proven by tc_gemm2_kernel:
+// the two CTAs of a cluster take neighbouring M tiles (2 x 128 output pixels) of the same N tile; each loads its own halo patch
+// and HALF of the weight rows (BN/2 output channels of every tap); every TMA signals the leader's barriers; the leader issues
+// tcgen05.mma.cta_group::2 with M = 256, N = BN; commits are multicast to both CTAs.  Per MMA each SM then reads 4 KB of A and
+// BN/2 x 32 B of B instead of BN x 32 B (128 -> 96 cycles per instruction for BN = 128, 96 -> 80 for BN = 64).
+template <int BN>
+__global__ void __launch_bounds__(kThreads, 1)
+tc_conv_halo2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, const TcParams p) {
+    using Cfg = HaloCfg<BN>;
+    constexpr int kHalfTapBytes = (BN / 2) * BK * 2;          // this CTA's share of one tap's B tile
+    const uint32_t rank = cluster_ctarank();
+    const bool leader = rank == 0;
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* smem_a = smem;
+    uint8_t* smem_b = smem + p.a_stages * p.a_stage_bytes;
+    const int b_stage_bytes = p.S * kHalfTapBytes;
+    uint64_t* a_full = reinterpret_cast<uint64_t*>(smem_b + Cfg::kBStages * b_stage_bytes);
+    uint64_t* a_empty = a_full + kMaxAStages;
+    uint64_t* b_full = a_empty + kMaxAStages;
+    uint64_t* b_empty = b_full + Cfg::kBStages;
+    uint64_t* tmem_full = b_empty + Cfg::kBStages;
+    uint64_t* tmem_empty = tmem_full + 2;
+    uint32_t* tmem_base_smem = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (warp == 0 && lane == 0) { prefetch_tmap(&tmap_a); prefetch_tmap(&tmap_b); }
+    if (warp == 1 && lane == 0) {
+        for (int s = 0; s < p.a_stages; ++s) { mbar_init(a_full + s, 1); mbar_init(a_empty + s, 1); }
+        for (int s = 0; s < Cfg::kBStages; ++s) { mbar_init(b_full + s, 1); mbar_init(b_empty + s, 1); }
+        for (int s = 0; s < 2; ++s) { mbar_init(tmem_full + s, 1); mbar_init(tmem_empty + s, 8); }
+        fence_barrier_init();
+    }
+    if (warp == 2) tmem_alloc2(tmem_base_smem, Cfg::kTmemCols);
+    tc_fence_before();
+    cluster_sync_all();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_base_smem;
+    // pair tiles: nt slowest, pairs of neighbouring M tiles fastest; rank r takes M tile 2*pm + r (a ghost when n_tiles_m is odd)
+    const int n_pairs_m = (p.n_tiles_m + 1) / 2;
+    const int n_ptiles = n_pairs_m * p.n_tiles_n;
+    const int cluster_id = blockIdx.x >> 1, n_clusters = gridDim.x >> 1;
+
+    if (warp == 0) {
+        int as = 0; uint32_t aph = 0; int bs = 0; uint32_t bph = 0;
+        for (int pt = cluster_id; pt < n_ptiles; pt += n_clusters) {
+            const int nt = pt / n_pairs_m, mt = 2 * (pt % n_pairs_m) + (int)rank;
+            const bool ghost = mt >= p.n_tiles_m;
+            const int tw = mt % p.tiles_w, th = (mt / p.tiles_w) % p.tiles_h, n = ghost ? p.NB : mt / (p.tiles_w * p.tiles_h);
+            for (int cb = 0; cb < p.cblocks; ++cb) {
+                if (!mbar_wait(a_empty + as, aph ^ 1)) { *p.err = 21; return; }
+                if (elect_one()) {
+                    if (leader) mbar_arrive_expect_tx(a_full + as, 2 * p.a_stage_bytes);
+                    tma_load_4d_2sm(smem_a + as * p.a_stage_bytes, &tmap_a, mapa_u32(smem_u32(a_full + as), 0), cb * BK, tw * 8 - p.pad, th * 16 - p.pad, n);
+                }
+                __syncwarp();
+                if (++as == p.a_stages) { as = 0; aph ^= 1; }
+                for (int r = 0; r < p.R; ++r) {
+                    if (!mbar_wait(b_empty + bs, bph ^ 1)) { *p.err = 22; return; }
+                    if (elect_one()) {
+                        if (leader) mbar_arrive_expect_tx(b_full + bs, 2 * b_stage_bytes);
+                        tma_load_3d_2sm(smem_b + bs * b_stage_bytes, &tmap_b, mapa_u32(smem_u32(b_full + bs), 0), cb * BK, nt * BN + (int)rank * (BN / 2), r * p.S);
+                    }
+                    __syncwarp();
+                    if (++bs == Cfg::kBStages) { bs = 0; bph ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1 && leader) {
+        constexpr uint32_t idesc = umma_idesc_bf16(256, BN, 0, 0);
+        int as = 0; uint32_t aph = 0; int bs = 0; uint32_t bph = 0; int acc = 0; uint32_t acc_phase = 0;
+        for (int pt = cluster_id; pt < n_ptiles; pt += n_clusters) {
+            if (!mbar_wait(tmem_empty + acc, acc_phase ^ 1)) { *p.err = 23; return; }
+            tc_fence_after();
+            const uint32_t tmem_d = tmem_base + acc * BN;
+            for (int cb = 0; cb < p.cblocks; ++cb) {
+                if (!mbar_wait(a_full + as, aph)) { *p.err = 24; return; }
+                const uint32_t sa0 = smem_u32(smem_a + as * p.a_stage_bytes);
+                for (int r = 0; r < p.R; ++r) {
+                    if (!mbar_wait(b_full + bs, bph)) { *p.err = 25; return; }
+                    tc_fence_after();
+                    const uint32_t sb0 = smem_u32(smem_b + bs * b_stage_bytes);
+                    if (elect_one()) {
+                        for (int s = 0; s < p.S; ++s) {
+                            const uint32_t sa = sa0 + (uint32_t)((r * 16 + s) * 128);
+                            const uint32_t sb = sb0 + (uint32_t)(s * kHalfTapBytes);
+#pragma unroll
+                            for (int k = 0; k < BK / 16; ++k)
+                                tc_mma2_bf16(tmem_d, umma_desc_k_sw128_sbo(sa + k * 32, 2048), umma_desc_k_sw128(sb + k * 32), idesc, (cb | r | s | k) != 0);
+                        }
+                        tc_commit2_mcast(b_empty + bs, 0b11);
+                    }
+                    __syncwarp();
+                    if (++bs == Cfg::kBStages) { bs = 0; bph ^= 1; }
+                }
+                if (elect_one()) tc_commit2_mcast(a_empty + as, 0b11);
+                __syncwarp();
+                if (++as == p.a_stages) { as = 0; aph ^= 1; }
+            }
+            if (elect_one()) tc_commit2_mcast(tmem_full + acc, 0b11);
+            __syncwarp();
+            if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+        }
+    } else if (warp >= kEpiWarp0) {
+        const int q = warp & 3;
+        int acc = 0; uint32_t acc_phase = 0;
+        for (int pt = cluster_id; pt < n_ptiles; pt += n_clusters) {
+            const int nt = pt / n_pairs_m, mt = 2 * (pt % n_pairs_m) + (int)rank;
+            const bool ghost = mt >= p.n_tiles_m;
+            const int tw = mt % p.tiles_w, th = (mt / p.tiles_w) % p.tiles_h, n = mt / (p.tiles_w * p.tiles_h);
+            const int m = q * 32 + lane;
+            const int h = th * 16 + (m >> 3), w = tw * 8 + (m & 7);
+            const long long out_row = (!ghost && h < p.Hout && w < p.Wout) ? ((long long)n * p.Hout + h) * p.Wout + w : -1;
+            if (!mbar_wait(tmem_full + acc, acc_phase)) { if (lane == 0) *p.err = 26; break; }
+            tc_fence_after();
+            epilogue_tile<BN>(p, tmem_base, acc, q, lane, out_row, nt);
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_cluster(mapa_u32(smem_u32(tmem_empty + acc), 0));
+            if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+        }
+    }
+    tc_fence_before();
+    cluster_sync_all();
+    tc_fence_after();
+    if (warp == 2) tmem_dealloc2(tmem_base, Cfg::kTmemCols);
+}
+
+// ===================================================================================================================
 // Weight gradient:  dW[co][r][s][ci] = sum over output pixels p of dY[p, co] * X[p*stride + (r,s) - pad, ci]
 //
 // A GEMM whose reduction dimension is the PIXEL index, so both operands are "MN-major" for the tensor core (the channel
@@ -771,6 +903,31 @@ static const char* launch_halo(const CUtensorMap& ta, const CUtensorMap& tb, con
     return cudaLaunchKernelEx(&cfg, tc_conv_halo_kernel<BN, CL>, ta, tb, p) == cudaSuccess ? nullptr : "kernel launch failed";
 }
 
+static int g_halo_pair = 0;           // EXPERIMENTAL CTA-pair halo kernel (not yet run on hardware): off unless requested
+void tc_set_halo_pair(int v) { g_halo_pair = v ? 1 : 0; }
+
+template <int BN>
+static const char* launch_halo_pair(const CUtensorMap& ta, const CUtensorMap& tb, const TcParams& p, cudaStream_t stream) {
+    using Cfg = HaloCfg<BN>;
+    const int smem_bytes = p.a_stages * p.a_stage_bytes + Cfg::kBStages * p.S * (BN / 2) * BK * 2 + 1024 + 512;
+    if (smem_bytes > 227 * 1024) return "halo tile does not fit in shared memory";
+    static int attr = 0;
+    if (attr < smem_bytes) {
+        if (cudaFuncSetAttribute(tc_conv_halo2_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes) != cudaSuccess) return "cannot raise dynamic smem";
+        attr = smem_bytes;
+    }
+    const int ptiles = ((p.n_tiles_m + 1) / 2) * p.n_tiles_n;
+    int pairs = num_sms() / 2;
+    if (ptiles < pairs) pairs = ptiles;
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(2 * pairs); cfg.blockDim = dim3(kThreads); cfg.dynamicSmemBytes = smem_bytes; cfg.stream = stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, tc_conv_halo2_kernel<BN>, ta, tb, p) == cudaSuccess ? nullptr : "kernel launch failed";
+}
+
 static int g_conv_algo = -1;     // -1 auto (= per-tap until the halo variant is validated on hardware), 0 per-tap, 1 halo
 void tc_set_halo_desc_mode(int) {}   // kept for scripts/conv_one.py; the base_offset experiment is settled (always 0)
 void tc_set_conv_algo(int a) { g_conv_algo = a; }
@@ -828,6 +985,7 @@ const char* tc_conv_fprop(const void* X, const void* Wt, void* Y, const void* bi
     const bool halo_ok = stride == 1 && R * S > 1 && S <= 8 && Wout >= 8 && Hout >= 16 && (16 + R - 1) <= 256;
     if (g_conv_algo == 1 && halo_ok) {
         const int BN = Cout <= 64 ? 64 : 128;
+        const bool pair = g_halo_pair && Cout % BN == 0;        // each CTA of the pair loads BN/2 weight rows per tap
         CUtensorMap ta, tb;
         uint64_t da[4] = {(uint64_t)Cin, (uint64_t)Win, (uint64_t)Hin, (uint64_t)NB};
         uint64_t sa[3] = {(uint64_t)Cin * 2, (uint64_t)Win * Cin * 2, (uint64_t)Hin * Win * Cin * 2};
@@ -835,7 +993,7 @@ const char* tc_conv_fprop(const void* X, const void* Wt, void* Y, const void* bi
         const int Ktot = R * S * Cin;
         // weights [Cout][R*S][Cin] as a 3-D tensor (Cin, Cout, taps): one box = S taps of one filter row
         uint64_t db[3] = {(uint64_t)Cin, (uint64_t)Cout, (uint64_t)(R * S)}, sb[2] = {(uint64_t)Ktot * 2, (uint64_t)Cin * 2};
-        uint32_t boxb[3] = {BK, (uint32_t)BN, (uint32_t)S}, esb[3] = {1, 1, 1};
+        uint32_t boxb[3] = {BK, (uint32_t)(pair ? BN / 2 : BN), (uint32_t)S}, esb[3] = {1, 1, 1};
         if (const char* e = make_tmap(&ta, X, 4, da, sa, boxa, esa)) return e;
         if (const char* e = make_tmap(&tb, Wt, 3, db, sb, boxb, esb)) return e;
         TcParams p{};
@@ -849,6 +1007,7 @@ const char* tc_conv_fprop(const void* X, const void* Wt, void* Y, const void* bi
         p.a_stages = 2;
         if (p.b_resident && 3 * p.a_stage_bytes + HaloCfg<64>::kBStages * S * HaloCfg<64>::kBTapBytes + 2048 <= 227 * 1024) p.a_stages = 3;
         p.bias = (const __nv_bfloat16*)bias; p.residual = (const __nv_bfloat16*)residual; p.relu = relu; p.C = (__nv_bfloat16*)Y; p.err = err_word();
+        if (pair) { p.b_resident = 0; p.a_stages = 2; return BN == 64 ? launch_halo_pair<64>(ta, tb, p, stream) : launch_halo_pair<128>(ta, tb, p, stream); }
         if (g_halo_cluster == 2 && (p.n_tiles_m % 2) == 0 && !p.b_resident) return BN == 64 ? launch_halo<64, 2>(ta, tb, p, stream) : launch_halo<128, 2>(ta, tb, p, stream);
         return BN == 64 ? launch_halo<64, 1>(ta, tb, p, stream) : launch_halo<128, 1>(ta, tb, p, stream);
     }

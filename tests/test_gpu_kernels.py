@@ -459,3 +459,25 @@ def test_bn_finalize_wide_matches_default(ext, C, HW):
         outs.append([t.float() for t in (z, mean, invstd, rm, rv, dx, dg, db)])
     for a, c in zip(*outs):
         assert (a - c).abs().max().item() <= 2e-2 * max(1.0, a.abs().max().item())
+
+
+@pytest.mark.skipif(os.environ.get("PSB200_EXPERIMENTAL") != "1", reason="CTA-pair halo conv has not run on hardware yet (written after the round's GPU budget was spent)")
+@pytest.mark.parametrize("shape", [(8, 64, 32, 32, 64, 3, 1, 1), (4, 64, 16, 16, 128, 3, 1, 1), (2, 64, 56, 56, 64, 3, 1, 1), (3, 128, 24, 16, 256, 3, 1, 1),
+                                   (1, 64, 16, 8, 64, 3, 1, 1)])
+def test_tc_conv_halo_cta_pair(ext, shape):
+    """EXPERIMENTAL tc_conv_halo2_kernel (cta_group::2): same contract as test_tc_conv_fprop; the last shape has an odd number of M tiles (ghost half)."""
+    NB, Cin, H, W, Cout, R, st, pad = shape
+    ext.tc_set_conv_algo(1)
+    ext.tc_set_halo_pair(1)
+    torch.manual_seed(0)
+    x = (torch.randn(NB, Cin, H, W, device="cuda") * 0.5).to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
+    w = (torch.randn(Cout, Cin, R, R, device="cuda") * (1.0 / math.sqrt(Cin * R * R))).to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
+    try:
+        y = ext.conv_fprop(x, w, None, st, pad, False)
+        torch.cuda.synchronize()
+    finally:
+        ext.tc_set_halo_pair(0)
+        ext.tc_set_conv_algo(-1)
+    assert ext.tc_error() == 0
+    ref = F.conv2d(x.float(), w.float(), None, st, pad)
+    assert (y.float() - ref).abs().max().item() <= 0.02 * max(1.0, ref.abs().max().item())
