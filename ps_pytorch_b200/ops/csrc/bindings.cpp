@@ -11,6 +11,7 @@ void reduce_update(std::vector<int64_t>, std::vector<int64_t>, int64_t, double, 
                    std::vector<int64_t>, int64_t, int64_t, double, bool);
 void bcast(int64_t, std::vector<int64_t>, int64_t, int64_t, std::vector<int64_t>, int64_t, int64_t, int64_t, int64_t);
 void wait_flag(int64_t, int64_t, int64_t, int64_t, double);
+void ru_set_mc_src(int64_t);
 void add_step(int64_t, int64_t);
 void set_word(int64_t, int64_t);
 at::Tensor make_hp(double, double, double, double, bool, double, double, double, bool, int64_t, int64_t);
@@ -52,7 +53,7 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
     m.def("sgd_flat", &sgd_flat); m.def("adam_flat", &adam_flat);
     m.def("push", &push); m.def("reduce_update", &reduce_update); m.def("bcast", &bcast); m.def("wait_flag", &wait_flag);
     m.def("add_step", &add_step); m.def("set_word", &set_word); m.def("make_hp", &make_hp); m.def("hp_steps", &hp_steps);
-    m.def("bn_forward", &bn_forward); m.def("bn_backward", &bn_backward); m.def("bn_set_finalize_wide", &bn_set_finalize_wide);
+    m.def("ru_set_mc_src", &ru_set_mc_src); m.def("bn_forward", &bn_forward); m.def("bn_backward", &bn_backward); m.def("bn_set_finalize_wide", &bn_set_finalize_wide);
     m.def("relu_forward", &relu_forward); m.def("relu_backward", &relu_backward);
     m.def("maxpool2x2_forward", &maxpool2x2_forward); m.def("maxpool2x2_backward", &maxpool2x2_backward);
     m.def("gap_forward", &gap_forward); m.def("gap_backward", &gap_backward); m.def("softmax_ce", &softmax_ce);

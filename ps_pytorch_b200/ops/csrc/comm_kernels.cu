@@ -160,6 +160,7 @@ struct RUArgs {
     long long* err;
     unsigned long long timeout_ns;
     int advance_step;                     // last CTA bumps *step_ptr and hp->steps
+    const void* mc_src;                   // NVLS variant only: multicast mapping of the (symmetric) gradient arenas
 };
 
 // raw wire words of 8 elements from source k (kept packed in registers so that all K loads can be in flight at once)
@@ -194,7 +195,9 @@ __device__ __forceinline__ void accum_raw8(const Raw8& r, float* g) {
     for (int j = 0; j < 8; ++j) g[j] += f[j];
 }
 
-template <int MODE>
+// NVLS = true (EXPERIMENTAL, not yet run on hardware; bf16 pull mode with take == P == every device of the multicast group): the P peer loads per element
+// are replaced by one multimem.ld_reduce through the switch, so the server receives one reduced stream instead of P.
+template <int MODE, bool NVLS = false>
 __global__ void __launch_bounds__(256, 2) reduce_update_kernel(RUArgs a) {
     __shared__ unsigned s_mask;
     const long long step = *a.step_ptr;
@@ -223,7 +226,9 @@ __global__ void __launch_bounds__(256, 2) reduce_update_kernel(RUArgs a) {
         if (mask == 0) return;                     // timed out: error word is set, host raises
         for (long long i = a.lo[b] + ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 8; i < a.hi[b]; i += stride) {
             float g[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-            {
+            if (NVLS) {
+                unpack8(multimem_ld_reduce_bf16x8(reinterpret_cast<const __nv_bfloat16*>(a.mc_src) + i), g);
+            } else {
                 // issue every selected source's load before the first add: up to 8 independent P2P/HBM loads in flight per
                 // lane, held as packed wire words (4-8 registers each)
                 constexpr int kBatch = MODE == WIRE_FP32 ? 4 : kMaxPeers;
@@ -356,6 +361,10 @@ void push(int64_t src, bool src_fp32, int64_t dst, int64_t dst_scale, int64_t lo
     C10_CUDA_KERNEL_LAUNCH_CHECK();
 }
 
+// one-shot selector of the NVLS variant for the NEXT reduce_update calls (0 = off): multicast address of the gradient arenas
+static int64_t g_ru_mc_src = 0;
+void ru_set_mc_src(int64_t p) { g_ru_mc_src = p; }
+
 void reduce_update(std::vector<int64_t> src, std::vector<int64_t> src_scale, int64_t take, double inv_div, int64_t mode,
                    int64_t g_ready, int64_t step_ptr, std::vector<int64_t> lo, std::vector<int64_t> hi, at::Tensor w,
                    c10::optional<at::Tensor> s0, c10::optional<at::Tensor> s1, c10::optional<at::Tensor> s2, int64_t hp,
@@ -384,7 +393,11 @@ void reduce_update(std::vector<int64_t> src, std::vector<int64_t> src_scale, int
     for (size_t b = 0; b < lo.size(); ++b) tot = std::max<long long>(tot, hi[b] - lo[b]);
     const int grid = grid_for(tot, 8);
     auto stream = at::cuda::getCurrentCUDAStream();
-    if (mode == WIRE_BF16) reduce_update_kernel<WIRE_BF16><<<grid, 256, 0, stream>>>(a);
+    a.mc_src = nullptr;
+    if (g_ru_mc_src && mode == WIRE_BF16 && a.take == a.P) {
+        a.mc_src = P(g_ru_mc_src);
+        reduce_update_kernel<WIRE_BF16, true><<<grid, 256, 0, stream>>>(a);
+    } else if (mode == WIRE_BF16) reduce_update_kernel<WIRE_BF16><<<grid, 256, 0, stream>>>(a);
     else if (mode == WIRE_FP8) reduce_update_kernel<WIRE_FP8><<<grid, 256, 0, stream>>>(a);
     else reduce_update_kernel<WIRE_FP32><<<grid, 256, 0, stream>>>(a);
     C10_CUDA_KERNEL_LAUNCH_CHECK();

@@ -34,6 +34,14 @@ __device__ __forceinline__ void st_na_v4(void* p, const uint4& v) {  // streamin
     asm volatile("st.global.L1::no_allocate.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 }
 // NVLS: one store, delivered by the switch to every GPU bound to the multicast object
+// In-switch reduction (NVLS): ONE load from the multicast address returns the sum over every device bound to the multicast object of the
+// 8 bf16 values at that symmetric offset; the adds happen in the NVSwitch with fp32 accumulation, the result is rounded to bf16.
+__device__ __forceinline__ uint4 multimem_ld_reduce_bf16x8(const void* mc) {
+    uint4 v;
+    asm volatile("multimem.ld_reduce.relaxed.sys.global.add.acc::f32.v4.bf16x2 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(mc) : "memory");
+    return v;
+}
 __device__ __forceinline__ void multimem_st_v4(void* mc, const uint4& v) {
     asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(mc), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 }

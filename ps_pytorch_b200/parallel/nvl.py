@@ -202,15 +202,29 @@ class NvlTransport(Transport):
             s0, s1, s2 = fs["buf"], None, None
         else:
             s0, s1, s2 = fs["m"], fs["v"], fs["vmax"]
-        self.ext.reduce_update(src, scl, int(take), 1.0 / float(k), int(mode), self.arena.local_ptr + self.off_flags + self.F_GREADY,
-                               self.p_psstep, lo, hi, master.flat, s0, s1, s2, hp_ptr, self._ru_dst(d),
-                               (self.arena.mc_ptr + self.off_w) if use_mc else 0, wready, self.p_counters, self.p_err,
-                               float(timeout_s or self.timeout_s), True)
+        nvls = self._nvls_reduce_ok(mode, take, len(src))
+        if nvls:
+            self.ext.ru_set_mc_src(self.arena.mc_ptr + self.off_grads)
+        try:
+            self.ext.reduce_update(src, scl, int(take), 1.0 / float(k), int(mode), self.arena.local_ptr + self.off_flags + self.F_GREADY,
+                                   self.p_psstep, lo, hi, master.flat, s0, s1, s2, hp_ptr, self._ru_dst(d),
+                                   (self.arena.mc_ptr + self.off_w) if use_mc else 0, wready, self.p_counters, self.p_err,
+                                   float(timeout_s or self.timeout_s), True)
+        finally:
+            if nvls:
+                self.ext.ru_set_mc_src(0)
         ops.count_launch()
         fs["steps"] += 1
         self._host_psstep += 1
         self._published = step + 1
         self.stats["bcast_bytes"] += self.T * 2
+
+    def _nvls_reduce_ok(self, mode, take, nsrc) -> bool:
+        """EXPERIMENTAL (``PSB200_NVLS_REDUCE=1``; not yet run on hardware): in pull mode the gradient arenas sit at the same symmetric offset
+        on every rank, so the server can read ONE in-switch-reduced stream (``multimem.ld_reduce``) instead of one stream per peer.  Valid only
+        when every device of the multicast group contributes: bf16 gradients, sharded topology, take == P == world size."""
+        return (os.environ.get("PSB200_NVLS_REDUCE", "0") == "1" and self.topology == "sharded" and bool(self.arena.mc_ptr) and mode == 0
+                and take == nsrc == self.world_size)
 
     def _ru_dst(self, d):
         # the kernel walks dst[] and w_ready[] with one index: in pull mode every entry stores to the PS replica (idempotent) while
@@ -343,10 +357,17 @@ class NvlTransport(Transport):
         self._raise_ready(self._my_slot())
         d = self.worker_ranks
         lo, hi = self.shards[self.rank]
-        self.ext.reduce_update([self.arena.peer_ptrs[r] + self.off_grads for r in d], [], len(d), 1.0 / len(d), 0,
-                               self.arena.local_ptr + self.off_flags + self.F_GREADY, self.p_psstep, [lo], [hi], self._ar_w, None, None, None,
-                               self._ar_hp.data_ptr(), [self.arena.peer_ptrs[r] + self.off_grads for r in d], 0,
-                               [self._flag(r, self.F_WREADY + 8 * self.rank) for r in d], self.p_counters, self.p_err, self.timeout_s, True)
+        nvls = self._nvls_reduce_ok(0, len(d), len(d))
+        if nvls:
+            self.ext.ru_set_mc_src(self.arena.mc_ptr + self.off_grads)
+        try:
+            self.ext.reduce_update([self.arena.peer_ptrs[r] + self.off_grads for r in d], [], len(d), 1.0 / len(d), 0,
+                                   self.arena.local_ptr + self.off_flags + self.F_GREADY, self.p_psstep, [lo], [hi], self._ar_w, None, None, None,
+                                   self._ar_hp.data_ptr(), [self.arena.peer_ptrs[r] + self.off_grads for r in d], 0,
+                                   [self._flag(r, self.F_WREADY + 8 * self.rank) for r in d], self.p_counters, self.p_err, self.timeout_s, True)
+        finally:
+            if nvls:
+                self.ext.ru_set_mc_src(0)
         ops.count_launch()
         self.ext.add_step(self.p_wstep, 1)
         # results are complete for the caller once every owner has published its shard

@@ -148,3 +148,13 @@ def test_cli_sharded_and_ddp_on_gpus(tmp_path, mode):
     m = build_model("ResNet18", 10)
     load_model_into(m, model_path(d, 12))
     assert all(torch.isfinite(p).all() for p in m.parameters())
+
+
+@pytest.mark.skipif(os.environ.get("PSB200_EXPERIMENTAL") != "1", reason="NVLS in-switch reduction has not run on hardware yet (written after the round's GPU budget was spent)")
+def test_nvls_ld_reduce_sharded_matches_reference(tmp_path):
+    """EXPERIMENTAL: sharded topology with the multimem.ld_reduce variant of the reduce kernel must produce the reference update."""
+    n = min(torch.cuda.device_count(), 2)
+    res = _run(n, str(tmp_path / "w.pt"), ["--steps", "3", "--network", "LeNet", "--bs", "64", "--topology", "sharded", "--grad-dtype", "bf16",
+                                           "--colocate", "1", "--backend", "library"], env_extra={"PSB200_NVLS_REDUCE": "1"})
+    ref = _reference(n, 3, 64, "LeNet")
+    _check(res, ref, _init("LeNet"), 0.97)
