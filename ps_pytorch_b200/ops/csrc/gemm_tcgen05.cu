@@ -298,7 +298,7 @@ tc_gemm2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
         for (int tile = pair; tile < n_tiles; tile += n_pairs) {
             const int mt = tile / p.n_tiles_n, nt = tile % p.n_tiles_n;
             for (int kb = 0; kb < p.num_kb; ++kb) {
-                if (!mbar_wait(empty_bar + stage, phase ^ 1)) { *p.err = 1; break; }
+                if (!mbar_wait(empty_bar + stage, phase ^ 1)) { *p.err = 1; goto teardown; }
                 uint8_t* sa = smem + stage * Cfg::kStageBytes;
                 uint8_t* sb = sa + Cfg::kABytes;
                 if (elect_one()) {
@@ -315,13 +315,12 @@ tc_gemm2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
         // ===================================================== MMA issuer (leader CTA only)
         constexpr uint32_t idesc = umma_idesc_bf16(256, BN2, 0, 0);
         int stage = 0; uint32_t phase = 0; int acc = 0; uint32_t acc_phase = 0;
-        bool ok = true;
-        for (int tile = pair; tile < n_tiles && ok; tile += n_pairs) {
-            if (!mbar_wait(tmem_empty + acc, acc_phase ^ 1)) { *p.err = 2; break; }
+        for (int tile = pair; tile < n_tiles; tile += n_pairs) {
+            if (!mbar_wait(tmem_empty + acc, acc_phase ^ 1)) { *p.err = 2; goto teardown; }
             tc_fence_after();
             const uint32_t tmem_d = tmem_base + acc * BN2;
             for (int kb = 0; kb < p.num_kb; ++kb) {
-                if (!mbar_wait(full_bar + stage, phase)) { *p.err = 3; ok = false; break; }
+                if (!mbar_wait(full_bar + stage, phase)) { *p.err = 3; goto teardown; }
                 tc_fence_after();
                 const uint32_t sa = smem_u32(smem + stage * Cfg::kStageBytes);
                 const uint32_t sb = sa + Cfg::kABytes;
@@ -334,7 +333,7 @@ tc_gemm2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
                 __syncwarp();
                 if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
             }
-            if (ok && elect_one()) tc_commit2_mcast(tmem_full + acc, 0b11);
+            if (elect_one()) tc_commit2_mcast(tmem_full + acc, 0b11);
             __syncwarp();
             if (++acc == 2) { acc = 0; acc_phase ^= 1; }
         }
@@ -346,7 +345,7 @@ tc_gemm2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
             const int mt = tile / p.n_tiles_n, nt = tile % p.n_tiles_n;
             const int m = mt * 256 + (int)rank * 128 + q * 32 + lane;
             const long long out_row = m < p.M ? m : -1;
-            if (!mbar_wait(tmem_full + acc, acc_phase)) { if (lane == 0) *p.err = 4; break; }
+            if (!mbar_wait(tmem_full + acc, acc_phase)) { if (lane == 0) *p.err = 4; goto teardown; }
             tc_fence_after();
             epilogue_tile<BN2>(p, tmem_base, acc, q, lane, out_row, nt);
             tc_fence_before();
@@ -355,7 +354,8 @@ tc_gemm2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
             if (++acc == 2) { acc = 0; acc_phase ^= 1; }
         }
     }
-    // ---- teardown: nobody may still be signalling the peer or using TMEM
+teardown:
+    // every thread of both CTAs gets here (also after a timed-out wait): nobody may still be signalling the peer or using TMEM
     tc_fence_before();
     cluster_sync_all();
     tc_fence_after();
@@ -575,7 +575,7 @@ tc_conv_halo2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
             const bool ghost = mt >= p.n_tiles_m;
             const int tw = mt % p.tiles_w, th = (mt / p.tiles_w) % p.tiles_h, n = ghost ? p.NB : mt / (p.tiles_w * p.tiles_h);
             for (int cb = 0; cb < p.cblocks; ++cb) {
-                if (!mbar_wait(a_empty + as, aph ^ 1)) { *p.err = 21; return; }
+                if (!mbar_wait(a_empty + as, aph ^ 1)) { *p.err = 21; goto teardown; }
                 if (elect_one()) {
                     if (leader) mbar_arrive_expect_tx(a_full + as, 2 * p.a_stage_bytes);
                     tma_load_4d_2sm(smem_a + as * p.a_stage_bytes, &tmap_a, mapa_u32(smem_u32(a_full + as), 0), cb * BK, tw * 8 - p.pad, th * 16 - p.pad, n);
@@ -583,7 +583,7 @@ tc_conv_halo2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
                 __syncwarp();
                 if (++as == p.a_stages) { as = 0; aph ^= 1; }
                 for (int r = 0; r < p.R; ++r) {
-                    if (!mbar_wait(b_empty + bs, bph ^ 1)) { *p.err = 22; return; }
+                    if (!mbar_wait(b_empty + bs, bph ^ 1)) { *p.err = 22; goto teardown; }
                     if (elect_one()) {
                         if (leader) mbar_arrive_expect_tx(b_full + bs, 2 * b_stage_bytes);
                         tma_load_3d_2sm(smem_b + bs * b_stage_bytes, &tmap_b, mapa_u32(smem_u32(b_full + bs), 0), cb * BK, nt * BN + (int)rank * (BN / 2), r * p.S);
@@ -597,14 +597,14 @@ tc_conv_halo2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
         constexpr uint32_t idesc = umma_idesc_bf16(256, BN, 0, 0);
         int as = 0; uint32_t aph = 0; int bs = 0; uint32_t bph = 0; int acc = 0; uint32_t acc_phase = 0;
         for (int pt = cluster_id; pt < n_ptiles; pt += n_clusters) {
-            if (!mbar_wait(tmem_empty + acc, acc_phase ^ 1)) { *p.err = 23; return; }
+            if (!mbar_wait(tmem_empty + acc, acc_phase ^ 1)) { *p.err = 23; goto teardown; }
             tc_fence_after();
             const uint32_t tmem_d = tmem_base + acc * BN;
             for (int cb = 0; cb < p.cblocks; ++cb) {
-                if (!mbar_wait(a_full + as, aph)) { *p.err = 24; return; }
+                if (!mbar_wait(a_full + as, aph)) { *p.err = 24; goto teardown; }
                 const uint32_t sa0 = smem_u32(smem_a + as * p.a_stage_bytes);
                 for (int r = 0; r < p.R; ++r) {
-                    if (!mbar_wait(b_full + bs, bph)) { *p.err = 25; return; }
+                    if (!mbar_wait(b_full + bs, bph)) { *p.err = 25; goto teardown; }
                     tc_fence_after();
                     const uint32_t sb0 = smem_u32(smem_b + bs * b_stage_bytes);
                     if (elect_one()) {
@@ -638,7 +638,7 @@ tc_conv_halo2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
             const int m = q * 32 + lane;
             const int h = th * 16 + (m >> 3), w = tw * 8 + (m & 7);
             const long long out_row = (!ghost && h < p.Hout && w < p.Wout) ? ((long long)n * p.Hout + h) * p.Wout + w : -1;
-            if (!mbar_wait(tmem_full + acc, acc_phase)) { if (lane == 0) *p.err = 26; break; }
+            if (!mbar_wait(tmem_full + acc, acc_phase)) { if (lane == 0) *p.err = 26; goto teardown; }
             tc_fence_after();
             epilogue_tile<BN>(p, tmem_base, acc, q, lane, out_row, nt);
             tc_fence_before();
@@ -647,6 +647,9 @@ tc_conv_halo2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
             if (++acc == 2) { acc = 0; acc_phase ^= 1; }
         }
     }
+teardown:
+    // every thread of both CTAs reaches this point, also after a timed-out wait (error word set): a thread that returned early would
+    // leave its peers blocked in the cluster barrier
     tc_fence_before();
     cluster_sync_all();
     tc_fence_after();
