@@ -6,6 +6,10 @@ torchrun-style environment (RANK, LOCAL_RANK, WORLD_SIZE, MASTER_ADDR=127.0.0.1,
 if any rank dies the rest of the process *group started here* is terminated (exact PIDs, never by pattern), so a
 failed rank cannot leave spinning peers behind — the failure detection the reference lacks.
 ``torch.distributed.run`` is an equally valid launcher; the scripts only read the environment.
+
+``--max-restarts R`` adds fail-stop recovery: when a rank dies the job is torn down and started again (new rendezvous port,
+``PSB200_RESTART_COUNT`` = attempt number, ``--restart-args`` appended — by default ``--resume``, so the PS reloads the newest
+``model_step_<N>`` + optimizer sidecar and the step counter continues from there), at most R times.
 """
 from __future__ import annotations
 
@@ -68,16 +72,34 @@ def launch(nprocs: int, cmd, master_port: int = 0, env_extra=None, timeout: floa
     return rc
 
 
+def launch_with_restarts(nprocs: int, cmd, restart_args, max_restarts: int, master_port: int = 0, timeout: float = 0.0, log_dir: str = "") -> int:
+    """Run ``cmd`` on ``nprocs`` ranks; on a failed attempt (not a timeout, not Ctrl-C) start over with ``restart_args`` appended."""
+    attempt = 0
+    while True:
+        rc = launch(nprocs, cmd + (list(restart_args) if attempt else []), 0 if attempt else master_port,
+                    env_extra={"PSB200_RESTART_COUNT": str(attempt)}, timeout=timeout, log_dir=log_dir)
+        if rc in (0, 124, 130) or attempt >= max_restarts:
+            return rc
+        attempt += 1
+        sys.stderr.write("[launch] attempt failed with %d; restart %d/%d with %s\n" % (rc, attempt, max_restarts, " ".join(restart_args) or "(no extra args)"))
+        time.sleep(1.0)
+
+
 def main():
     ap = argparse.ArgumentParser(description=__doc__, formatter_class=argparse.RawDescriptionHelpFormatter)
     ap.add_argument("-n", "--nprocs", type=int, required=True)
     ap.add_argument("--master-port", type=int, default=0)
     ap.add_argument("--timeout", type=float, default=0.0)
     ap.add_argument("--log-dir", type=str, default="")
+    ap.add_argument("--max-restarts", type=int, default=0, help="relaunch the whole job up to this many times when a rank dies")
+    ap.add_argument("--restart-args", type=str, default="--resume", help="arguments appended to the script on restarts")
     ap.add_argument("script")
     ap.add_argument("script_args", nargs=argparse.REMAINDER)
     a = ap.parse_args()
-    sys.exit(launch(a.nprocs, [sys.executable, a.script] + a.script_args, a.master_port, timeout=a.timeout, log_dir=a.log_dir))
+    cmd = [sys.executable, a.script] + a.script_args
+    if a.max_restarts > 0:
+        sys.exit(launch_with_restarts(a.nprocs, cmd, a.restart_args.split(), a.max_restarts, a.master_port, a.timeout, a.log_dir))
+    sys.exit(launch(a.nprocs, cmd, a.master_port, timeout=a.timeout, log_dir=a.log_dir))
 
 
 if __name__ == "__main__":

@@ -193,6 +193,7 @@ def run_distributed(args):
     layout = ParamLayout.from_module(proto, channels_last=(device.type == "cuda"))
     comm = make_transport(args, layout, device, world)
     stragglers = parse_stragglers(args.inject_straggler)
+    failures = {int(r): int(st) for r, st in (item.split(":") for item in filter(None, (getattr(args, "inject_failure", "") or "").split(",")))}
     common = dict(batch_size=args.batch_size, learning_rate=args.lr, max_epochs=args.epochs, momentum=args.momentum,
                   network=args.network, comm_method=args.comm_type, eval_freq=args.eval_freq, train_dir=args.train_dir,
                   max_steps=args.max_steps, compress_grad=args.compress_grad, device=device, mode=args.mode, dtype=args.dtype)
@@ -201,7 +202,7 @@ def run_distributed(args):
                          dampening=args.dampening, amsgrad=args.amsgrad, strict_reference=args.strict_reference,
                          worker_dtype=dtype, resume=args.resume)
     kwargs_worker = dict(common, kill_threshold=args.kill_threshold, overlap=args.overlap, num_buckets=args.num_buckets,
-                         cuda_graph=args.cuda_graph, straggle_ms=stragglers.get(rank, 0.0), log_interval=args.log_interval,
+                         cuda_graph=args.cuda_graph, straggle_ms=stragglers.get(rank, 0.0), fail_at_step=failures.get(rank, 0), log_interval=args.log_interval,
                          jsonl=(args.jsonl + ".rank%d" % rank) if args.jsonl else "")
     from .ps import SyncReplicasMaster_NN
     from .worker import DistributedWorker

@@ -8,6 +8,7 @@ rebuild), and "send grads" is one push per bucket that can overlap the remaining
 """
 from __future__ import annotations
 
+import os
 import time
 import torch
 
@@ -71,6 +72,7 @@ class DistributedWorker(object):
         self._num_buckets = kwargs.get('num_buckets', 4)
         self._use_graph = kwargs.get('cuda_graph', False) and self._mode == 'normal'
         self._straggle_ms = float(kwargs.get('straggle_ms', 0.0))
+        self._fail_at_step = int(kwargs.get('fail_at_step', 0))           # fault injection (--inject-failure), first attempt only
         self._log_interval = max(1, int(kwargs.get('log_interval', 1)))
         self._jsonl = JsonlSink(kwargs.get('jsonl') or None)
         self._is_ckpt_source = comm.worker_ranks[0] == comm.rank
@@ -153,6 +155,9 @@ class DistributedWorker(object):
         fetch_dur = time.time() - t0
         if self._straggle_ms > 0:
             time.sleep(self._straggle_ms * 1e-3)                          # fault injection (--inject-straggler)
+        if self._fail_at_step and self.cur_step == self._fail_at_step and os.environ.get("PSB200_RESTART_COUNT", "0") == "0":
+            logger.error("Worker %d: injected failure at step %d", self.rank, self.cur_step)
+            os._exit(17)
         if self._mode == 'timeout':
             self.compute.kill_deadline = time.time() + float(self.kill_threshold)
         killed = False

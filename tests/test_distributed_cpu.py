@@ -120,3 +120,20 @@ def test_resume_from_checkpoint_sidecar(tmp_path):
     assert "resumed from step 6" in r.stdout + r.stderr
     assert "Master node is entering step: 7" in r.stdout + r.stderr and "entering step: 6\n" not in r.stdout + r.stderr
     assert os.path.isfile(db + "model_step_9")
+
+
+def test_fail_stop_recovery_with_restarts(tmp_path):
+    """A worker dies at step 5 (fault injection); the supervising launcher tears the job down, restarts it with --resume, the PS reloads
+    model_step_3 + its optimizer sidecar and training continues to step 9 (the reference has neither failure detection nor resume)."""
+    d = str(tmp_path) + "/"
+    env = dict(os.environ, PYTHONPATH=ROOT, OMP_NUM_THREADS="2")
+    cmd = [sys.executable, "-m", "ps_pytorch_b200.launch", "-n", "3", "--timeout", "200", "--max-restarts", "2", os.path.join(ROOT, "src", "distributed_nn.py"),
+           "--network", "LeNet", "--dataset", "MNIST", "--batch-size", "16", "--max-steps", "9", "--eval-freq", "3", "--train-dir", d,
+           "--compress-grad", "None", "--inject-failure", "2:5", "--log-interval", "1", "--enable-gpu="]
+    r = subprocess.run(cmd, cwd=ROOT, env=env, capture_output=True, text=True, timeout=280)
+    out = r.stdout + r.stderr
+    assert r.returncode == 0, out[-3000:]
+    assert "injected failure at step 5" in out and "restart 1/2 with --resume" in out
+    assert "resumed from step 3" in out
+    assert os.path.isfile(d + "model_step_9")
+    assert "Worker: 1, Step: 9" in out
