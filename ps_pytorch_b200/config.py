@@ -85,6 +85,7 @@ def add_fit_args(parser: argparse.ArgumentParser, argv=None):
     parser.add_argument('--num-buckets', type=int, default=4, help='bucket count for --overlap')
     parser.add_argument('--cuda-graph', type=str2bool, default=True, nargs='?', const=True, help='capture the worker step in a CUDA graph')
     parser.add_argument('--inject-straggler', type=str, default='', help='rank:ms[,rank:ms] artificial delay per step (fault injection)')
+    parser.add_argument('--metrics-port', type=int, default=0, help='Prometheus endpoint: worker rank r serves http://0.0.0.0:<port+r>/metrics (0 = off)')
     parser.add_argument('--inject-failure', type=str, default='', help='rank:step — that worker exits with code 17 at that step on the first attempt (fault injection for --max-restarts)')
     parser.add_argument('--resume', type=str2bool, default=False, nargs='?', const=True, help='resume from the newest checkpoint + sidecar in --train-dir')
     parser.add_argument('--strict-reference', type=str2bool, default=False, nargs='?', const=True,

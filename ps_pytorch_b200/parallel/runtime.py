@@ -202,7 +202,7 @@ def run_distributed(args):
                          dampening=args.dampening, amsgrad=args.amsgrad, strict_reference=args.strict_reference,
                          worker_dtype=dtype, resume=args.resume)
     kwargs_worker = dict(common, kill_threshold=args.kill_threshold, overlap=args.overlap, num_buckets=args.num_buckets,
-                         cuda_graph=args.cuda_graph, straggle_ms=stragglers.get(rank, 0.0), fail_at_step=failures.get(rank, 0), log_interval=args.log_interval,
+                         cuda_graph=args.cuda_graph, straggle_ms=stragglers.get(rank, 0.0), fail_at_step=failures.get(rank, 0), metrics_port=getattr(args, "metrics_port", 0), log_interval=args.log_interval,
                          jsonl=(args.jsonl + ".rank%d" % rank) if args.jsonl else "")
     from .ps import SyncReplicasMaster_NN
     from .worker import DistributedWorker

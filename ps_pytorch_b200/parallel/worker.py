@@ -18,7 +18,7 @@ from ..models import build_model
 from ..models.layerwise import LayerwiseBackwardMixin, StragglerKilled
 from ..utils import checkpoint as ckpt
 from ..utils.metrics import accuracy  # noqa: F401  (the reference defines accuracy() in this module; kept importable from here)
-from ..utils.obs import JsonlSink, format_worker_line, logger
+from ..utils.obs import JsonlSink, MetricsExporter, format_worker_line, logger
 
 STEP_START_ = 1
 
@@ -75,6 +75,7 @@ class DistributedWorker(object):
         self._fail_at_step = int(kwargs.get('fail_at_step', 0))           # fault injection (--inject-failure), first attempt only
         self._log_interval = max(1, int(kwargs.get('log_interval', 1)))
         self._jsonl = JsonlSink(kwargs.get('jsonl') or None)
+        self._metrics = MetricsExporter(int(kwargs.get('metrics_port', 0) or 0), self.rank)
         self._is_ckpt_source = comm.worker_ranks[0] == comm.rank
         self.losses = []
         self.step_times = []
@@ -191,6 +192,7 @@ class DistributedWorker(object):
             logger.info(line)
             self._jsonl.write(rank=self.rank, step=self.cur_step, loss=loss_v, time=dur, fetch=fetch_dur,
                               forward=ph.get("forward", 0.0), backward=ph.get("backward", 0.0), comm=comm_dur, msg_mb=msg_mb)
+            self._metrics.update(self.cur_step, loss_v, dur, self.batch_size / max(dur, 1e-9), ph.get("forward", 0.0), ph.get("backward", 0.0), comm_dur, msg_mb)
         elif not log_now:
             self.compute.timer.discard()
         return self.cur_step < self._max_steps

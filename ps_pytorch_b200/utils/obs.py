@@ -86,6 +86,40 @@ class JsonlSink:
             self.f.close()
 
 
+class MetricsExporter:
+    """Prometheus endpoint (``--metrics-port P`` → rank r serves http://0.0.0.0:P+r/metrics): the fields of the worker log line as gauges, so a
+    long job can be scraped instead of grepped.  A no-op when the port is 0 or ``prometheus_client`` is missing."""
+
+    def __init__(self, port: int, rank: int):
+        self.on = False
+        if not port:
+            return
+        try:
+            from prometheus_client import CollectorRegistry, Counter, Gauge, start_http_server
+        except ImportError:
+            logger.warning("--metrics-port given but prometheus_client is not installed")
+            return
+        self.reg = CollectorRegistry()
+        lab = {"rank": str(rank)}
+        mk = lambda n, d: Gauge("psb200_" + n, d, list(lab), registry=self.reg).labels(**lab)
+        self.step = mk("step", "last finished training step")
+        self.loss = mk("loss", "loss of the last logged step")
+        self.step_s = mk("step_seconds", "wall time of the last logged step")
+        self.ips = mk("images_per_second", "per-worker throughput of the last logged step")
+        self.fwd = mk("forward_seconds", "device time of the forward pass")
+        self.bwd = mk("backward_seconds", "device time of the backward pass")
+        self.comm = mk("comm_seconds", "time in the gradient push")
+        self.msg = Counter("psb200_pushed_megabytes", "gradient payload pushed", list(lab), registry=self.reg).labels(**lab)
+        start_http_server(port + rank, registry=self.reg)
+        self.on = True
+
+    def update(self, step, loss, dur, ips, fwd, bwd, comm, msg_mb):
+        if not self.on:
+            return
+        self.step.set(step); self.loss.set(loss); self.step_s.set(dur); self.ips.set(ips)
+        self.fwd.set(fwd); self.bwd.set(bwd); self.comm.set(comm); self.msg.inc(max(0.0, msg_mb or 0.0))
+
+
 def format_worker_line(rank, step, epoch, seen, total, loss, t_iter, t_fetch, t_fwd, t_bwd, t_comm, msg_mb=None, ips=None):
     pct = 100.0 * seen / max(total, 1)
     s = WORKER_LOG_FORMAT.format(rank, step, epoch, seen, total, pct, loss, t_iter, t_fetch, t_fwd, t_bwd, t_comm)

@@ -117,3 +117,18 @@ def test_compression_facade_names():
             "assert c._trim_msg(b'abc'+bytes([0x29])*32+b'junk')==b'abc' and c._trim_msg(b'abc')==b'abc'; print('ok')")
     r = subprocess.run([sys.executable, "-c", code], cwd=os.path.join(root, "src"), capture_output=True, text=True, timeout=120)
     assert r.returncode == 0 and "ok" in r.stdout, r.stderr[-1500:]
+
+
+def test_prometheus_metrics_endpoint():
+    """--metrics-port: the worker log fields are scrapeable gauges (rank r on port+r)."""
+    import socket, urllib.request
+    from ps_pytorch_b200.utils.obs import MetricsExporter
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    m = MetricsExporter(port - 3, 3)
+    assert m.on
+    m.update(step=7, loss=0.25, dur=0.5, ips=2048.0, fwd=0.1, bwd=0.2, comm=0.05, msg_mb=1.5)
+    m.update(step=8, loss=0.20, dur=0.5, ips=2048.0, fwd=0.1, bwd=0.2, comm=0.05, msg_mb=1.5)
+    body = urllib.request.urlopen("http://127.0.0.1:%d/metrics" % port, timeout=10).read().decode()
+    assert 'psb200_step{rank="3"} 8.0' in body and 'psb200_loss{rank="3"} 0.2' in body
+    assert 'psb200_pushed_megabytes_total{rank="3"} 3.0' in body
+    assert not MetricsExporter(0, 0).on
