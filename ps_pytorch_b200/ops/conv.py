@@ -39,8 +39,11 @@ def unsupported_reason(x, weight, stride, padding, dilation, groups):
     if not hasattr(ext, "conv_fprop"):
         return "tcgen05 implicit-GEMM conv not built"
     global _pair_applied
-    if _HALO_PAIR and not _pair_applied:
-        ext.tc_set_halo_pair(1)
+    if not _pair_applied:
+        if _HALO_PAIR:
+            ext.tc_set_halo_pair(1)
+        if os.environ.get("PSB200_TC_CONV_ALGO", "") != "":            # -1 auto (per-tap), 0 per-tap, 1 halo where eligible
+            ext.tc_set_conv_algo(int(os.environ["PSB200_TC_CONV_ALGO"]))
         _pair_applied = True
     if isinstance(padding, str):
         return "string padding"

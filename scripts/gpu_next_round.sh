@@ -13,9 +13,9 @@ if [ "$N" = "1" ]; then
     env $([ "$mode" = wide ] && echo PSB200_BN_FINALIZE=wide) timeout 200 python bench.py --steps 40 --warmup 5 --skip-e2e 2>&1 | tail -1 > gpurun_out/next_round_bench_finalize_$mode.json
     python -c "import json; d=json.load(open('gpurun_out/next_round_bench_finalize_$mode.json')); print('$mode', d['ms_per_step'], 'ms/step', d['clocks'])"
   done
-  # all-tc convolutions with and without the CTA-pair halo kernel
+  # all-tc convolutions (halo kernel where eligible) with and without the CTA-pair variant; the per-tap-only number of round 1 was 9.13 ms
   for pair in 0 1; do
-    PSB200_TC_CONV=1 PSB200_TC_HALO_PAIR=$pair timeout 240 python bench.py --steps 30 --warmup 5 --skip-e2e 2>&1 | tail -1 > gpurun_out/next_round_bench_tcconv_pair$pair.json
+    PSB200_TC_CONV=1 PSB200_TC_CONV_ALGO=1 PSB200_TC_HALO_PAIR=$pair timeout 240 python bench.py --steps 30 --warmup 5 --skip-e2e 2>&1 | tail -1 > gpurun_out/next_round_bench_tcconv_pair$pair.json
     python -c "import json; d=json.load(open('gpurun_out/next_round_bench_tcconv_pair$pair.json')); print('tc conv, halo pair=$pair', d['ms_per_step'], 'ms/step')"
   done
 else
