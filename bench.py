@@ -109,6 +109,8 @@ class ClockSampler:
 def main():
     a = parse()
     if a.impl == "reference":
+        if int(os.environ.get("RANK", 0)) != 0:          # under torchrun every rank gets here: one line, from rank 0
+            return 0
         print(json.dumps({"impl": "reference", "unavailable": "hwang595/ps_pytorch has no setup.py/pyproject (pip: 'not installable'), and its "
                           "entry points import mpi4py + blosc (absent, no network) and need mpirun + dataset downloads; see DESIGN.md"}))
         return 0
