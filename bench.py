@@ -6,10 +6,11 @@ job, device-timed, max over ranks.
     python bench.py --gpus 1 --steps 30 --warmup 5
     python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29500 bench.py --gpus 8 ...
 
-``--impl reference`` is the reference arm (unmodified hwang595/ps_pytorch): it cannot be installed here — the tree has no
-setup.py/pyproject (pip: "not installable"), and it imports mpi4py + blosc which are absent — so that arm prints
-``{"impl": "reference", "unavailable": ...}``.  ``--impl nccl-baseline`` runs ``baseline/nccl_ps.py``: the reference
-algorithm re-expressed with NCCL reduce/broadcast + stock torch.nn (the operative baseline of BASELINE.md §2).
+``--impl reference`` is the reference arm: the UNMODIFIED hwang595/ps_pytorch tree (verbatim copy in the git-ignored
+``baseline/_ref``) run through its own entry point ``src/distributed_nn.py`` with the flags of ``src/run_pytorch.sh``
+(``baseline/ref_arm.py``; mpirun / mpi4py / blosc, none of which exist in this image, are replaced by the stand-ins in
+``baseline/refshim``).  ``--impl nccl-baseline`` runs ``baseline/nccl_ps.py``: the reference algorithm re-expressed with
+NCCL reduce/broadcast + stock torch.nn (the operative baseline of BASELINE.md §2).
 """
 from __future__ import annotations
 
@@ -109,10 +110,17 @@ class ClockSampler:
 def main():
     a = parse()
     if a.impl == "reference":
-        if int(os.environ.get("RANK", 0)) != 0:          # under torchrun every rank gets here: one line, from rank 0
+        if int(os.environ.get("RANK", 0)) != 0:          # under torchrun every rank gets here: rank 0 launches the whole reference job
             return 0
-        print(json.dumps({"impl": "reference", "unavailable": "hwang595/ps_pytorch has no setup.py/pyproject (pip: 'not installable'), and its "
-                          "entry points import mpi4py + blosc (absent, no network) and need mpirun + dataset downloads; see DESIGN.md"}))
+        sys.path.insert(0, os.path.join(ROOT, "baseline"))
+        import ref_arm
+        sampler = ClockSampler()
+        sampler.start()
+        out = ref_arm.run(a.gpus, a.steps, a.warmup, network=a.network, dataset=a.dataset, batch_size=a.batch_size)
+        clocks = sampler.stop(a.gpus)
+        if "unavailable" not in out:
+            out["clocks"] = clocks
+        print(json.dumps(out))
         return 0
     import torch
     import torch.distributed as dist
