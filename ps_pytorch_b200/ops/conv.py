@@ -1,9 +1,16 @@
-"""Convolutions on the tcgen05 implicit-GEMM kernels (``csrc/gemm_tcgen05.cu``).
+"""Convolutions on the hand-written tcgen05 implicit-GEMM kernels (``csrc/gemm_tcgen05.cu``, ``csrc/conv2_tcgen05.cu``).
 
-Forward (fprop: per-tap / halo / weight-stationary variants), the data gradient of stride-1 convolutions (the same kernels on
-flipped+transposed weights) and the weight gradient (MN-major operands, split-K with fp32 vector reductions) run on the
-hand-written kernels; only the data gradient of *strided* convolutions still goes through cuDNN
-(``torch.ops.aten.convolution_backward``), logged once per process by ``note_fallback``."""
+Routing (all three passes are ours; cuDNN is only reachable through ``PSB200_TC_CONV=0`` / ``set_tc_conv(False)``):
+
+===========================  =====================================================================================================
+forward                      3x3/stride-1 maps with W >= 8, H >= 16: CTA-pair *halo* kernel (input patch fetched once per channel block,
+                             taps are shifted smem windows); everything else (strided, 1x1, small maps): CTA-pair *tap-table* kernel
+data gradient, stride 1      the same two kernels on the transposed (+180-degree rotated for the halo form) filter
+data gradient, stride 2      tap-table kernel, one parity class of output pixels per tile group — no zero insertion
+weight gradient              split-K tcgen05 kernel with MN-major operands (fp32 vector reductions into a scratch)
+===========================  =====================================================================================================
+
+``PSB200_TC_CONV``: "1" (default) every supported convolution on our kernels; "0" the library path (A/B runs)."""
 from __future__ import annotations
 
 import os
@@ -13,13 +20,9 @@ import torch
 from . import count_launch, require
 from ..nn.backend import note_fallback
 
-# Measured on B200 (profiles/run4_conv_microbench.md) the per-tap tcgen05 kernel reaches 0.38-0.76 PFLOP/s where cuDNN's
-# sm100 kernels reach 0.75-1.34, so the *default* convolution path is the library one and the hand-written kernel is opt-in
-# (PSB200_TC_CONV=1 / set_tc_conv(True)) until it wins; every other layer of the sm100 backend is ours regardless.
-_MODE = os.environ.get("PSB200_TC_CONV", "0").lower()       # "0" library, "1" every supported conv, "auto" only where ours wins
+_MODE = os.environ.get("PSB200_TC_CONV", "1").lower()
 _ENABLED = _MODE != "0"
-_HALO_PAIR = os.environ.get("PSB200_TC_HALO_PAIR", "0") != "0"   # EXPERIMENTAL cta_group::2 halo kernel, not yet run on hardware
-_pair_applied = False
+_applied = False
 
 
 def set_tc_conv(on) -> None:
@@ -32,29 +35,39 @@ def tc_conv_enabled() -> bool:
     return _ENABLED
 
 
+def _apply_switches(ext):
+    global _applied
+    if _applied:
+        return
+    if os.environ.get("PSB200_TC_HALO_PAIR", "") != "":
+        ext.tc_set_halo_pair(int(os.environ["PSB200_TC_HALO_PAIR"]))
+    if os.environ.get("PSB200_TC_CONV_ALGO", "") != "":            # -1 auto (halo where eligible), 0 per-tap, 1 halo
+        ext.tc_set_conv_algo(int(os.environ["PSB200_TC_CONV_ALGO"]))
+    _applied = True
+
+
 def unsupported_reason(x, weight, stride, padding, dilation, groups):
     if not _ENABLED:
-        return "tcgen05 conv is opt-in (PSB200_TC_CONV=1); cuDNN is faster today"
+        return "tcgen05 conv disabled (PSB200_TC_CONV=0)"
     ext = require()
-    if not hasattr(ext, "conv_fprop"):
+    if not hasattr(ext, "conv2"):
         return "tcgen05 implicit-GEMM conv not built"
-    global _pair_applied
-    if not _pair_applied:
-        if _HALO_PAIR:
-            ext.tc_set_halo_pair(1)
-        if os.environ.get("PSB200_TC_CONV_ALGO", "") != "":            # -1 auto (per-tap), 0 per-tap, 1 halo where eligible
-            ext.tc_set_conv_algo(int(os.environ["PSB200_TC_CONV_ALGO"]))
-        _pair_applied = True
+    _apply_switches(ext)
     if isinstance(padding, str):
         return "string padding"
-    if _MODE == "auto":
-        # measured policy (profiles/run20_gemm.md): 1x1 stride-1 convolutions with >= 256 output channels are plain GEMMs on which the
-        # 256-column tcgen05 kernel matches or beats the library
-        if not (weight.size(2) == 1 and weight.size(3) == 1 and stride[0] == 1 and weight.size(0) % 256 == 0):
-            return "auto policy keeps this shape on cuDNN"
     r = ext.conv_unsupported_reason(list(x.shape), list(weight.shape), list(stride), list(padding), list(dilation), groups,
                                     x.dtype == torch.bfloat16 and weight.dtype == torch.bfloat16)
-    return r or None
+    if r:
+        return r
+    if weight.size(0) % 64:
+        return "Cout is not a multiple of 64"
+    if stride[0] not in (1, 2):
+        return "stride > 2"
+    if weight.size(2) * weight.size(3) > 9:
+        return "filter larger than 9 taps"
+    if stride[0] == 2 and (x.size(2) % 2 or x.size(3) % 2):
+        return "strided convolution of an odd-sized map"
+    return None
 
 
 _scratch = {}
@@ -74,13 +87,36 @@ def _krsc(w):
     return w if w.is_contiguous(memory_format=torch.channels_last) else w.contiguous(memory_format=torch.channels_last)
 
 
+def _halo_ok(h_out, w_out, r, s, stride):
+    return stride == 1 and r * s > 1 and s <= 8 and w_out >= 8 and h_out >= 16
+
+
+def fprop(ext, x, w, bias, stride, pad, relu, residual=None):
+    r, s = w.size(2), w.size(3)
+    ho, wo = (x.size(2) + 2 * pad - r) // stride + 1, (x.size(3) + 2 * pad - s) // stride + 1
+    count_launch()
+    if _halo_ok(ho, wo, r, s, stride):
+        return ext.conv_fprop(x, w, bias, stride, pad, relu, residual)
+    return ext.conv2(x, w, bias, stride, pad, relu, residual, False, 0, 0)
+
+
+def dgrad(ext, dy, weight, in_h, in_w, stride, pad, residual=None):
+    """dX of conv(x, weight, stride, pad) from dY; ``residual`` (shape of dX) is added in the kernel epilogue."""
+    r, s = weight.size(2), weight.size(3)
+    w = _krsc(weight)
+    count_launch(2)
+    if stride == 1 and _halo_ok(in_h, in_w, r, s, 1) and r == s and in_h == dy.size(2) + r - 1 - 2 * pad:
+        # dX = conv(dY, rot180(W)^T, pad = R-1-pad): the halo kernel on the transformed filter
+        return ext.conv_fprop(dy, ext.weight_transpose(w, True), None, 1, r - 1 - pad, False, residual)
+    return ext.conv2(dy, ext.weight_transpose(w, False), None, stride, pad, False, residual, True, in_h, in_w)
+
+
 class _ConvFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, weight, bias, stride, pad, relu):
         ext = require()
         x = x.contiguous(memory_format=torch.channels_last)
-        y = ext.conv_fprop(x, _krsc(weight), bias, stride, pad, relu)
-        count_launch()
+        y = fprop(ext, x, _krsc(weight), bias, stride, pad, relu)
         ctx.save_for_backward(x, weight, y if relu else None)
         ctx.stride, ctx.pad, ctx.has_bias, ctx.relu = stride, pad, bias is not None, relu
         return y
@@ -97,24 +133,15 @@ class _ConvFn(torch.autograd.Function):
         r = weight.size(2)
         dx = dw = db = None
         need_dx, need_dw = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
-        if need_dx and s == 1 and weight.size(0) % 64 == 0 and weight.size(1) % 8 == 0:
-            # dX = conv(dY, flip(W)^T, pad = R-1-pad): the same implicit-GEMM kernel on transformed weights
-            wt = weight.flip(2, 3).permute(1, 0, 2, 3).contiguous(memory_format=torch.channels_last)
-            dx = ext.conv_fprop(dy, wt, None, 1, r - 1 - p, False)
-            count_launch()
-            need_dx = False
-        if need_dw and weight.size(0) % 64 == 0 and weight.size(1) % 64 == 0:
+        if need_dx:
+            dx = dgrad(ext, dy, weight, x.size(2), x.size(3), s, p)
+        if need_dw and weight.size(1) % 64 == 0:
             dw = ext.conv_wgrad(dy, x, _wgrad_scratch(weight), r, weight.size(3), s, p)
             count_launch(2)
             need_dw = False
-        if need_dx or need_dw:
-            note_fallback("conv2d.backward", "strided data gradient uses cuDNN")
-            gi, gw, _ = torch.ops.aten.convolution_backward(dy, x, weight, None, (s, s), (p, p), (1, 1), False, (0, 0), 1,
-                                                            (need_dx, need_dw, False))
-            if need_dx:
-                dx = gi
-            if need_dw:
-                dw = gw
+        if need_dw:
+            note_fallback("conv2d.backward", "weight gradient with Cin % 64 != 0 uses cuDNN")
+            _gi, dw, _ = torch.ops.aten.convolution_backward(dy, x, weight, None, (s, s), (p, p), (1, 1), False, (0, 0), 1, (False, True, False))
         if ctx.has_bias and ctx.needs_input_grad[2]:
             db = dy.float().sum((0, 2, 3)).to(dy.dtype)
         return dx, dw, db, None, None, None

@@ -317,7 +317,7 @@ __global__ void __launch_bounds__(256) bn_bwd_finalize_kernel(const float* __res
     }
 }
 
-// ---- wide finalize (opt-in: bn_set_finalize_wide(1) / PSB200_BN_FINALIZE=wide) -------------------------------------------
+// ---- wide finalize (default; bn_set_finalize_wide(0) / PSB200_BN_FINALIZE=narrow selects the old kernels) -------------------------------------------
 // profiles/run23_launch_list_final.md: the finalize kernels above cost 26-35 us each under ncu (40 launches per ResNet-18 step) because 2-16 CTAs
 // walk ~74 partial rows per thread in dependent batches.  Here one CTA owns 8 channels (one 32-byte sector of a partial row): thread
 // (g = tid / 8, cc = tid % 8) sums rows g, g+32, g+64, ... with eight predicated loads in flight per batch (3 batches for 592 rows),
@@ -395,7 +395,7 @@ __global__ void __launch_bounds__(256) bn_bwd_finalize_wide_kernel(const float* 
     }
 }
 
-static int g_bn_finalize_wide = 0;
+static int g_bn_finalize_wide = 1;      // default since round 2 (validated on B200: 6.96 vs 7.23 ms/step, profiles/run24_*.md)
 void bn_set_finalize_wide(int on) { g_bn_finalize_wide = on ? 1 : 0; }
 
 template <bool RELU, bool RES, bool MASKX>

@@ -6,6 +6,9 @@
 namespace psb {
 const char* tc_gemm_tn(const void*, const void*, void*, const void*, int, int, int, int, cudaStream_t);
 const char* tc_conv_fprop(const void*, const void*, void*, const void*, const void*, int, int, int, int, int, int, int, int, int, int, cudaStream_t);
+const char* tc_conv2(const void*, const void*, void*, const void*, const void*, int, int, int, int, int, int, int, int, int, int, int, int, int, cudaStream_t);
+const char* weight_transpose(const void*, void*, int, int, int, int, cudaStream_t);
+void tc_set_conv2_bn(int);
 void tc_set_conv_algo(int);
 void tc_set_halo_desc_mode(int);
 void tc_set_halo_cluster(int);
@@ -56,6 +59,44 @@ at::Tensor conv_fprop(at::Tensor x, at::Tensor w, c10::optional<at::Tensor> bias
     return y;
 }
 
+// CTA-pair tap-table kernel (conv2_tcgen05.cu).
+//   dgrad = false: a = x [NB,Cin,H,W] NHWC, w = the parameter [Cout,Cin,R,S] channels_last; returns y.
+//   dgrad = true:  a = dy [NB,Cout,Ho,Wo] NHWC, w = the TRANSPOSED parameter (weight_transpose: logically [Cin,Cout,R,S] channels_last, physically
+//                  [Cin][R][S][Cout]); in_h/in_w = spatial size of the forward input; returns dx [NB,Cin,in_h,in_w].  residual (same shape as the
+//                  result) is added in the epilogue.
+at::Tensor conv2(at::Tensor a, at::Tensor w, c10::optional<at::Tensor> bias, int64_t stride, int64_t pad, bool relu, c10::optional<at::Tensor> residual,
+                 bool dgrad, int64_t in_h, int64_t in_w) {
+    TORCH_CHECK(a.is_cuda() && a.scalar_type() == at::kBFloat16 && w.scalar_type() == at::kBFloat16 && a.dim() == 4 && w.dim() == 4);
+    TORCH_CHECK(a.is_contiguous(at::MemoryFormat::ChannelsLast), "activations must be NHWC");
+    TORCH_CHECK(w.is_contiguous(at::MemoryFormat::ChannelsLast), "weights must be [N][R][S][K]");
+    const int NB = a.size(0), Cred = a.size(1), Ha = a.size(2), Wa = a.size(3), N = w.size(0), R = w.size(2), S = w.size(3);
+    TORCH_CHECK(w.size(1) == Cred, "weight reduction dimension does not match the activations");
+    int Ho, Wo;
+    if (dgrad) { Ho = (int)in_h; Wo = (int)in_w; }
+    else { Ho = (Ha + 2 * pad - R) / stride + 1; Wo = (Wa + 2 * pad - S) / stride + 1; }
+    at::Tensor y = at::empty({NB, N, Ho, Wo}, a.options().memory_format(at::MemoryFormat::ChannelsLast));
+    const void* rp = nullptr;
+    if (residual.has_value()) {
+        TORCH_CHECK(residual->scalar_type() == at::kBFloat16 && residual->sizes() == y.sizes() && residual->is_contiguous(at::MemoryFormat::ChannelsLast),
+                    "residual must be an NHWC bf16 tensor of the output shape");
+        rp = residual->data_ptr();
+    }
+    const char* e = tc_conv2(a.data_ptr(), w.data_ptr(), y.data_ptr(), opt_ptr(bias, N), rp, NB, Ha, Wa, Cred, N, R, S, (int)stride, (int)pad, dgrad ? 1 : 0, Ho, Wo,
+                             relu, at::cuda::getCurrentCUDAStream());
+    TORCH_CHECK(e == nullptr, "tc_conv2: ", e);
+    return y;
+}
+
+// parameter [Cout,Cin,R,S] channels_last -> logically [Cin,Cout,R,S] channels_last (physically [Cin][R][S][Cout]); flip rotates the taps by 180 degrees
+at::Tensor weight_transpose_t(at::Tensor w, bool flip) {
+    TORCH_CHECK(w.is_cuda() && w.scalar_type() == at::kBFloat16 && w.dim() == 4 && w.is_contiguous(at::MemoryFormat::ChannelsLast));
+    const int Cout = w.size(0), Cin = w.size(1), R = w.size(2), S = w.size(3);
+    at::Tensor out = at::empty({Cin, Cout, R, S}, w.options().memory_format(at::MemoryFormat::ChannelsLast));
+    const char* e = weight_transpose(w.data_ptr(), out.data_ptr(), Cout, R * S, Cin, flip ? 1 : 0, at::cuda::getCurrentCUDAStream());
+    TORCH_CHECK(e == nullptr, e);
+    return out;
+}
+
 // dW [Cout,Cin,R,S] channels_last (physically [Cout][R][S][Cin]) from dy (NHWC) and x (NHWC).  `scratch` is a persistent fp32 buffer of
 // Cout*R*S*Cin floats that must be zero on entry and is left zeroed.
 at::Tensor conv_wgrad(at::Tensor dy, at::Tensor x, at::Tensor scratch, int64_t R, int64_t S, int64_t stride, int64_t pad) {
@@ -100,6 +141,10 @@ void bind_gemm(pybind11::module_& m) {
     m.def("gemm_tn", &psb::gemm_tn);
     m.def("conv_fprop", &psb::conv_fprop, pybind11::arg("x"), pybind11::arg("w"), pybind11::arg("bias"), pybind11::arg("stride"), pybind11::arg("pad"),
           pybind11::arg("relu"), pybind11::arg("residual") = c10::optional<at::Tensor>());
+    m.def("conv2", &psb::conv2, pybind11::arg("a"), pybind11::arg("w"), pybind11::arg("bias"), pybind11::arg("stride"), pybind11::arg("pad"), pybind11::arg("relu"),
+          pybind11::arg("residual") = c10::optional<at::Tensor>(), pybind11::arg("dgrad") = false, pybind11::arg("in_h") = 0, pybind11::arg("in_w") = 0);
+    m.def("weight_transpose", &psb::weight_transpose_t);
+    m.def("tc_set_conv2_bn", &psb::tc_set_conv2_bn);
     m.def("tc_set_conv_algo", &psb::tc_set_conv_algo);
     m.def("tc_set_halo_desc_mode", &psb::tc_set_halo_desc_mode);
     m.def("tc_set_halo_cluster", &psb::tc_set_halo_cluster);

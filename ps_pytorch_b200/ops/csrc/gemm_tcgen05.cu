@@ -23,33 +23,9 @@
 #include <stdint.h>
 #include <stdio.h>
 #include <mutex>
-#include "tc_ptx.cuh"
+#include "tc_common.cuh"
 
 namespace psb {
-
-using namespace tc;
-
-constexpr int BM = 128;
-constexpr int BK = 64;                 // 64 bf16 = one 128-byte swizzle row
-constexpr int kThreads = 256;
-constexpr int kEpiWarp0 = 4;
-
-struct TcParams {
-    int M, N, num_kb;
-    int mode;                          // 0 GEMM, 1 implicit-GEMM conv
-    int n_tiles_m, n_tiles_n;
-    // conv geometry
-    int Hout, Wout, NB, stride, pad, S, cblocks;
-    int BW, BH, BNI, tiles_w, tiles_h;
-    const __nv_bfloat16* bias;
-    const __nv_bfloat16* residual;      // optional [M,N] tensor added in the epilogue (dgrad + skip-gradient fusion)
-    int relu;
-    int R, halo_w, a_stage_bytes;       // halo kernel: filter rows, halo box width, bytes per A stage
-    int b_resident, a_stages;           // weight-stationary mode: all R filter rows of B stay in smem for the whole kernel
-    int desc_mode;
-    __nv_bfloat16* C;
-    int* err;                          // set to 1 if a barrier wait timed out (protocol bug), never hang
-};
 
 template <int BN> struct TcCfg {
     static constexpr int kStages = BN == 64 ? 8 : (BN == 128 ? 6 : 4);
@@ -59,74 +35,6 @@ template <int BN> struct TcCfg {
     static constexpr int kTmemCols = 2 * BN;                      // two accumulator stages (power of two: 128 / 256)
     static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
 };
-
-// TMEM accumulator quarter -> (+bias) (+residual) (ReLU) -> bf16 -> global.  Thread `lane` of warp quarter q owns one output row.
-template <int BN>
-__device__ __forceinline__ void epilogue_tile(const TcParams& p, uint32_t tmem_base, int acc, int q, int lane, long long out_row, int nt) {
-    const bool vec_ok = (p.N % 8) == 0;
-    __nv_bfloat16* crow = p.C + out_row * (long long)p.N + (long long)nt * BN;
-    const __nv_bfloat16* rrow = p.residual ? p.residual + out_row * (long long)p.N + (long long)nt * BN : nullptr;
-#pragma unroll 1
-    for (int c0 = 0; c0 < BN; c0 += 32) {
-        uint32_t v[32];
-        tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + c0), v);
-        tmem_ld_wait();
-        const int col0 = nt * BN + c0;
-        if (out_row >= 0 && col0 < p.N) {
-            float f[32];
-#pragma unroll
-            for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
-            if (p.bias) {
-#pragma unroll
-                for (int j = 0; j < 32; ++j) if (col0 + j < p.N) f[j] += __bfloat162float(p.bias[col0 + j]);
-            }
-            const bool full = vec_ok && col0 + 32 <= p.N;
-            if (rrow) {
-                if (full) {
-#pragma unroll
-                    for (int j = 0; j < 32; j += 8) {
-                        const uint4 rv = *reinterpret_cast<const uint4*>(rrow + c0 + j);
-                        const uint32_t w[4] = {rv.x, rv.y, rv.z, rv.w};
-#pragma unroll
-                        for (int k = 0; k < 4; ++k) { f[j + 2 * k] += __uint_as_float(w[k] << 16); f[j + 2 * k + 1] += __uint_as_float(w[k] & 0xffff0000u); }
-                    }
-                } else {
-                    for (int j = 0; j < 32; ++j) if (col0 + j < p.N) f[j] += __bfloat162float(rrow[c0 + j]);
-                }
-            }
-            if (p.relu) {
-#pragma unroll
-                for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.f);
-            }
-            if (full && (p.N % 16) == 0) {
-                // 256-bit stores (STG.E.ENL2.256): every thread writes whole 32-byte sectors of its output row
-#pragma unroll
-                for (int j = 0; j < 32; j += 16) {
-                    uint32_t o[8];
-#pragma unroll
-                    for (int k = 0; k < 8; ++k) {
-                        __nv_bfloat162 h = __floats2bfloat162_rn(f[j + 2 * k], f[j + 2 * k + 1]);
-                        o[k] = *reinterpret_cast<uint32_t*>(&h);
-                    }
-                    asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(crow + c0 + j), "r"(o[0]), "r"(o[1]), "r"(o[2]), "r"(o[3]),
-                                 "r"(o[4]), "r"(o[5]), "r"(o[6]), "r"(o[7]) : "memory");
-                }
-            } else if (full) {
-#pragma unroll
-                for (int j = 0; j < 32; j += 8) {
-                    uint4 o;
-                    __nv_bfloat162 h0 = __floats2bfloat162_rn(f[j], f[j + 1]), h1 = __floats2bfloat162_rn(f[j + 2], f[j + 3]);
-                    __nv_bfloat162 h2 = __floats2bfloat162_rn(f[j + 4], f[j + 5]), h3 = __floats2bfloat162_rn(f[j + 6], f[j + 7]);
-                    o.x = *reinterpret_cast<uint32_t*>(&h0); o.y = *reinterpret_cast<uint32_t*>(&h1);
-                    o.z = *reinterpret_cast<uint32_t*>(&h2); o.w = *reinterpret_cast<uint32_t*>(&h3);
-                    *reinterpret_cast<uint4*>(crow + c0 + j) = o;
-                }
-            } else {
-                for (int j = 0; j < 32; ++j) if (col0 + j < p.N) crow[c0 + j] = __float2bfloat16_rn(f[j]);
-            }
-        }
-    }
-}
 
 template <int BN>
 __global__ void __launch_bounds__(kThreads, 1)
@@ -522,8 +430,7 @@ tc_conv_halo_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
 }
 
 // ===================================================================================================================
-// CTA-pair halo convolution (EXPERIMENTAL: written after this round's GPU budget was spent; compiled, not yet run on hardware;
-// enabled only by tc_set_halo_pair(1) / PSB200_TC_HALO_PAIR=1).
+// CTA-pair halo convolution (default for halo-eligible shapes since it was validated on hardware in round 2).
 //
 // Same tile geometry and shifted-window A descriptors as tc_conv_halo_kernel, with the pair mechanics proven by tc_gemm2_kernel:
 // the two CTAs of a cluster take neighbouring M tiles (2 x 128 output pixels) of the same N tile; each loads its own halo patch
@@ -835,7 +742,7 @@ static EncodeTiledFn get_encode() {
 }
 
 // rank-`rank` bf16 tensor map with 128-byte swizzle; dims/strides innermost first (strides in BYTES, for dims 1..rank-1)
-static const char* make_tmap(CUtensorMap* m, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+const char* make_tmap(CUtensorMap* m, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
                              const uint32_t* box, const uint32_t* estrides) {
     EncodeTiledFn enc = get_encode();
     if (!enc) return "cuTensorMapEncodeTiled unavailable";
@@ -846,7 +753,7 @@ static const char* make_tmap(CUtensorMap* m, const void* base, int rank, const u
     return nullptr;
 }
 
-static int* err_word() {                // one device word shared by all launches; checked by tc_check_error()
+int* err_word() {                // one device word shared by all launches; checked by tc_check_error()
     static int* p = nullptr;
     if (!p) { cudaMalloc(&p, sizeof(int)); cudaMemset(p, 0, sizeof(int)); }
     return p;
@@ -858,7 +765,7 @@ int tc_check_error() {
     return h;
 }
 
-static int num_sms() {
+int num_sms() {
     static int n = 0;
     if (!n) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev); }
     return n;
@@ -906,7 +813,7 @@ static const char* launch_halo(const CUtensorMap& ta, const CUtensorMap& tb, con
     return cudaLaunchKernelEx(&cfg, tc_conv_halo_kernel<BN, CL>, ta, tb, p) == cudaSuccess ? nullptr : "kernel launch failed";
 }
 
-static int g_halo_pair = 0;           // EXPERIMENTAL CTA-pair halo kernel (not yet run on hardware): off unless requested
+static int g_halo_pair = 1;           // CTA-pair halo kernel (validated on B200 in round 2); tc_set_halo_pair(0) selects the 1-CTA variants
 void tc_set_halo_pair(int v) { g_halo_pair = v ? 1 : 0; }
 
 template <int BN>
@@ -931,7 +838,7 @@ static const char* launch_halo_pair(const CUtensorMap& ta, const CUtensorMap& tb
     return cudaLaunchKernelEx(&cfg, tc_conv_halo2_kernel<BN>, ta, tb, p) == cudaSuccess ? nullptr : "kernel launch failed";
 }
 
-static int g_conv_algo = -1;     // -1 auto (= per-tap until the halo variant is validated on hardware), 0 per-tap, 1 halo
+static int g_conv_algo = -1;     // -1 auto (= halo where eligible), 0 per-tap, 1 halo
 void tc_set_halo_desc_mode(int) {}   // kept for scripts/conv_one.py; the base_offset experiment is settled (always 0)
 void tc_set_conv_algo(int a) { g_conv_algo = a; }
 
@@ -986,7 +893,7 @@ const char* tc_conv_fprop(const void* X, const void* Wt, void* Y, const void* bi
     if (Cout % 8) return "Cout must be a multiple of 8";
     const int Hout = (Hin + 2 * pad - R) / stride + 1, Wout = (Win + 2 * pad - S) / stride + 1;
     const bool halo_ok = stride == 1 && R * S > 1 && S <= 8 && Wout >= 8 && Hout >= 16 && (16 + R - 1) <= 256;
-    if (g_conv_algo == 1 && halo_ok) {
+    if (g_conv_algo != 0 && halo_ok) {
         const int BN = Cout <= 64 ? 64 : 128;
         const bool pair = g_halo_pair && Cout % BN == 0;        // each CTA of the pair loads BN/2 weight rows per tap
         CUtensorMap ta, tb;

@@ -14,16 +14,16 @@ from . import count_launch, require
 # wgrad and the 16 extra registers cost occupancy.  Off by default.
 _MASKX = os.environ.get("PSB200_BN_MASKX", "0") != "0"
 _DETERMINISTIC = os.environ.get("PSB200_BN_FUSED_FINALIZE", "0") == "0"
-# "wide": one CTA per 8 channels in the two finalize kernels (profiles/run23_launch_list_final.md).  Written after this round's GPU budget was
-# spent: compiled and covered by an opt-in test, off by default until it has been run on hardware.
-_FINALIZE_WIDE = os.environ.get("PSB200_BN_FINALIZE", "") == "wide"
+# "wide" finalize kernels (one CTA per 8 channels, all partial loads of a thread in flight at once) are the default since they were
+# validated on hardware (6.96 vs 7.23 ms/step, profiles/run24_gated_kernels.md); PSB200_BN_FINALIZE=narrow selects the old ones.
+_FINALIZE_NARROW = os.environ.get("PSB200_BN_FINALIZE", "") == "narrow"
 _wide_applied = False
 
 
 def _apply_switches(ext):
     global _wide_applied
-    if _FINALIZE_WIDE and not _wide_applied:
-        ext.bn_set_finalize_wide(1)
+    if _FINALIZE_NARROW and not _wide_applied:
+        ext.bn_set_finalize_wide(0)
         _wide_applied = True
 
 

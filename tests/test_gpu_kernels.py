@@ -306,12 +306,14 @@ def test_tc_conv_fprop(ext, shape, algo):
     NB, Cin, H, W, Cout, R, st, pad = shape
     ext.tc_set_conv_algo(min(algo, 1))            # 2 = halo with the 2-CTA weight-multicast cluster
     ext.tc_set_halo_cluster(2 if algo == 2 else 1)
+    ext.tc_set_halo_pair(0)                       # the 1-CTA variants; the CTA-pair form has its own test below
     torch.manual_seed(0)
     x = (torch.randn(NB, Cin, H, W, device="cuda") * 0.5).to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
     w = (torch.randn(Cout, Cin, R, R, device="cuda") * (1.0 / math.sqrt(Cin * R * R))).to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
     y = ext.conv_fprop(x, w, None, st, pad, False)
     torch.cuda.synchronize()
     ext.tc_set_conv_algo(-1)
+    ext.tc_set_halo_pair(1)
     assert ext.tc_error() == 0
     ref = F.conv2d(x.float(), w.float(), None, st, pad)
     assert y.shape == ref.shape
@@ -335,7 +337,6 @@ def test_tc_conv_autograd_matches_cudnn(ext):
     yr = F.conv2d(xr, wr, None, 1, 1); yr.backward(g.float())
     assert (y.float() - yr).abs().max().item() < 0.05
     assert (x.grad.float() - xr.grad).abs().max().item() < 0.05 * max(1.0, xr.grad.abs().max().item())
-    C.set_tc_conv(False)
     assert (conv.weight.grad.float() - wr.grad).abs().max().item() < 0.03 * max(1.0, wr.grad.abs().max().item())
 
 
@@ -437,10 +438,9 @@ def test_tc_gemm_cta_pair(ext, shape):
     assert (y - ref).abs().max().item() <= 0.02 * max(1.0, ref.abs().max().item())
 
 
-@pytest.mark.skipif(os.environ.get("PSB200_EXPERIMENTAL") != "1", reason="wide BN finalize has not run on hardware yet (written after the round's GPU budget was spent)")
 @pytest.mark.parametrize("C,HW", [(64, 32), (128, 16), (512, 4), (8, 8)])
 def test_bn_finalize_wide_matches_default(ext, C, HW):
-    """Opt-in wide finalize kernels (one CTA per 8 channels) must reproduce the default two-stage path: forward output, statistics, and all gradients."""
+    """Wide finalize kernels (default since round 2) (one CTA per 8 channels) must reproduce the default two-stage path: forward output, statistics, and all gradients."""
     torch.manual_seed(0)
     x = torch.randn(64, C, HW, HW, device="cuda").to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
     dz = torch.randn_like(x)
@@ -455,17 +455,16 @@ def test_bn_finalize_wide_matches_default(ext, C, HW):
             dx, dres, dg, db = ext.bn_backward(dz, z, x, w, mean, invstd, True, False, None, None, None)[:4]
             torch.cuda.synchronize()
         finally:
-            ext.bn_set_finalize_wide(0)
+            ext.bn_set_finalize_wide(1)
         outs.append([t.float() for t in (z, mean, invstd, rm, rv, dx, dg, db)])
     for a, c in zip(*outs):
         assert (a - c).abs().max().item() <= 2e-2 * max(1.0, a.abs().max().item())
 
 
-@pytest.mark.skipif(os.environ.get("PSB200_EXPERIMENTAL") != "1", reason="CTA-pair halo conv has not run on hardware yet (written after the round's GPU budget was spent)")
 @pytest.mark.parametrize("shape", [(8, 64, 32, 32, 64, 3, 1, 1), (4, 64, 16, 16, 128, 3, 1, 1), (2, 64, 56, 56, 64, 3, 1, 1), (3, 128, 24, 16, 256, 3, 1, 1),
                                    (1, 64, 16, 8, 64, 3, 1, 1)])
 def test_tc_conv_halo_cta_pair(ext, shape):
-    """EXPERIMENTAL tc_conv_halo2_kernel (cta_group::2): same contract as test_tc_conv_fprop; the last shape has an odd number of M tiles (ghost half)."""
+    """tc_conv_halo2_kernel (cta_group::2): same contract as test_tc_conv_fprop; the last shape has an odd number of M tiles (ghost half)."""
     NB, Cin, H, W, Cout, R, st, pad = shape
     ext.tc_set_conv_algo(1)
     ext.tc_set_halo_pair(1)
@@ -476,8 +475,90 @@ def test_tc_conv_halo_cta_pair(ext, shape):
         y = ext.conv_fprop(x, w, None, st, pad, False)
         torch.cuda.synchronize()
     finally:
-        ext.tc_set_halo_pair(0)
         ext.tc_set_conv_algo(-1)
     assert ext.tc_error() == 0
     ref = F.conv2d(x.float(), w.float(), None, st, pad)
     assert (y.float() - ref).abs().max().item() <= 0.02 * max(1.0, ref.abs().max().item())
+
+
+# ---------------------------------------------------------------------------------------------------- CTA-pair tap-table kernel (conv2_tcgen05.cu)
+_CONV2_SHAPES = [  # NB, Cin, H, W, Cout, R, stride, pad
+    (8, 64, 32, 32, 64, 3, 1, 1), (8, 64, 32, 32, 128, 3, 2, 1), (8, 64, 32, 32, 128, 1, 2, 0), (16, 128, 16, 16, 256, 3, 2, 1),
+    (32, 256, 8, 8, 256, 3, 1, 1), (32, 256, 8, 8, 512, 3, 2, 1), (64, 512, 4, 4, 512, 3, 1, 1), (5, 128, 16, 16, 256, 1, 1, 0),
+    (3, 64, 8, 8, 64, 3, 1, 1), (2, 64, 14, 14, 64, 3, 1, 1), (7, 256, 8, 8, 512, 1, 2, 0)]
+
+
+@pytest.mark.parametrize("shape", _CONV2_SHAPES)
+@pytest.mark.parametrize("bn", [-1, 64])
+def test_tc_conv2_fprop(ext, shape, bn):
+    """tc_conv2_kernel forward (cta_group::2, 256-pixel x BN tiles) against an fp32 convolution; bn=64 forces the narrow N tile
+    (several N tiles per M tile); the odd-count shapes exercise the ghost half of the last pair."""
+    NB, Cin, H, W, Cout, R, st, pad = shape
+    torch.manual_seed(0)
+    x = (torch.randn(NB, Cin, H, W, device="cuda") * 0.5).to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
+    w = (torch.randn(Cout, Cin, R, R, device="cuda") * (1.0 / math.sqrt(Cin * R * R))).to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
+    ext.tc_set_conv2_bn(bn)
+    try:
+        y = ext.conv2(x, w, None, st, pad, False)
+        torch.cuda.synchronize()
+    finally:
+        ext.tc_set_conv2_bn(-1)
+    assert ext.tc_error() == 0
+    ref = F.conv2d(x.float(), w.float(), None, st, pad)
+    assert y.shape == ref.shape
+    err = (y.float() - ref).abs().max().item()
+    assert err <= 0.02 * max(1.0, ref.abs().max().item()), (shape, err)
+
+
+@pytest.mark.parametrize("shape", _CONV2_SHAPES)
+@pytest.mark.parametrize("res", [False, True])
+def test_tc_conv2_dgrad(ext, shape, res):
+    """Data gradient through the tap-table kernel: stride 1 (one class, all taps) and stride 2 (four parity classes, incl. the
+    1x1/s2 case where three classes have no taps and must come out as zeros / as the residual)."""
+    NB, Cin, H, W, Cout, R, st, pad = shape
+    torch.manual_seed(1)
+    Ho = (H + 2 * pad - R) // st + 1
+    w = (torch.randn(Cout, Cin, R, R, device="cuda") * (1.0 / math.sqrt(Cin * R * R))).to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
+    dy = (torch.randn(NB, Cout, Ho, Ho if H == W else (W + 2 * pad - R) // st + 1, device="cuda") * 0.5).to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
+    r = (torch.randn(NB, Cin, H, W, device="cuda")).to(torch.bfloat16).contiguous(memory_format=torch.channels_last) if res else None
+    wt = ext.weight_transpose(w, False)
+    assert torch.equal(wt, w.permute(1, 0, 2, 3).contiguous(memory_format=torch.channels_last))
+    dx = ext.conv2(dy, wt, None, st, pad, False, r, True, H, W)
+    torch.cuda.synchronize()
+    assert ext.tc_error() == 0
+    ref = torch.nn.grad.conv2d_input((NB, Cin, H, W), w.float(), dy.float(), st, pad)
+    if res:
+        ref = ref + r.float()
+    err = (dx.float() - ref).abs().max().item()
+    assert err <= 0.02 * max(1.0, ref.abs().max().item()), (shape, err)
+
+
+def test_weight_transpose_flip(ext):
+    w = torch.randn(128, 64, 3, 3, device="cuda").to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
+    ref = w.flip(2, 3).permute(1, 0, 2, 3).contiguous(memory_format=torch.channels_last)
+    assert torch.equal(ext.weight_transpose(w, True), ref)
+
+
+@pytest.mark.parametrize("cfg", [(64, 64, 32, 1), (64, 128, 32, 2), (128, 128, 16, 1), (256, 512, 8, 2), (512, 512, 4, 1)])
+def test_conv_autograd_all_passes_ours(ext, cfg):
+    """nn.Conv2d forward + both gradients on our kernels only (no library fallback may be logged), vs fp32 autograd."""
+    from ps_pytorch_b200 import nn as pnn
+    from ps_pytorch_b200.nn import backend as B
+    Cin, Cout, HW, st = cfg
+    torch.manual_seed(0)
+    conv = pnn.Conv2d(Cin, Cout, 3, st, 1, bias=False).cuda().to(torch.bfloat16).to(memory_format=torch.channels_last)
+    x = torch.randn(16, Cin, HW, HW, device="cuda").to(torch.bfloat16).contiguous(memory_format=torch.channels_last).requires_grad_(True)
+    before = set(B._warned)
+    with pnn.backend("sm100"):
+        y = conv(x)
+        g = torch.randn_like(y)
+        y.backward(g)
+    torch.cuda.synchronize()
+    assert ext.tc_error() == 0
+    assert not [k for k in set(B._warned) - before if k[0].startswith("conv2d")], set(B._warned) - before
+    xr = x.detach().float().requires_grad_(True)
+    wr = conv.weight.detach().float().requires_grad_(True)
+    yr = F.conv2d(xr, wr, None, st, 1); yr.backward(g.float())
+    assert (y.float() - yr).abs().max().item() <= 0.02 * max(1.0, yr.abs().max().item())
+    assert (x.grad.float() - xr.grad).abs().max().item() <= 0.03 * max(1.0, xr.grad.abs().max().item())
+    assert (conv.weight.grad.float() - wr.grad).abs().max().item() <= 0.03 * max(1.0, wr.grad.abs().max().item())
