@@ -12,6 +12,8 @@ import torch.nn as tnn
 import torch.nn.functional as F
 
 from .. import nn
+from ..nn.backend import use_sm100
+from ..ops import conv as _conv
 from .layerwise import LayerwiseBackwardMixin
 
 
@@ -21,7 +23,7 @@ class _Shortcut(tnn.Sequential):
     def forward(self, x):
         if len(self) == 0:
             return x
-        return self[1](self[0](x))
+        return self[1](self[0](x, bn=self[1]))
 
 
 class BasicBlock(tnn.Module):
@@ -40,8 +42,11 @@ class BasicBlock(tnn.Module):
                 nn.BatchNorm2d(self.expansion * planes))
 
     def forward(self, x):
-        out = self.bn1(self.conv1(x), relu=True)
-        return self.bn2(self.conv2(out), residual=self.shortcut(x), relu=True)
+        # the gradient arriving through the skip path is parked and added inside conv1's dgrad epilogue (ops/conv.py:stash_grad)
+        h = _conv.new_grad_holder(x) if use_sm100(x) else None
+        xs = _conv.stash_grad(x, h) if h is not None else x
+        out = self.bn1(self.conv1(x, grad_holder=h, bn=self.bn1), relu=True)
+        return self.bn2(self.conv2(out, bn=self.bn2), residual=self.shortcut(xs), relu=True)
 
 
 class Bottleneck(tnn.Module):
@@ -62,9 +67,11 @@ class Bottleneck(tnn.Module):
                 nn.BatchNorm2d(self.expansion * planes))
 
     def forward(self, x):
-        out = self.bn1(self.conv1(x), relu=True)
-        out = self.bn2(self.conv2(out), relu=True)
-        return self.bn3(self.conv3(out), residual=self.shortcut(x), relu=True)
+        h = _conv.new_grad_holder(x) if use_sm100(x) else None
+        xs = _conv.stash_grad(x, h) if h is not None else x
+        out = self.bn1(self.conv1(x, grad_holder=h, bn=self.bn1), relu=True)
+        out = self.bn2(self.conv2(out, bn=self.bn2), relu=True)
+        return self.bn3(self.conv3(out, bn=self.bn3), residual=self.shortcut(xs), relu=True)
 
 
 class ResNet(tnn.Module):

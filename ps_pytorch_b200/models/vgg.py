@@ -30,6 +30,9 @@ class _Features(tnn.Sequential):
             if isinstance(m, (nn.BatchNorm2d, nn.Conv2d)) and isinstance(nxt, tnn.ReLU):
                 x = m(x, relu=True)          # BN+ReLU in one pass / bias+ReLU in the conv epilogue
                 i += 2
+            elif isinstance(m, nn.Conv2d) and isinstance(nxt, nn.BatchNorm2d):
+                x = m(x, bn=nxt)             # the BN's batch statistics are reduced in the convolution epilogue
+                i += 1
             else:
                 x = m(x)
                 i += 1

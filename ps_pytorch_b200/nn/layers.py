@@ -19,14 +19,26 @@ from .backend import use_sm100, note_fallback
 
 
 class Conv2d(nn.Conv2d):
-    def forward(self, x, relu: bool = False):
-        """``relu=True`` fuses bias + ReLU into the convolution epilogue (VGG's conv→ReLU pairs)."""
+    def forward(self, x, relu: bool = False, grad_holder=None, bn=None):
+        """``relu=True`` fuses bias + ReLU into the convolution epilogue (VGG's conv→ReLU pairs).  ``grad_holder`` (``ops.conv.GradHolder``):
+        the skip-connection gradient parked there by ``stash_grad`` is added in this convolution's dgrad epilogue.  ``bn``: the
+        ``BatchNorm2d`` that consumes this output next; in training its batch statistics are then reduced in the convolution epilogue
+        (no separate statistics pass over the activation)."""
         if use_sm100(x):
             from ..ops import conv as _conv
             why = _conv.unsupported_reason(x, self.weight, self.stride, self.padding, self.dilation, self.groups)
             if why is None:
-                return _conv.conv2d(x, self.weight, self.bias, self.stride, self.padding, relu)
+                stats = None
+                if bn is not None and not relu and (bn.training or not bn.track_running_stats) and torch.is_grad_enabled():
+                    from ..ops import norm as _norm
+                    if x.dtype == torch.bfloat16 and bn.num_features == self.out_channels and self.out_channels % 8 == 0 \
+                            and (self.out_channels // 8) & (self.out_channels // 8 - 1) == 0 and self.out_channels // 8 <= 256:
+                        stats = _conv.stats_buffer(self, self.out_channels, x.device)
+                return _conv.conv2d(x, self.weight, self.bias, self.stride, self.padding, relu, grad_holder, stats)
             note_fallback("conv2d", why)
+        if grad_holder is not None:
+            grad_holder.consumed = True           # library path: nobody will pick the parked gradient up
+        if use_sm100(x):
             from ..ops import libconv as _lc
             if _lc.enabled() and torch.is_grad_enabled() and not isinstance(self.padding, str):
                 y = _lc.conv2d(x, self.weight, self.bias, self.stride, self.padding, self.dilation, self.groups)

@@ -91,13 +91,28 @@ def _halo_ok(h_out, w_out, r, s, stride):
     return stride == 1 and r * s > 1 and s <= 8 and w_out >= 8 and h_out >= 16
 
 
-def fprop(ext, x, w, bias, stride, pad, relu, residual=None):
+def fprop(ext, x, w, bias, stride, pad, relu, residual=None, stats=None):
     r, s = w.size(2), w.size(3)
     ho, wo = (x.size(2) + 2 * pad - r) // stride + 1, (x.size(3) + 2 * pad - s) // stride + 1
     count_launch()
     if _halo_ok(ho, wo, r, s, stride):
-        return ext.conv_fprop(x, w, bias, stride, pad, relu, residual)
-    return ext.conv2(x, w, bias, stride, pad, relu, residual, False, 0, 0)
+        return ext.conv_fprop(x, w, bias, stride, pad, relu, residual, stats)
+    return ext.conv2(x, w, bias, stride, pad, relu, residual, False, 0, 0, stats)
+
+
+_STATS_IN_EPILOGUE = os.environ.get("PSB200_CONV_BN_STATS", "1") != "0"
+
+
+def stats_buffer(module, cout, device):
+    """Persistent fp32 [4 * #SMs][2][Cout] partial-statistics rows written by the conv epilogue (one private row per epilogue warp) and
+    read + re-zeroed by the BatchNorm finalize kernel; None when the fusion is switched off (PSB200_CONV_BN_STATS=0)."""
+    if not _STATS_IN_EPILOGUE:
+        return None
+    buf = getattr(module, "_psb_stats_buf", None)
+    if buf is None or buf.device != device:
+        buf = torch.zeros(4 * require().num_sms() * 2 * cout, dtype=torch.float32, device=device)
+        module._psb_stats_buf = buf
+    return buf
 
 
 def dgrad(ext, dy, weight, in_h, in_w, stride, pad, residual=None):
@@ -111,14 +126,60 @@ def dgrad(ext, dy, weight, in_h, in_w, stride, pad, residual=None):
     return ext.conv2(dy, ext.weight_transpose(w, False), None, stride, pad, False, residual, True, in_h, in_w)
 
 
+class GradHolder:
+    """Rendezvous for the skip-connection gradient of a residual block (see ``stash_grad``)."""
+    __slots__ = ("grad", "consumed")
+
+    def __init__(self):
+        self.grad, self.consumed = None, False
+
+
+class _StashGrad(torch.autograd.Function):
+    """Identity in forward.  In backward the incoming gradient is parked in the holder instead of being returned, and the convolution that
+    shares this input adds it in its dgrad epilogue (``residual=``): autograd's separate accumulate kernel at every skip connection
+    (8 per ResNet-18 step) disappears.  If that convolution has already run (or never will), the gradient is returned normally."""
+
+    @staticmethod
+    def forward(ctx, x, holder):
+        ctx.holder = holder
+        return x.view_as(x)
+
+    @staticmethod
+    def backward(ctx, g):
+        h = ctx.holder
+        if h.consumed:
+            return g, None
+        h.grad = g if h.grad is None else h.grad + g
+        return None, None
+
+
+def stash_grad(x, holder):
+    return _StashGrad.apply(x, holder)
+
+
+_SKIP_FUSION = os.environ.get("PSB200_SKIP_GRAD_FUSION", "1") != "0"
+
+
+def set_skip_fusion(on: bool) -> None:
+    global _SKIP_FUSION
+    _SKIP_FUSION = bool(on)
+
+
+def new_grad_holder(x):
+    """A holder when fusing the skip gradient is possible for this input (our conv path, training), else None."""
+    if not (_ENABLED and _SKIP_FUSION and torch.is_grad_enabled() and x.is_cuda and x.requires_grad and x.dtype == torch.bfloat16):
+        return None
+    return GradHolder()
+
+
 class _ConvFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, x, weight, bias, stride, pad, relu):
+    def forward(ctx, x, weight, bias, stride, pad, relu, holder=None, stats=None):
         ext = require()
         x = x.contiguous(memory_format=torch.channels_last)
-        y = fprop(ext, x, _krsc(weight), bias, stride, pad, relu)
+        y = fprop(ext, x, _krsc(weight), bias, stride, pad, relu, None, stats)
         ctx.save_for_backward(x, weight, y if relu else None)
-        ctx.stride, ctx.pad, ctx.has_bias, ctx.relu = stride, pad, bias is not None, relu
+        ctx.stride, ctx.pad, ctx.has_bias, ctx.relu, ctx.holder = stride, pad, bias is not None, relu, holder
         return y
 
     @staticmethod
@@ -133,8 +194,19 @@ class _ConvFn(torch.autograd.Function):
         r = weight.size(2)
         dx = dw = db = None
         need_dx, need_dw = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
+        h = ctx.holder
+        skip = None
+        if h is not None:
+            if need_dx and h.grad is not None and h.grad.shape == x.shape and h.grad.dtype == dy.dtype:
+                skip = h.grad.contiguous(memory_format=torch.channels_last)
+                h.grad = None
+            else:
+                h.consumed = True                     # from now on the stash hands its gradient to autograd itself
         if need_dx:
-            dx = dgrad(ext, dy, weight, x.size(2), x.size(3), s, p)
+            dx = dgrad(ext, dy, weight, x.size(2), x.size(3), s, p, residual=skip)
+            if h is not None and h.grad is not None:  # parked but not fusable: add the slow way
+                dx = dx + h.grad.to(dx.dtype)
+                h.grad = None
         if need_dw and weight.size(1) % 64 == 0:
             dw = ext.conv_wgrad(dy, x, _wgrad_scratch(weight), r, weight.size(3), s, p)
             count_launch(2)
@@ -144,8 +216,11 @@ class _ConvFn(torch.autograd.Function):
             _gi, dw, _ = torch.ops.aten.convolution_backward(dy, x, weight, None, (s, s), (p, p), (1, 1), False, (0, 0), 1, (False, True, False))
         if ctx.has_bias and ctx.needs_input_grad[2]:
             db = dy.float().sum((0, 2, 3)).to(dy.dtype)
-        return dx, dw, db, None, None, None
+        return dx, dw, db, None, None, None, None, None
 
 
-def conv2d(x, weight, bias, stride, padding, relu=False):
-    return _ConvFn.apply(x, weight, bias, int(stride[0]), int(padding[0]), bool(relu))
+def conv2d(x, weight, bias, stride, padding, relu=False, grad_holder=None, stats=None):
+    y = _ConvFn.apply(x, weight, bias, int(stride[0]), int(padding[0]), bool(relu), grad_holder, stats)
+    if stats is not None:
+        y._psb_stats = stats          # picked up (once) by the BatchNorm that consumes y: ops/norm.py:batch_norm
+    return y

@@ -18,7 +18,7 @@ at::Tensor make_hp(double, double, double, double, bool, double, double, double,
 int64_t hp_steps(at::Tensor);
 // bn_kernels.cu
 std::vector<at::Tensor> bn_forward(at::Tensor, c10::optional<at::Tensor>, c10::optional<at::Tensor>, c10::optional<at::Tensor>, c10::optional<at::Tensor>,
-                                   c10::optional<at::Tensor>, bool, double, double, bool, c10::optional<at::Tensor>);
+                                   c10::optional<at::Tensor>, bool, double, double, bool, c10::optional<at::Tensor>, c10::optional<at::Tensor>);
 std::vector<at::Tensor> bn_backward(at::Tensor, c10::optional<at::Tensor>, at::Tensor, c10::optional<at::Tensor>, at::Tensor, at::Tensor, bool, bool, c10::optional<at::Tensor>,
                                     c10::optional<at::Tensor>, c10::optional<at::Tensor>);
 void bn_set_finalize_wide(int);
@@ -53,7 +53,9 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
     m.def("sgd_flat", &sgd_flat); m.def("adam_flat", &adam_flat);
     m.def("push", &push); m.def("reduce_update", &reduce_update); m.def("bcast", &bcast); m.def("wait_flag", &wait_flag);
     m.def("add_step", &add_step); m.def("set_word", &set_word); m.def("make_hp", &make_hp); m.def("hp_steps", &hp_steps);
-    m.def("ru_set_mc_src", &ru_set_mc_src); m.def("bn_forward", &bn_forward); m.def("bn_backward", &bn_backward); m.def("bn_set_finalize_wide", &bn_set_finalize_wide);
+    m.def("ru_set_mc_src", &ru_set_mc_src); m.def("bn_forward", &bn_forward, pybind11::arg("x"), pybind11::arg("gamma"), pybind11::arg("beta"), pybind11::arg("running_mean"), pybind11::arg("running_var"),
+          pybind11::arg("residual"), pybind11::arg("training"), pybind11::arg("momentum"), pybind11::arg("eps"), pybind11::arg("relu"), pybind11::arg("ws"),
+          pybind11::arg("conv_partial") = c10::optional<at::Tensor>()); m.def("bn_backward", &bn_backward); m.def("bn_set_finalize_wide", &bn_set_finalize_wide);
     m.def("relu_forward", &relu_forward); m.def("relu_backward", &relu_backward);
     m.def("maxpool2x2_forward", &maxpool2x2_forward); m.def("maxpool2x2_backward", &maxpool2x2_backward);
     m.def("gap_forward", &gap_forward); m.def("gap_backward", &gap_backward); m.def("softmax_ce", &softmax_ce);

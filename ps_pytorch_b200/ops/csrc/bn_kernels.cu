@@ -323,7 +323,7 @@ __global__ void __launch_bounds__(256) bn_bwd_finalize_kernel(const float* __res
 // (g = tid / 8, cc = tid % 8) sums rows g, g+32, g+64, ... with eight predicated loads in flight per batch (3 batches for 592 rows),
 // the 32 row groups are folded through shared memory and threads 0..7 finish their channel with the same arithmetic as above.
 // Sums s (first half of a partial row) and q (second half) for channel c over all nblk rows; valid in threads with g == 0 after the call.
-__device__ __forceinline__ void wide_partial_sum(const float* __restrict__ partial, int nblk, int C, int c, float& s, float& q) {
+__device__ __forceinline__ void wide_partial_sum(const float* partial, int nblk, int C, int c, float& s, float& q, bool clear = false) {
     __shared__ float ss[32][8], sq[32][8];
     const int cc = threadIdx.x & 7, g = threadIdx.x >> 3;
     float s8[8] = {0, 0, 0, 0, 0, 0, 0, 0}, q8[8] = {0, 0, 0, 0, 0, 0, 0, 0};
@@ -333,8 +333,13 @@ __device__ __forceinline__ void wide_partial_sum(const float* __restrict__ parti
             for (int u = 0; u < 8; ++u) {
                 const int bb = b + 32 * u;
                 if (bb < nblk) {
-                    s8[u] += __ldg(partial + (long long)bb * 2 * C + c);
-                    q8[u] += __ldg(partial + (long long)bb * 2 * C + C + c);
+                    float* ps = const_cast<float*>(partial) + (long long)bb * 2 * C + c;
+                    if (clear) {                 // rows written by a convolution epilogue: read once, leave zeroed for the next step
+                        s8[u] += __ldcg(ps); q8[u] += __ldcg(ps + C);
+                        ps[0] = 0.f; ps[C] = 0.f;
+                    } else {
+                        s8[u] += __ldg(ps); q8[u] += __ldg(ps + C);
+                    }
                 }
             }
         }
@@ -350,18 +355,18 @@ __device__ __forceinline__ void wide_partial_sum(const float* __restrict__ parti
 }
 
 template <typename PT>
-__global__ void __launch_bounds__(256) bn_finalize_wide_kernel(const float* __restrict__ partial, int nblk, int C, long long M,
+__global__ void __launch_bounds__(256) bn_finalize_wide_kernel(const float* partial, int nblk, int C, long long M,
                                                                const __nv_bfloat16* __restrict__ x_row0, const PT* __restrict__ gamma,
                                                                const PT* __restrict__ beta, float* running_mean, float* running_var,
                                                                float momentum, float eps, float* __restrict__ mean, float* __restrict__ invstd,
-                                                               float* __restrict__ coef_a, float* __restrict__ coef_b) {
+                                                               float* __restrict__ coef_a, float* __restrict__ coef_b, int clear) {
     const int c = blockIdx.x * 8 + (threadIdx.x & 7);
     float s, q;
-    wide_partial_sum(partial, nblk, C, c, s, q);
+    wide_partial_sum(partial, nblk, C, c, s, q, clear != 0);
     if ((threadIdx.x >> 3) == 0 && c < C) {
         const float inv_m = 1.f / (float)M;
         const float dm = s * inv_m;
-        const float K = __bfloat162float(x_row0[c]);
+        const float K = x_row0 ? __bfloat162float(x_row0[c]) : 0.f;      // conv-epilogue statistics are unshifted sums
         const float mu = K + dm;
         const float var = fmaxf(q * inv_m - dm * dm, 0.f);
         const float is = rsqrtf(var + eps);
@@ -440,7 +445,7 @@ static void check_act(const at::Tensor& t, const char* name) {
 std::vector<at::Tensor> bn_forward(at::Tensor x, c10::optional<at::Tensor> gamma, c10::optional<at::Tensor> beta,
                                    c10::optional<at::Tensor> running_mean, c10::optional<at::Tensor> running_var,
                                    c10::optional<at::Tensor> residual, bool training, double momentum, double eps, bool relu,
-                                   c10::optional<at::Tensor> ws) {
+                                   c10::optional<at::Tensor> ws, c10::optional<at::Tensor> conv_partial) {
     check_act(x, "x");
     const int C = (int)x.size(1);
     const long long M = x.numel() / C;
@@ -458,7 +463,21 @@ std::vector<at::Tensor> bn_forward(at::Tensor x, c10::optional<at::Tensor> gamma
     float* rm = running_mean.has_value() ? running_mean->data_ptr<float>() : nullptr;
     float* rv = running_var.has_value() ? running_var->data_ptr<float>() : nullptr;
     const uint4* xp = reinterpret_cast<const uint4*>(x.data_ptr());
-    if (training) {
+    if (training && conv_partial.has_value()) {
+        // statistics were accumulated by the producing convolution's epilogue (rows [r][2][C] of plain sums, zero where unused)
+        TORCH_CHECK(conv_partial->is_cuda() && conv_partial->scalar_type() == at::kFloat && conv_partial->is_contiguous() && conv_partial->numel() % (2 * C) == 0,
+                    "conv_partial must be a contiguous fp32 [rows, 2, C] tensor");
+        const int rows = (int)(conv_partial->numel() / (2 * C));
+        if (p_bf16)
+            bn_finalize_wide_kernel<__nv_bfloat16><<<(C + 7) / 8, 256, 0, stream>>>(conv_partial->data_ptr<float>(), rows, C, M, nullptr,
+                (const __nv_bfloat16*)gp, (const __nv_bfloat16*)bp, rm, rv, (float)momentum, (float)eps, mean.data_ptr<float>(), invstd.data_ptr<float>(),
+                ca.data_ptr<float>(), cb.data_ptr<float>(), 1);
+        else
+            bn_finalize_wide_kernel<float><<<(C + 7) / 8, 256, 0, stream>>>(conv_partial->data_ptr<float>(), rows, C, M, nullptr,
+                (const float*)gp, (const float*)bp, rm, rv, (float)momentum, (float)eps, mean.data_ptr<float>(), invstd.data_ptr<float>(),
+                ca.data_ptr<float>(), cb.data_ptr<float>(), 1);
+        C10_CUDA_KERNEL_LAUNCH_CHECK();
+    } else if (training) {
         const int RP = kBnThreads / LC;
         const int nblk = stream_grid(M, RP * 8);
         if (ws.has_value()) {
@@ -475,11 +494,11 @@ std::vector<at::Tensor> bn_forward(at::Tensor x, c10::optional<at::Tensor> gamma
         if (g_bn_finalize_wide && p_bf16)
             bn_finalize_wide_kernel<__nv_bfloat16><<<(C + 7) / 8, 256, 0, stream>>>(partial.data_ptr<float>(), nblk, C, M, (const __nv_bfloat16*)x.data_ptr(),
                 (const __nv_bfloat16*)gp, (const __nv_bfloat16*)bp, rm, rv, (float)momentum, (float)eps, mean.data_ptr<float>(), invstd.data_ptr<float>(),
-                ca.data_ptr<float>(), cb.data_ptr<float>());
+                ca.data_ptr<float>(), cb.data_ptr<float>(), 0);
         else if (g_bn_finalize_wide)
             bn_finalize_wide_kernel<float><<<(C + 7) / 8, 256, 0, stream>>>(partial.data_ptr<float>(), nblk, C, M, (const __nv_bfloat16*)x.data_ptr(),
                 (const float*)gp, (const float*)bp, rm, rv, (float)momentum, (float)eps, mean.data_ptr<float>(), invstd.data_ptr<float>(),
-                ca.data_ptr<float>(), cb.data_ptr<float>());
+                ca.data_ptr<float>(), cb.data_ptr<float>(), 0);
         else if (p_bf16)
             bn_finalize_kernel<__nv_bfloat16><<<fb, 256, 0, stream>>>(partial.data_ptr<float>(), nblk, C, M, (const __nv_bfloat16*)x.data_ptr(),
                 (const __nv_bfloat16*)gp, (const __nv_bfloat16*)bp, rm, rv, (float)momentum, (float)eps, mean.data_ptr<float>(), invstd.data_ptr<float>(),

@@ -52,6 +52,7 @@ struct Conv2Params {
     int relu;
     __nv_bfloat16* C;
     int* err;
+    float* stats;                // optional BatchNorm partial statistics [gridDim.x * 4][2][N] (tc_common.cuh: epilogue_tile)
 };
 
 template <int BN> struct Conv2Cfg {
@@ -155,6 +156,12 @@ tc_conv2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
         // ===================================================== epilogue (both CTAs; each drains its own 128 TMEM lanes)
         const int q = warp & 3;
         int acc = 0; uint32_t acc_phase = 0;
+        float* const srow = p.stats ? p.stats + (size_t)(blockIdx.x * 4 + q) * 2 * p.N : nullptr;
+        constexpr bool kRegStats = StatsCfg<BN>::kInRegs;
+        const bool use_racc = kRegStats && srow != nullptr && p.n_tiles_n == 1;      // one N tile: a thread's columns never change
+        float racc[kRegStats ? 2 * BN : 2];
+#pragma unroll
+        for (int j = 0; j < (kRegStats ? 2 * BN : 2); ++j) racc[j] = 0.f;
         for (int t = cluster_id; t < n_ptiles; t += n_clusters) {
             const int nt = t % p.n_tiles_n; const int rest = t / p.n_tiles_n;
             const int cls = rest / pairs_per_cls, mt = 2 * (rest % pairs_per_cls) + (int)rank;
@@ -169,12 +176,13 @@ tc_conv2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
             }
             if (!mbar_wait(tmem_full + acc, acc_phase)) { if (lane == 0) *p.err = 34; goto teardown; }
             tc_fence_after();
-            epilogue_tile<BN>(p, tmem_base, acc, q, lane, out_row, nt, p.tab.ntaps[cls] == 0);
+            epilogue_tile<BN>(p, tmem_base, acc, q, lane, out_row, nt, p.tab.ntaps[cls] == 0, srow, use_racc ? racc : nullptr);
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive_cluster(mapa_u32(smem_u32(tmem_empty + acc), 0));
+            if (lane == 0) mbar_arrive_cluster_relaxed(mapa_u32(smem_u32(tmem_empty + acc), 0));
             if (++acc == 2) { acc = 0; acc_phase ^= 1; }
         }
+        if constexpr (kRegStats) { if (use_racc) stats_flush<BN>(racc, srow, p.N, 0, lane); }
     }
 teardown:
     // every thread of both CTAs gets here (also after a timed-out wait): nobody may still be signalling the peer or using TMEM
@@ -211,7 +219,7 @@ void tc_set_conv2_bn(int b) { g_conv2_bn = b; }
 // Cred = Cin; dgrad: the transposed parameter [Cin][R][S][Cout], N = Cin, Cred = Cout).  Y: NHWC [NB, Hout, Wout, N].
 // dgrad = 0: Hout/Wout are derived.  dgrad = 1: Hout/Wout are the INPUT map of the forward convolution and must be given.
 const char* tc_conv2(const void* A, const void* Wt, void* Y, const void* bias, const void* residual, int NB, int Ha, int Wa, int Cred, int N,
-                     int R, int S, int stride, int pad, int dgrad, int Hout, int Wout, int relu, cudaStream_t stream) {
+                     int R, int S, int stride, int pad, int dgrad, int Hout, int Wout, int relu, float* stats, cudaStream_t stream) {
     if (Cred % 64) return "reduction channels must be a multiple of 64";
     if (N % 64) return "output channels must be a multiple of 64";
     if (stride < 1 || stride > 2) return "stride must be 1 or 2";
@@ -271,7 +279,7 @@ const char* tc_conv2(const void* A, const void* Wt, void* Y, const void* bias, c
     p.tiles_w = (p.Wg + BW - 1) / BW; p.tiles_h = (p.Hg + BH - 1) / BH;
     p.tiles_per_cls = p.tiles_w * p.tiles_h * ((NB + BNI - 1) / BNI);
     p.NB = NB; p.Hout = Hout; p.Wout = Wout;
-    p.bias = (const __nv_bfloat16*)bias; p.residual = (const __nv_bfloat16*)residual; p.relu = relu; p.C = (__nv_bfloat16*)Y; p.err = err_word();
+    p.bias = (const __nv_bfloat16*)bias; p.residual = (const __nv_bfloat16*)residual; p.relu = relu; p.C = (__nv_bfloat16*)Y; p.err = err_word(); p.stats = stats;
     return BN == 64 ? launch_conv2<64>(ta, tb, p, stream) : (BN == 128 ? launch_conv2<128>(ta, tb, p, stream) : launch_conv2<256>(ta, tb, p, stream));
 }
 

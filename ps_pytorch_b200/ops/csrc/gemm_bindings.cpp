@@ -5,8 +5,9 @@
 
 namespace psb {
 const char* tc_gemm_tn(const void*, const void*, void*, const void*, int, int, int, int, cudaStream_t);
-const char* tc_conv_fprop(const void*, const void*, void*, const void*, const void*, int, int, int, int, int, int, int, int, int, int, cudaStream_t);
-const char* tc_conv2(const void*, const void*, void*, const void*, const void*, int, int, int, int, int, int, int, int, int, int, int, int, int, cudaStream_t);
+const char* tc_conv_fprop(const void*, const void*, void*, const void*, const void*, int, int, int, int, int, int, int, int, int, int, float*, cudaStream_t);
+const char* tc_conv2(const void*, const void*, void*, const void*, const void*, int, int, int, int, int, int, int, int, int, int, int, int, int, float*, cudaStream_t);
+int num_sms();
 const char* weight_transpose(const void*, void*, int, int, int, int, cudaStream_t);
 void tc_set_conv2_bn(int);
 void tc_set_conv_algo(int);
@@ -18,11 +19,23 @@ void tc_set_gemm_bn(int);
 int tc_check_error();
 const char* stem_wgrad_launch(const void*, const void*, void*, float*, int, int, int, int, int, cudaStream_t);
 const char* tc_conv_wgrad(const void*, const void*, void*, float*, int, int, int, int, int, int, int, int, int, cudaStream_t);
+const char* tc_conv_wgrad_halo(const void*, const void*, void*, float*, int, int, int, int, int, cudaStream_t);
+bool tc_wgrad_halo_eligible(int, int, int, int, int, int, int, int);
+static int g_wgrad_algo = -1;          // -1 auto (halo form where eligible), 0 per-tap, 1 halo
+void tc_set_wgrad_algo(int a) { g_wgrad_algo = a; }
 
 static const void* opt_ptr(const c10::optional<at::Tensor>& t, int64_t n) {
     if (!t.has_value()) return nullptr;
     TORCH_CHECK(t->scalar_type() == at::kBFloat16 && t->is_contiguous() && t->numel() == n, "bias must be contiguous bf16 of size N");
     return t->data_ptr();
+}
+
+// optional BatchNorm partial-statistics buffer for a convolution epilogue: fp32, zero on entry, at least [4 * #SMs][2][N]
+static float* stats_ptr(const c10::optional<at::Tensor>& t, int64_t N) {
+    if (!t.has_value()) return nullptr;
+    TORCH_CHECK(t->is_cuda() && t->scalar_type() == at::kFloat && t->is_contiguous() && t->numel() >= (int64_t)4 * num_sms() * 2 * N,
+                "stats must be a contiguous fp32 buffer of at least 4 * #SMs * 2 * N floats");
+    return t->data_ptr<float>();
 }
 
 // y[M,N] = x[M,K] @ w[N,K]^T (+bias)(+relu); all bf16
@@ -39,7 +52,7 @@ at::Tensor gemm_tn(at::Tensor x, at::Tensor w, c10::optional<at::Tensor> bias, b
 
 // x: [NB,Cin,H,W] channels_last; w: [Cout,Cin,R,S] channels_last (physically [Cout][R][S][Cin]); returns channels_last y
 at::Tensor conv_fprop(at::Tensor x, at::Tensor w, c10::optional<at::Tensor> bias, int64_t stride, int64_t pad, bool relu,
-                      c10::optional<at::Tensor> residual) {
+                      c10::optional<at::Tensor> residual, c10::optional<at::Tensor> stats) {
     TORCH_CHECK(x.is_cuda() && x.scalar_type() == at::kBFloat16 && w.scalar_type() == at::kBFloat16 && x.dim() == 4 && w.dim() == 4);
     TORCH_CHECK(x.is_contiguous(at::MemoryFormat::ChannelsLast), "x must be NHWC");
     TORCH_CHECK(w.is_contiguous(at::MemoryFormat::ChannelsLast), "w must be [Cout][R][S][Cin]");
@@ -54,7 +67,7 @@ at::Tensor conv_fprop(at::Tensor x, at::Tensor w, c10::optional<at::Tensor> bias
         rp = residual->data_ptr();
     }
     const char* e = tc_conv_fprop(x.data_ptr(), w.data_ptr(), y.data_ptr(), opt_ptr(bias, Cout), rp, NB, H, W, Cin, Cout, R, S, (int)stride, (int)pad, relu,
-                                  at::cuda::getCurrentCUDAStream());
+                                  stats_ptr(stats, Cout), at::cuda::getCurrentCUDAStream());
     TORCH_CHECK(e == nullptr, "tc_conv_fprop: ", e);
     return y;
 }
@@ -65,7 +78,7 @@ at::Tensor conv_fprop(at::Tensor x, at::Tensor w, c10::optional<at::Tensor> bias
 //                  [Cin][R][S][Cout]); in_h/in_w = spatial size of the forward input; returns dx [NB,Cin,in_h,in_w].  residual (same shape as the
 //                  result) is added in the epilogue.
 at::Tensor conv2(at::Tensor a, at::Tensor w, c10::optional<at::Tensor> bias, int64_t stride, int64_t pad, bool relu, c10::optional<at::Tensor> residual,
-                 bool dgrad, int64_t in_h, int64_t in_w) {
+                 bool dgrad, int64_t in_h, int64_t in_w, c10::optional<at::Tensor> stats) {
     TORCH_CHECK(a.is_cuda() && a.scalar_type() == at::kBFloat16 && w.scalar_type() == at::kBFloat16 && a.dim() == 4 && w.dim() == 4);
     TORCH_CHECK(a.is_contiguous(at::MemoryFormat::ChannelsLast), "activations must be NHWC");
     TORCH_CHECK(w.is_contiguous(at::MemoryFormat::ChannelsLast), "weights must be [N][R][S][K]");
@@ -82,7 +95,7 @@ at::Tensor conv2(at::Tensor a, at::Tensor w, c10::optional<at::Tensor> bias, int
         rp = residual->data_ptr();
     }
     const char* e = tc_conv2(a.data_ptr(), w.data_ptr(), y.data_ptr(), opt_ptr(bias, N), rp, NB, Ha, Wa, Cred, N, R, S, (int)stride, (int)pad, dgrad ? 1 : 0, Ho, Wo,
-                             relu, at::cuda::getCurrentCUDAStream());
+                             relu, stats_ptr(stats, N), at::cuda::getCurrentCUDAStream());
     TORCH_CHECK(e == nullptr, "tc_conv2: ", e);
     return y;
 }
@@ -105,8 +118,12 @@ at::Tensor conv_wgrad(at::Tensor dy, at::Tensor x, at::Tensor scratch, int64_t R
     const int NB = x.size(0), Cin = x.size(1), H = x.size(2), W = x.size(3), Cout = dy.size(1);
     TORCH_CHECK(scratch.scalar_type() == at::kFloat && scratch.is_contiguous() && scratch.numel() >= (int64_t)Cout * R * S * Cin);
     at::Tensor dw = at::empty({Cout, Cin, R, S}, x.options().memory_format(at::MemoryFormat::ChannelsLast));
-    const char* e = tc_conv_wgrad(dy.data_ptr(), x.data_ptr(), dw.data_ptr(), scratch.data_ptr<float>(), NB, H, W, Cin, Cout, (int)R, (int)S, (int)stride, (int)pad,
-                                  at::cuda::getCurrentCUDAStream());
+    const char* e;
+    if (g_wgrad_algo != 0 && tc_wgrad_halo_eligible(H, W, Cin, Cout, (int)R, (int)S, (int)stride, (int)pad))
+        e = tc_conv_wgrad_halo(dy.data_ptr(), x.data_ptr(), dw.data_ptr(), scratch.data_ptr<float>(), NB, H, W, Cin, Cout, at::cuda::getCurrentCUDAStream());
+    else
+        e = tc_conv_wgrad(dy.data_ptr(), x.data_ptr(), dw.data_ptr(), scratch.data_ptr<float>(), NB, H, W, Cin, Cout, (int)R, (int)S, (int)stride, (int)pad,
+                          at::cuda::getCurrentCUDAStream());
     TORCH_CHECK(e == nullptr, "tc_conv_wgrad: ", e);
     return dw;
 }
@@ -140,9 +157,11 @@ int64_t tc_error() { return tc_check_error(); }
 void bind_gemm(pybind11::module_& m) {
     m.def("gemm_tn", &psb::gemm_tn);
     m.def("conv_fprop", &psb::conv_fprop, pybind11::arg("x"), pybind11::arg("w"), pybind11::arg("bias"), pybind11::arg("stride"), pybind11::arg("pad"),
-          pybind11::arg("relu"), pybind11::arg("residual") = c10::optional<at::Tensor>());
+          pybind11::arg("relu"), pybind11::arg("residual") = c10::optional<at::Tensor>(), pybind11::arg("stats") = c10::optional<at::Tensor>());
     m.def("conv2", &psb::conv2, pybind11::arg("a"), pybind11::arg("w"), pybind11::arg("bias"), pybind11::arg("stride"), pybind11::arg("pad"), pybind11::arg("relu"),
-          pybind11::arg("residual") = c10::optional<at::Tensor>(), pybind11::arg("dgrad") = false, pybind11::arg("in_h") = 0, pybind11::arg("in_w") = 0);
+          pybind11::arg("residual") = c10::optional<at::Tensor>(), pybind11::arg("dgrad") = false, pybind11::arg("in_h") = 0, pybind11::arg("in_w") = 0,
+          pybind11::arg("stats") = c10::optional<at::Tensor>());
+    m.def("num_sms", &psb::num_sms);
     m.def("weight_transpose", &psb::weight_transpose_t);
     m.def("tc_set_conv2_bn", &psb::tc_set_conv2_bn);
     m.def("tc_set_conv_algo", &psb::tc_set_conv_algo);
@@ -153,6 +172,7 @@ void bind_gemm(pybind11::module_& m) {
     m.def("tc_set_gemm_bn", &psb::tc_set_gemm_bn);
     m.def("conv_unsupported_reason", &psb::conv_unsupported_reason);
     m.def("conv_wgrad", &psb::conv_wgrad);
+    m.def("tc_set_wgrad_algo", &psb::tc_set_wgrad_algo);
     m.def("stem_wgrad", &psb::stem_wgrad);
     m.def("tc_error", &psb::tc_error);
 }

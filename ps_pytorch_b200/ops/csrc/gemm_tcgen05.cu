@@ -122,6 +122,12 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         // ===================================================== epilogue (4 warps, one TMEM lane quarter each)
         const int q = warp & 3;
         int acc = 0; uint32_t acc_phase = 0;
+        float* const srow = p.stats ? p.stats + (size_t)(blockIdx.x * 4 + q) * 2 * p.N : nullptr;
+        constexpr bool kRegStats = StatsCfg<BN>::kInRegs;
+        const bool use_racc = kRegStats && srow != nullptr && p.n_tiles_n == 1;      // one N tile: a thread's columns never change
+        float racc[kRegStats ? 2 * BN : 2];
+#pragma unroll
+        for (int j = 0; j < (kRegStats ? 2 * BN : 2); ++j) racc[j] = 0.f;
         for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
             const int mt = tile / p.n_tiles_n, nt = tile % p.n_tiles_n;
             const int row_in_tile = q * 32 + lane;
@@ -137,12 +143,13 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
             }
             if (!mbar_wait(tmem_full + acc, acc_phase)) { if (lane == 0) *p.err = 4; return; }
             tc_fence_after();
-            epilogue_tile<BN>(p, tmem_base, acc, q, lane, out_row, nt);
+            epilogue_tile<BN>(p, tmem_base, acc, q, lane, out_row, nt, false, srow, use_racc ? racc : nullptr);
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(tmem_empty + acc);
+            if (lane == 0) mbar_arrive_relaxed(tmem_empty + acc);
             if (++acc == 2) { acc = 0; acc_phase ^= 1; }
         }
+        if constexpr (kRegStats) { if (use_racc) stats_flush<BN>(racc, srow, p.N, 0, lane); }
     }
     // ---- teardown
     tc_fence_before();
@@ -258,7 +265,7 @@ tc_gemm2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
             epilogue_tile<BN2>(p, tmem_base, acc, q, lane, out_row, nt);
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive_cluster(mapa_u32(smem_u32(tmem_empty + acc), 0));
+            if (lane == 0) mbar_arrive_cluster_relaxed(mapa_u32(smem_u32(tmem_empty + acc), 0));
             if (++acc == 2) { acc = 0; acc_phase ^= 1; }
         }
     }
@@ -287,7 +294,7 @@ teardown:
 // Weights stream one filter ROW per TMA: a 3-D box (64 k, BN out-channels, S taps) = S consecutive K-major B tiles, so the
 // producer issues R+1 bulk copies per channel block instead of R*S+1 and the MMA warp waits on R barriers (the first
 // version issued one 8-16 KB copy per tap and the MMA warp spent a third of its time waiting on them, profiles/run7_*.md).
-constexpr int kMaxAStages = 4;
+constexpr int kMaxAStages = 4, kMaxBStages = 8;
 template <int BN> struct HaloCfg {
     static constexpr int kAStages = 2;
     static constexpr int kBStages = BN == 64 ? 4 : 3;
@@ -405,6 +412,12 @@ tc_conv_halo_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     } else if (warp >= kEpiWarp0) {
         const int q = warp & 3;
         int acc = 0; uint32_t acc_phase = 0;
+        float* const srow = p.stats ? p.stats + (size_t)(blockIdx.x * 4 + q) * 2 * p.N : nullptr;
+        constexpr bool kRegStats = StatsCfg<BN>::kInRegs;
+        const bool use_racc = kRegStats && srow != nullptr && p.n_tiles_n == 1;      // one N tile: a thread's columns never change
+        float racc[kRegStats ? 2 * BN : 2];
+#pragma unroll
+        for (int j = 0; j < (kRegStats ? 2 * BN : 2); ++j) racc[j] = 0.f;
         for (int it = 0; it < n_iters; ++it) {
             const int tile = it * gridDim.x + blockIdx.x;
             const bool ghost = tile >= n_tiles;
@@ -415,12 +428,13 @@ tc_conv_halo_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
             const long long out_row = (!ghost && h < p.Hout && w < p.Wout) ? ((long long)n * p.Hout + h) * p.Wout + w : -1;
             if (!mbar_wait(tmem_full + acc, acc_phase)) { if (lane == 0) *p.err = 16; return; }
             tc_fence_after();
-            epilogue_tile<BN>(p, tmem_base, acc, q, lane, out_row, nt);
+            epilogue_tile<BN>(p, tmem_base, acc, q, lane, out_row, nt, false, srow, use_racc ? racc : nullptr);
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(tmem_empty + acc);
+            if (lane == 0) mbar_arrive_relaxed(tmem_empty + acc);
             if (++acc == 2) { acc = 0; acc_phase ^= 1; }
         }
+        if constexpr (kRegStats) { if (use_racc) stats_flush<BN>(racc, srow, p.N, 0, lane); }
     }
     tc_fence_before();
     __syncthreads();
@@ -449,11 +463,15 @@ tc_conv_halo2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
     uint8_t* smem_a = smem;
     uint8_t* smem_b = smem + p.a_stages * p.a_stage_bytes;
     const int b_stage_bytes = p.S * kHalfTapBytes;
-    uint64_t* a_full = reinterpret_cast<uint64_t*>(smem_b + Cfg::kBStages * b_stage_bytes);
+    // B stages: a ring of p.b_stages filter-row stages, or (p.b_resident) ALL cblocks * R filter rows of this CTA's half of the weights, loaded
+    // once and kept for the whole kernel (stage = cb * R + r): the weights of a 64- or 128-channel layer are 36-144 KB per CTA, while
+    // re-streaming them for every tile made L2->SM delivery (~40 B/cycle/SM) the bound of these layers (profiles/run25_conv_ncu.md).
+    const int nbs = p.b_stages;
+    uint64_t* a_full = reinterpret_cast<uint64_t*>(smem_b + nbs * b_stage_bytes);
     uint64_t* a_empty = a_full + kMaxAStages;
     uint64_t* b_full = a_empty + kMaxAStages;
-    uint64_t* b_empty = b_full + Cfg::kBStages;
-    uint64_t* tmem_full = b_empty + Cfg::kBStages;
+    uint64_t* b_empty = b_full + kMaxBStages;
+    uint64_t* tmem_full = b_empty + kMaxBStages;
     uint64_t* tmem_empty = tmem_full + 2;
     uint32_t* tmem_base_smem = reinterpret_cast<uint32_t*>(tmem_empty + 2);
 
@@ -461,7 +479,7 @@ tc_conv_halo2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
     if (warp == 0 && lane == 0) { prefetch_tmap(&tmap_a); prefetch_tmap(&tmap_b); }
     if (warp == 1 && lane == 0) {
         for (int s = 0; s < p.a_stages; ++s) { mbar_init(a_full + s, 1); mbar_init(a_empty + s, 1); }
-        for (int s = 0; s < Cfg::kBStages; ++s) { mbar_init(b_full + s, 1); mbar_init(b_empty + s, 1); }
+        for (int s = 0; s < nbs; ++s) { mbar_init(b_full + s, 1); mbar_init(b_empty + s, 1); }
         for (int s = 0; s < 2; ++s) { mbar_init(tmem_full + s, 1); mbar_init(tmem_empty + s, 8); }
         fence_barrier_init();
     }
@@ -477,6 +495,7 @@ tc_conv_halo2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
 
     if (warp == 0) {
         int as = 0; uint32_t aph = 0; int bs = 0; uint32_t bph = 0;
+        bool first = true;
         for (int pt = cluster_id; pt < n_ptiles; pt += n_clusters) {
             const int nt = pt / n_pairs_m, mt = 2 * (pt % n_pairs_m) + (int)rank;
             const bool ghost = mt >= p.n_tiles_m;
@@ -489,6 +508,7 @@ tc_conv_halo2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
                 }
                 __syncwarp();
                 if (++as == p.a_stages) { as = 0; aph ^= 1; }
+                if (p.b_resident && !first) continue;              // the weights are already resident (stage cb * R + r)
                 for (int r = 0; r < p.R; ++r) {
                     if (!mbar_wait(b_empty + bs, bph ^ 1)) { *p.err = 22; goto teardown; }
                     if (elect_one()) {
@@ -496,9 +516,10 @@ tc_conv_halo2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
                         tma_load_3d_2sm(smem_b + bs * b_stage_bytes, &tmap_b, mapa_u32(smem_u32(b_full + bs), 0), cb * BK, nt * BN + (int)rank * (BN / 2), r * p.S);
                     }
                     __syncwarp();
-                    if (++bs == Cfg::kBStages) { bs = 0; bph ^= 1; }
+                    if (++bs == nbs) { bs = 0; bph ^= 1; }
                 }
             }
+            first = false;
         }
     } else if (warp == 1 && leader) {
         constexpr uint32_t idesc = umma_idesc_bf16(256, BN, 0, 0);
@@ -511,6 +532,7 @@ tc_conv_halo2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
                 if (!mbar_wait(a_full + as, aph)) { *p.err = 24; goto teardown; }
                 const uint32_t sa0 = smem_u32(smem_a + as * p.a_stage_bytes);
                 for (int r = 0; r < p.R; ++r) {
+                    if (p.b_resident) { bs = cb * p.R + r; bph = 0; }        // phase 0 of a resident stage stays complete
                     if (!mbar_wait(b_full + bs, bph)) { *p.err = 25; goto teardown; }
                     tc_fence_after();
                     const uint32_t sb0 = smem_u32(smem_b + bs * b_stage_bytes);
@@ -522,10 +544,10 @@ tc_conv_halo2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
                             for (int k = 0; k < BK / 16; ++k)
                                 tc_mma2_bf16(tmem_d, umma_desc_k_sw128_sbo(sa + k * 32, 2048), umma_desc_k_sw128(sb + k * 32), idesc, (cb | r | s | k) != 0);
                         }
-                        tc_commit2_mcast(b_empty + bs, 0b11);
+                        if (!p.b_resident) tc_commit2_mcast(b_empty + bs, 0b11);
                     }
                     __syncwarp();
-                    if (++bs == Cfg::kBStages) { bs = 0; bph ^= 1; }
+                    if (!p.b_resident && ++bs == nbs) { bs = 0; bph ^= 1; }
                 }
                 if (elect_one()) tc_commit2_mcast(a_empty + as, 0b11);
                 __syncwarp();
@@ -538,6 +560,12 @@ tc_conv_halo2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
     } else if (warp >= kEpiWarp0) {
         const int q = warp & 3;
         int acc = 0; uint32_t acc_phase = 0;
+        float* const srow = p.stats ? p.stats + (size_t)(blockIdx.x * 4 + q) * 2 * p.N : nullptr;
+        constexpr bool kRegStats = StatsCfg<BN>::kInRegs;
+        const bool use_racc = kRegStats && srow != nullptr && p.n_tiles_n == 1;      // one N tile: a thread's columns never change
+        float racc[kRegStats ? 2 * BN : 2];
+#pragma unroll
+        for (int j = 0; j < (kRegStats ? 2 * BN : 2); ++j) racc[j] = 0.f;
         for (int pt = cluster_id; pt < n_ptiles; pt += n_clusters) {
             const int nt = pt / n_pairs_m, mt = 2 * (pt % n_pairs_m) + (int)rank;
             const bool ghost = mt >= p.n_tiles_m;
@@ -547,12 +575,13 @@ tc_conv_halo2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
             const long long out_row = (!ghost && h < p.Hout && w < p.Wout) ? ((long long)n * p.Hout + h) * p.Wout + w : -1;
             if (!mbar_wait(tmem_full + acc, acc_phase)) { if (lane == 0) *p.err = 26; goto teardown; }
             tc_fence_after();
-            epilogue_tile<BN>(p, tmem_base, acc, q, lane, out_row, nt);
+            epilogue_tile<BN>(p, tmem_base, acc, q, lane, out_row, nt, false, srow, use_racc ? racc : nullptr);
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive_cluster(mapa_u32(smem_u32(tmem_empty + acc), 0));
+            if (lane == 0) mbar_arrive_cluster_relaxed(mapa_u32(smem_u32(tmem_empty + acc), 0));
             if (++acc == 2) { acc = 0; acc_phase ^= 1; }
         }
+        if constexpr (kRegStats) { if (use_racc) stats_flush<BN>(racc, srow, p.N, 0, lane); }
     }
 teardown:
     // every thread of both CTAs reaches this point, also after a timed-out wait (error word set): a thread that returned early would
@@ -705,7 +734,7 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmap_dy, const __grid_consta
             }
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(tmem_empty + acc);
+            if (lane == 0) mbar_arrive_relaxed(tmem_empty + acc);
             if (++acc == 2) { acc = 0; acc_phase ^= 1; }
         }
     }
@@ -724,6 +753,10 @@ __global__ void wgrad_finish_kernel(float* __restrict__ acc, __nv_bfloat16* __re
         uint2 o; o.x = *reinterpret_cast<uint32_t*>(&a); o.y = *reinterpret_cast<uint32_t*>(&b);
         *reinterpret_cast<uint2*>(out + i) = o;
     }
+}
+
+void wgrad_finish_launch(float* acc, void* out, long long n, cudaStream_t stream) {
+    wgrad_finish_kernel<<<(int)((n / 4 + 255) / 256 < 1184 ? (n / 4 + 255) / 256 : 1184), 256, 0, stream>>>(acc, (__nv_bfloat16*)out, n);
 }
 
 // ------------------------------------------------------------------------------------------------------------------ host
@@ -819,7 +852,7 @@ void tc_set_halo_pair(int v) { g_halo_pair = v ? 1 : 0; }
 template <int BN>
 static const char* launch_halo_pair(const CUtensorMap& ta, const CUtensorMap& tb, const TcParams& p, cudaStream_t stream) {
     using Cfg = HaloCfg<BN>;
-    const int smem_bytes = p.a_stages * p.a_stage_bytes + Cfg::kBStages * p.S * (BN / 2) * BK * 2 + 1024 + 512;
+    const int smem_bytes = p.a_stages * p.a_stage_bytes + p.b_stages * p.S * (BN / 2) * BK * 2 + 1024 + 512;
     if (smem_bytes > 227 * 1024) return "halo tile does not fit in shared memory";
     static int attr = 0;
     if (attr < smem_bytes) {
@@ -888,7 +921,7 @@ const char* tc_gemm_tn(const void* A, const void* B, void* C, const void* bias, 
 
 // Y[NB,Hout,Wout,Cout] = conv(X[NB,Hin,Win,Cin], Wt[Cout][R][S][Cin]), NHWC bf16
 const char* tc_conv_fprop(const void* X, const void* Wt, void* Y, const void* bias, const void* residual, int NB, int Hin, int Win, int Cin, int Cout,
-                          int R, int S, int stride, int pad, int relu, cudaStream_t stream) {
+                          int R, int S, int stride, int pad, int relu, float* stats, cudaStream_t stream) {
     if (Cin % 64) return "Cin must be a multiple of 64";
     if (Cout % 8) return "Cout must be a multiple of 8";
     const int Hout = (Hin + 2 * pad - R) / stride + 1, Wout = (Win + 2 * pad - S) / stride + 1;
@@ -916,8 +949,17 @@ const char* tc_conv_fprop(const void* X, const void* Wt, void* Y, const void* bi
         p.b_resident = (g_halo_resident && p.cblocks == 1 && p.n_tiles_n == 1 && R <= HaloCfg<64>::kBStages && BN == 64) ? 1 : 0;
         p.a_stages = 2;
         if (p.b_resident && 3 * p.a_stage_bytes + HaloCfg<64>::kBStages * S * HaloCfg<64>::kBTapBytes + 2048 <= 227 * 1024) p.a_stages = 3;
-        p.bias = (const __nv_bfloat16*)bias; p.residual = (const __nv_bfloat16*)residual; p.relu = relu; p.C = (__nv_bfloat16*)Y; p.err = err_word();
-        if (pair) { p.b_resident = 0; p.a_stages = 2; return BN == 64 ? launch_halo_pair<64>(ta, tb, p, stream) : launch_halo_pair<128>(ta, tb, p, stream); }
+        p.bias = (const __nv_bfloat16*)bias; p.residual = (const __nv_bfloat16*)residual; p.relu = relu; p.C = (__nv_bfloat16*)Y; p.err = err_word(); p.stats = stats;
+        if (pair) {
+            // keep this CTA's half of ALL the weights in shared memory when they fit next to the activation stages
+            const int b_stage = S * (BN / 2) * BK * 2, all_b = p.cblocks * R * b_stage;
+            p.b_resident = 0; p.a_stages = 2; p.b_stages = BN == 64 ? HaloCfg<64>::kBStages : HaloCfg<128>::kBStages;
+            if (g_halo_resident && p.n_tiles_n == 1 && p.cblocks * R <= kMaxBStages && 2 * p.a_stage_bytes + all_b + 2048 <= 227 * 1024) {
+                p.b_resident = 1; p.b_stages = p.cblocks * R;
+                while (p.a_stages < kMaxAStages && (p.a_stages + 1) * p.a_stage_bytes + all_b + 2048 <= 227 * 1024) ++p.a_stages;
+            }
+            return BN == 64 ? launch_halo_pair<64>(ta, tb, p, stream) : launch_halo_pair<128>(ta, tb, p, stream);
+        }
         if (g_halo_cluster == 2 && (p.n_tiles_m % 2) == 0 && !p.b_resident) return BN == 64 ? launch_halo<64, 2>(ta, tb, p, stream) : launch_halo<128, 2>(ta, tb, p, stream);
         return BN == 64 ? launch_halo<64, 1>(ta, tb, p, stream) : launch_halo<128, 1>(ta, tb, p, stream);
     }
@@ -946,7 +988,7 @@ const char* tc_conv_fprop(const void* X, const void* Wt, void* Y, const void* bi
     p.tiles_w = (Wout + BW - 1) / BW; p.tiles_h = (Hout + BH - 1) / BH;
     const int tiles_n_img = (NB + BNI - 1) / BNI;
     p.n_tiles_m = p.tiles_w * p.tiles_h * tiles_n_img; p.n_tiles_n = (Cout + BN - 1) / BN;
-    p.bias = (const __nv_bfloat16*)bias; p.residual = (const __nv_bfloat16*)residual; p.relu = relu; p.C = (__nv_bfloat16*)Y; p.err = err_word();
+    p.bias = (const __nv_bfloat16*)bias; p.residual = (const __nv_bfloat16*)residual; p.relu = relu; p.C = (__nv_bfloat16*)Y; p.err = err_word(); p.stats = stats;
     return BN == 64 ? launch<64>(ta, tb, p, stream) : (BN == 128 ? launch<128>(ta, tb, p, stream) : launch<256>(ta, tb, p, stream));
 }
 

@@ -27,21 +27,62 @@ struct TcParams {
     const __nv_bfloat16* residual;      // optional [M,N] tensor added in the epilogue (dgrad + skip-gradient fusion)
     int relu;
     int R, halo_w, a_stage_bytes;       // halo kernel: filter rows, halo box width, bytes per A stage
-    int b_resident, a_stages;           // weight-stationary mode: all R filter rows of B stay in smem for the whole kernel
+    int b_resident, a_stages, b_stages; // weight-stationary mode: all filter rows of B stay in smem for the whole kernel (halo kernels)
     int desc_mode;
     __nv_bfloat16* C;
     int* err;                          // set to 1 if a barrier wait timed out (protocol bug), never hang
+    float* stats;                      // optional BatchNorm partial statistics [gridDim.x * 4 warps][2][N] (see epilogue_tile)
 };
 
 // TMEM accumulator quarter -> (+bias) (+residual) (ReLU) -> bf16 -> global.  Thread `lane` of warp quarter q owns one output row.
 // P is any parameter block with N, C, bias, residual, relu.  zero_acc: the tile had no MMAs (a dgrad parity class without taps): the
 // accumulator is taken as 0 instead of being read.
+// stats_row (optional): this warp's private row [2][N] of per-channel partial sums for the BatchNorm that follows the convolution:
+// the 32 output rows a warp holds are reduced per column with a transposing butterfly (31 shuffles per quantity: lane i ends up with the
+// total of column i) and added to the row with one coalesced RED per quantity — the separate bn_stats pass (one full read of the
+// activation per BN layer) disappears.  Rows are private per warp, so the REDs never contend; bn_finalize sums the rows and re-zeroes them.
+__device__ __forceinline__ void butterfly_colsum(float (&a)[32], int lane) {
+#pragma unroll
+    for (int half = 16; half >= 1; half >>= 1) {
+        const bool up = (lane & half) != 0;
+#pragma unroll
+        for (int j = 0; j < half; ++j) {
+            const float keep = up ? a[j + half] : a[j];
+            const float send = up ? a[j] : a[j + half];
+            a[j] = keep + __shfl_xor_sync(0xffffffffu, send, half);
+        }
+    }
+}
+
+// For BN = 64 (the 64-channel layers, where a tile's MMAs take ~1200 cycles and the epilogue is close to the critical path) the butterfly
+// per tile costs more than the statistics pass it replaces (measured: +0.06 ms/step).  There the per-column sums are instead carried in
+// REGISTERS across all tiles of the persistent CTA (racc[0..BN) sums, racc[BN..2BN) sums of squares of this thread's rows: 2 FP32 ops per
+// element) and reduced + written once per kernel by stats_flush.
+template <int BN> struct StatsCfg { static constexpr bool kInRegs = BN <= 64; };
+
+template <int BN>
+__device__ __forceinline__ void stats_flush(float (&racc)[2 * BN], float* stats_row, int N, int col_base, int lane) {
+#pragma unroll
+    for (int c0 = 0; c0 < BN; c0 += 32) {
+        float a[32], b[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) { a[j] = racc[c0 + j]; b[j] = racc[BN + c0 + j]; }
+        butterfly_colsum(a, lane);
+        butterfly_colsum(b, lane);
+        if (col_base + c0 + lane < N) {
+            atomicAdd(stats_row + col_base + c0 + lane, a[0]);
+            atomicAdd(stats_row + N + col_base + c0 + lane, b[0]);
+        }
+    }
+}
+
 template <int BN, class P>
-__device__ __forceinline__ void epilogue_tile(const P& p, uint32_t tmem_base, int acc, int q, int lane, long long out_row, int nt, bool zero_acc = false) {
+__device__ __forceinline__ void epilogue_tile(const P& p, uint32_t tmem_base, int acc, int q, int lane, long long out_row, int nt, bool zero_acc = false,
+                                              float* stats_row = nullptr, float* racc = nullptr) {
     const bool vec_ok = (p.N % 8) == 0;
     __nv_bfloat16* crow = p.C + out_row * (long long)p.N + (long long)nt * BN;
     const __nv_bfloat16* rrow = p.residual ? p.residual + out_row * (long long)p.N + (long long)nt * BN : nullptr;
-#pragma unroll 1
+#pragma unroll (StatsCfg<BN>::kInRegs ? BN / 32 : 1)
     for (int c0 = 0; c0 < BN; c0 += 32) {
         uint32_t v[32];
         if (!zero_acc) {
@@ -52,8 +93,10 @@ __device__ __forceinline__ void epilogue_tile(const P& p, uint32_t tmem_base, in
             for (int j = 0; j < 32; ++j) v[j] = 0u;
         }
         const int col0 = nt * BN + c0;
+        float f[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) f[j] = 0.f;
         if (out_row >= 0 && col0 < p.N) {
-            float f[32];
 #pragma unroll
             for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
             if (p.bias) {
@@ -103,6 +146,20 @@ __device__ __forceinline__ void epilogue_tile(const P& p, uint32_t tmem_base, in
                 }
             } else {
                 for (int j = 0; j < 32; ++j) if (col0 + j < p.N) crow[c0 + j] = __float2bfloat16_rn(f[j]);
+            }
+        }
+        if (StatsCfg<BN>::kInRegs && racc != nullptr) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) { racc[c0 + j] += f[j]; racc[BN + c0 + j] = fmaf(f[j], f[j], racc[BN + c0 + j]); }
+        } else if (stats_row != nullptr && col0 < p.N) {   // warp-uniform; rows without an output pixel contribute zeros
+            float sq[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) sq[j] = f[j] * f[j];
+            butterfly_colsum(f, lane);
+            butterfly_colsum(sq, lane);
+            if (col0 + lane < p.N) {
+                atomicAdd(stats_row + col0 + lane, f[0]);
+                atomicAdd(stats_row + p.N + col0 + lane, sq[0]);
             }
         }
     }

@@ -52,15 +52,21 @@ def bn_unsupported_reason(x: torch.Tensor):
 
 class _BatchNormFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, x, weight, bias, residual, running_mean, running_var, training, momentum, eps, relu, ws):
+    def forward(ctx, x, weight, bias, residual, running_mean, running_var, training, momentum, eps, relu, ws, conv_partial=None):
         ext = require()
         _apply_switches(ext)
         x = x.contiguous(memory_format=torch.channels_last)
         if residual is not None:
             residual = residual.contiguous(memory_format=torch.channels_last)
-        z, mean, invstd, ca, cb = ext.bn_forward(x, weight, bias, running_mean, running_var, residual, training, momentum, eps, relu,
-                                                 ws if training else None)
-        count_launch((2 if ws is not None else 3) if training else 2)
+        if conv_partial is not None and training:
+            # the producing convolution already reduced the batch statistics in its epilogue: finalize + apply only
+            z, mean, invstd, ca, cb = ext.bn_forward(x, weight, bias, running_mean, running_var, residual, training, momentum, eps, relu, None,
+                                                     conv_partial)
+            count_launch(2)
+        else:
+            z, mean, invstd, ca, cb = ext.bn_forward(x, weight, bias, running_mean, running_var, residual, training, momentum, eps, relu,
+                                                     ws if training else None)
+            count_launch((2 if ws is not None else 3) if training else 2)
         ctx.relu, ctx.has_res, ctx.training, ctx.ws = relu, residual is not None, training, ws
         # BN+ReLU without a residual: the backward recomputes the ReLU mask from x (a*x+b > 0), so z is neither saved nor re-read
         maskx = relu and residual is None and _MASKX
@@ -78,7 +84,7 @@ class _BatchNormFn(torch.autograd.Function):
         count_launch(2 if ctx.ws is not None else 3)
         if weight is None:
             dgamma = dbeta = None
-        return dx, dgamma, dbeta, (dres if ctx.has_res else None), None, None, None, None, None, None, None
+        return dx, dgamma, dbeta, (dres if ctx.has_res else None), None, None, None, None, None, None, None, None
 
 
 def batch_norm(x, module, residual=None, relu=False):
@@ -86,5 +92,9 @@ def batch_norm(x, module, residual=None, relu=False):
     if training and module.track_running_stats and module.num_batches_tracked is not None and not getattr(module, "external_counter", False):
         module.num_batches_tracked.add_(1)
     mom = 0.1 if module.momentum is None else module.momentum
+    part = getattr(x, "_psb_stats", None)            # left by the convolution that produced x (ops/conv.py), consumed exactly once
+    if part is not None:
+        x._psb_stats = None
+        part = part.view(-1, 2, x.size(1)) if training else None
     return _BatchNormFn.apply(x, module.weight, module.bias, residual, module.running_mean, module.running_var,
-                              training, mom, module.eps, relu, _workspace(module, x.size(1), x.device))
+                              training, mom, module.eps, relu, _workspace(module, x.size(1), x.device), part)

@@ -15,6 +15,7 @@ from .. import nn as pnn
 from .. import ops as _ops
 from ..models.layerwise import LayerwiseBackwardMixin, StragglerKilled
 from ..utils.obs import PhaseTimer
+from ..utils.data import mark_h2d_issued
 
 
 def resolve_dtype(name: str, device) -> torch.dtype:
@@ -149,7 +150,10 @@ class WorkerCompute:
         self._layerwise_comm, self._layerwise_mode = communicator, mode
 
     def prepare_input(self, x: torch.Tensor, y: torch.Tensor):
+        host = x if (self.device.type == "cuda" and not x.is_cuda) else None
         x = x.to(self.device, non_blocking=True)
+        if host is not None:
+            mark_h2d_issued(host)
         if x.dtype != self.dtype:
             x = x.to(self.dtype)
         if self.channels_last and x.dim() == 4:
@@ -180,6 +184,7 @@ class WorkerCompute:
             buf[0].copy_(x, non_blocking=True)
             buf[1].copy_(y, non_blocking=True)
             buf[2].record(cs)
+            mark_h2d_issued(x, cs)
         self._staged = (x.data_ptr(), y.data_ptr(), i)
 
     def _take_staged(self, x, y):
@@ -207,6 +212,8 @@ class WorkerCompute:
             self._capture(x, y)
         self._static_x.copy_(x, non_blocking=True)       # H2D from the loader's pinned buffer, or D2D from the staged copy
         self._static_y.copy_(y, non_blocking=True)
+        if not x.is_cuda:
+            mark_h2d_issued(x)
         self._graph.replay()
         _ops.count_launch(self.graph_launches)
         return self._static_loss, self._static_logits

@@ -15,6 +15,7 @@ forced by running on one 8×B200 box with no network:
 """
 from __future__ import annotations
 
+import collections
 import os
 from typing import Optional, Tuple
 
@@ -102,10 +103,16 @@ class BatchLoader:
         self.mean = torch.tensor(mean).view(1, -1, 1, 1)
         self.inv_std = 1.0 / torch.tensor(std).view(1, -1, 1, 1)
         self.pin = pin and torch.cuda.is_available()
-        self._bufs = None
-        self._flip = 0
         self.prefetch = prefetch
-        self._nbuf = max(2, prefetch + 2)
+        # Pinned output buffers are a POOL with completion tracking, not a blind ring: a buffer goes back to the free list only after the
+        # consumer has moved `hold` batches past it AND the CUDA event recorded after its host->device copy (mark_h2d_issued) has
+        # completed.  The consumer keeps at most `hold` batches (the current one and the look-ahead the worker stages early).
+        self.hold = 2
+        self._nbuf = self.hold + max(prefetch, 0) + 2
+        self._pool = None
+        self._free = None
+        self._outstanding = collections.deque()
+        self._entry_of = {}
         try:
             from ..ops import host_ext
             self._native = host_ext.get() if out_dtype == torch.float32 else None
@@ -117,16 +124,45 @@ class BatchLoader:
         return n // self.batch_size if self.drop_last else (n + self.batch_size - 1) // self.batch_size
 
     def _out_buffers(self, b):
+        """A free pinned (images, labels) pair for a batch of ``b`` samples; blocks until the consumer has retired one."""
         if not self.pin:
             return None
-        if self._bufs is None or self._bufs[0][0].size(0) != b:
+        if self._pool is None or self._pool[0][0].size(0) < b:
+            import queue
             c, h, w = self.dataset.images.shape[1:]
-            mk = lambda: (torch.empty(b, c, h, w, dtype=self.out_dtype).contiguous(
+            n = max(b, self.batch_size)
+            mk = lambda: (torch.empty(n, c, h, w, dtype=self.out_dtype).contiguous(
                 memory_format=torch.channels_last if self.channels_last else torch.contiguous_format).pin_memory(),
-                torch.empty(b, dtype=torch.int64).pin_memory())
-            self._bufs = [mk() for _ in range(self._nbuf)]
-        self._flip = (self._flip + 1) % self._nbuf
-        return self._bufs[self._flip]
+                torch.empty(n, dtype=torch.int64).pin_memory())
+            self._pool = [mk() for _ in range(self._nbuf)]
+            self._free = queue.Queue()
+            for e in self._pool:
+                self._free.put(e)
+        e = self._free.get()
+        out = e if e[0].size(0) == b else (e[0][:b], e[1][:b])      # a short last batch is a view of a full-size buffer
+        self._entry_of[id(out[0])] = e
+        return out
+
+    def _retire(self, keep: int) -> None:
+        """Return buffers to the free list until at most ``keep`` yielded batches are outstanding."""
+        while len(self._outstanding) > keep:
+            x = self._outstanding.popleft()
+            e = self._entry_of.pop(id(x), None)
+            if e is None:
+                continue
+            ev = getattr(x, "_psb_evt", None)
+            if ev is not None:
+                ev.synchronize()                       # the H2D copy that read this buffer has finished
+                x._psb_evt = None
+            elif torch.cuda.is_available() and torch.cuda.is_initialized():
+                torch.cuda.synchronize()               # consumer did not say when its copy was issued: be safe
+            self._free.put(e)
+
+    def _track(self, item):
+        if self.pin and item is not None and id(item[0]) in self._entry_of:
+            self._retire(self.hold - 1)
+            self._outstanding.append(item[0])
+        return item
 
     def _make_batch_native(self, idx: torch.Tensor):
         """One multi-threaded C++ pass: gather + reflect-pad crop + flip + normalise into the (pinned) output buffer."""
@@ -181,9 +217,10 @@ class BatchLoader:
         n = len(self.dataset)
         order = torch.randperm(n, generator=self.gen) if self.shuffle else torch.arange(n)
         nb = len(self)
+        self._retire(0)                                # batches still held from the previous epoch
         if self.prefetch <= 0 or nb <= 1:
             for i in range(nb):
-                yield self.make_batch(order[i * self.batch_size:(i + 1) * self.batch_size])
+                yield self._track(self.make_batch(order[i * self.batch_size:(i + 1) * self.batch_size]))
         else:
             # background producer: batches are assembled (GIL released inside the C++ pass) while the step runs
             import queue
@@ -209,11 +246,15 @@ class BatchLoader:
                         break
                     if isinstance(item, Exception):
                         raise item
-                    yield item
+                    yield self._track(item)
             finally:
                 stop.set()
                 while not q.empty():
-                    q.get_nowait()
+                    left = q.get_nowait()
+                    if isinstance(left, tuple) and self.pin:       # assembled but never consumed: straight back to the pool
+                        e = self._entry_of.pop(id(left[0]), None)
+                        if e is not None:
+                            self._free.put(e)
         self.dataset.epochs_completed += 1
 
     # reference API ---------------------------------------------------------------------------------------
@@ -232,6 +273,17 @@ class BatchLoader:
 
 
 DataLoader = BatchLoader  # name used by the reference's single_machine.py
+
+
+def mark_h2d_issued(host_tensor: torch.Tensor, stream=None) -> None:
+    """Consumer side of the pinned-buffer protocol: call right after enqueueing the asynchronous host->device copy that reads
+    ``host_tensor`` (a batch yielded by a pinning ``BatchLoader``).  Records a CUDA event on that stream; the loader waits on it
+    before it lets the producer thread overwrite the buffer."""
+    if host_tensor.is_cuda or not host_tensor.is_pinned():
+        return
+    ev = torch.cuda.Event()
+    ev.record(stream if stream is not None else torch.cuda.current_stream())
+    host_tensor._psb_evt = ev
 
 
 def prepare_data(args, rank: int = 0, pin: bool = False, out_dtype=torch.float32, channels_last=False,

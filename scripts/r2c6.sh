@@ -1,0 +1,6 @@
+set -u
+export PYTHONPATH=.
+timeout 600 python -m pytest tests/test_gpu_kernels.py -q -x -k "wgrad" 2>&1 | tail -8
+timeout 600 python scripts/bench_conv2.py > gpurun_out/r2c6_bench_conv2.log 2>&1; tail -12 gpurun_out/r2c6_bench_conv2.log
+PSB200_TC_CONV=1 timeout 300 python bench.py --steps 30 --warmup 5 --skip-e2e 2> gpurun_out/r2c6_bench.err | tail -1 > gpurun_out/r2c6_bench.json
+python -c "import json; d=json.load(open('gpurun_out/r2c6_bench.json')); print('all ours', d['ms_per_step'], 'ms/step', d['config']['conv'], d['final_loss'])" || tail -5 gpurun_out/r2c6_bench.err

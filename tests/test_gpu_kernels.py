@@ -382,17 +382,28 @@ def test_tc_conv_residual_epilogue(ext):
 
 @pytest.mark.parametrize("shape", [  # NB, Cin, H, W, Cout, R, stride, pad
     (8, 128, 16, 16, 128, 3, 1, 1), (4, 64, 32, 32, 64, 3, 1, 1), (16, 256, 8, 8, 256, 3, 1, 1), (32, 512, 4, 4, 512, 3, 1, 1),
-    (8, 64, 32, 32, 128, 3, 2, 1), (8, 128, 16, 16, 256, 1, 2, 0), (4, 128, 16, 16, 64, 3, 1, 1), (3, 64, 14, 14, 64, 3, 1, 1)])
-def test_tc_conv_wgrad(ext, shape):
-    """tcgen05 weight gradient (MN-major operands, split-K + fp32 vector reductions) vs the fp32 autograd reference."""
+    (8, 64, 32, 32, 128, 3, 2, 1), (8, 128, 16, 16, 256, 1, 2, 0), (4, 128, 16, 16, 64, 3, 1, 1), (3, 64, 14, 14, 64, 3, 1, 1),
+    (5, 64, 8, 8, 128, 3, 1, 1), (2, 64, 24, 40, 64, 3, 1, 1), (7, 128, 8, 16, 128, 3, 1, 1)])
+@pytest.mark.parametrize("algo", [0, -1])
+def test_tc_conv_wgrad(ext, shape, algo):
+    """tcgen05 weight gradient vs the fp32 autograd reference.  algo 0 = per-tap kernel (MN-major operands, split-K + fp32 vector reductions),
+    -1 = auto: the tap-sharing halo kernel (one dY tile + one X patch per 128 pixels, three taps per MMA through shifted windows) on
+    3x3/s1 maps of at least 8x8, the per-tap kernel elsewhere."""
     NB, Cin, H, W, Cout, R, st, pad = shape
+    ext.tc_set_wgrad_algo(algo)
     torch.manual_seed(0)
     x = (torch.randn(NB, Cin, H, W, device="cuda") * 0.5).to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
-    Ho = (H + 2 * pad - R) // st + 1
-    dy = (torch.randn(NB, Cout, Ho, Ho, device="cuda") * 0.1).to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
+    Ho, Wo = (H + 2 * pad - R) // st + 1, (W + 2 * pad - R) // st + 1
+    dy = (torch.randn(NB, Cout, Ho, Wo, device="cuda") * 0.1).to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
     scratch = torch.zeros(Cout * R * R * Cin, device="cuda")
-    dw = ext.conv_wgrad(dy, x, scratch, R, R, st, pad)
-    torch.cuda.synchronize()
+    try:
+        dw = ext.conv_wgrad(dy, x, scratch, R, R, st, pad)
+        torch.cuda.synchronize()
+        # second call on the same scratch (self-cleaning) must give the same answer
+        dw2 = ext.conv_wgrad(dy, x, scratch, R, R, st, pad)
+        torch.cuda.synchronize()
+    finally:
+        ext.tc_set_wgrad_algo(-1)
     assert ext.tc_error() == 0
     assert scratch.abs().max().item() == 0, "scratch must be left zeroed"
     w = torch.zeros(Cout, Cin, R, R, device="cuda", requires_grad=True)
@@ -400,8 +411,6 @@ def test_tc_conv_wgrad(ext, shape):
     ref = w.grad
     err = (dw.float() - ref).abs().max().item()
     assert dw.shape == ref.shape and err <= 0.02 * max(1.0, ref.abs().max().item()), (shape, err, ref.abs().max().item())
-    # second call on the same scratch (self-cleaning) gives the same answer
-    dw2 = ext.conv_wgrad(dy, x, scratch, R, R, st, pad)
     assert (dw2.float() - dw.float()).abs().max().item() <= 0.02 * max(1.0, ref.abs().max().item())
 
 
@@ -543,7 +552,8 @@ def test_weight_transpose_flip(ext):
 def test_conv_autograd_all_passes_ours(ext, cfg):
     """nn.Conv2d forward + both gradients on our kernels only (no library fallback may be logged), vs fp32 autograd."""
     from ps_pytorch_b200 import nn as pnn
-    from ps_pytorch_b200.nn import backend as B
+    import sys
+    B = sys.modules["ps_pytorch_b200.nn.backend"]
     Cin, Cout, HW, st = cfg
     torch.manual_seed(0)
     conv = pnn.Conv2d(Cin, Cout, 3, st, 1, bias=False).cuda().to(torch.bfloat16).to(memory_format=torch.channels_last)
@@ -562,3 +572,76 @@ def test_conv_autograd_all_passes_ours(ext, cfg):
     assert (y.float() - yr).abs().max().item() <= 0.02 * max(1.0, yr.abs().max().item())
     assert (x.grad.float() - xr.grad).abs().max().item() <= 0.03 * max(1.0, xr.grad.abs().max().item())
     assert (conv.weight.grad.float() - wr.grad).abs().max().item() <= 0.03 * max(1.0, wr.grad.abs().max().item())
+
+
+@pytest.mark.parametrize("cin,planes,stride", [(64, 64, 1), (64, 128, 2), (256, 512, 2)])
+def test_basic_block_skip_gradient_fused_in_dgrad(ext, cin, planes, stride):
+    """The skip-connection gradient is parked by stash_grad and added inside conv1's dgrad epilogue: the block's input gradient must
+    match an fp32 reference of the same block (identity and down-sampling shortcuts)."""
+    import copy
+    from ps_pytorch_b200 import nn as pnn
+    from ps_pytorch_b200.models.resnet import BasicBlock
+    torch.manual_seed(0)
+    blk = BasicBlock(cin, planes, stride).cuda()
+    ref = copy.deepcopy(blk).float()
+    blk = blk.to(torch.bfloat16).to(memory_format=torch.channels_last)
+    from ps_pytorch_b200.ops import conv as C
+    hw = 16
+    x0 = torch.randn(8, cin, hw, hw, device="cuda").to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
+    g = None
+    grads, outs = [], []
+    for fused in (True, False):
+        C.set_skip_fusion(fused)
+        try:
+            x = x0.clone().requires_grad_(True)
+            blk.zero_grad()
+            with pnn.backend("sm100"):
+                y = blk(x)
+                if g is None:
+                    g = torch.randn_like(y)
+                y.backward(g)
+            torch.cuda.synchronize()
+        finally:
+            C.set_skip_fusion(True)
+        grads.append(x.grad.float()); outs.append(y.float())
+    assert ext.tc_error() == 0
+    xr = x0.float().requires_grad_(True)
+    with pnn.backend("library"):
+        yr = ref(xr)
+        yr.backward(g.float())
+    # (a) fused vs autograd's separate accumulate: same kernels, only the final add differs (fp32 in the epilogue vs a bf16 add)
+    d = (grads[0] - grads[1]).abs().max().item()
+    assert d <= 0.02 * max(1.0, grads[1].abs().max().item()), d
+    assert torch.equal(outs[0], outs[1])
+    # (b) against the fp32 block: bf16 activations through two BatchNorms, so compare in the Frobenius norm
+    rel = ((grads[0] - xr.grad).norm() / xr.grad.norm()).item()
+    assert rel <= 0.08, rel
+    assert ((outs[0] - yr).norm() / yr.norm()).item() <= 0.05
+
+
+@pytest.mark.parametrize("shape", [(16, 64, 32, 32, 64, 3, 1, 1), (16, 128, 16, 16, 128, 3, 1, 1), (16, 64, 32, 32, 128, 3, 2, 1), (32, 256, 8, 8, 512, 3, 2, 1),
+                                   (8, 64, 32, 32, 128, 1, 2, 0), (3, 64, 16, 8, 64, 3, 1, 1)])
+def test_conv_epilogue_bn_statistics(ext, shape):
+    """BatchNorm batch statistics reduced in the convolution epilogue (butterfly column sums + per-warp rows) must give the same
+    mean / invstd / output as the stand-alone statistics pass over the stored activation, and the rows must come back zeroed."""
+    from ps_pytorch_b200.ops import conv as C
+    NB, Cin, H, W, Cout, R, st, pad = shape
+    torch.manual_seed(0)
+    x = (torch.randn(NB, Cin, H, W, device="cuda") * 0.5 + 0.1).to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
+    w = (torch.randn(Cout, Cin, R, R, device="cuda") * (1.0 / math.sqrt(Cin * R * R))).to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
+    g = (torch.rand(Cout, device="cuda") + 0.5).to(torch.bfloat16)
+    b = torch.randn(Cout, device="cuda").to(torch.bfloat16)
+    buf = torch.zeros(4 * ext.num_sms() * 2 * Cout, device="cuda")
+    for it in range(2):                                   # second round: the buffer must have been left clean
+        y = C.fprop(ext, x, w, None, st, pad, False, None, buf)
+        rm1, rv1 = torch.zeros(Cout, device="cuda"), torch.ones(Cout, device="cuda")
+        z1, m1, i1, _, _ = ext.bn_forward(y, g, b, rm1, rv1, None, True, 0.1, 1e-5, True, None, buf.view(-1, 2, Cout))
+        rm2, rv2 = torch.zeros(Cout, device="cuda"), torch.ones(Cout, device="cuda")
+        z2, m2, i2, _, _ = ext.bn_forward(y, g, b, rm2, rv2, None, True, 0.1, 1e-5, True, None)
+        torch.cuda.synchronize()
+        assert ext.tc_error() == 0
+        assert float(buf.abs().max()) == 0.0
+        assert (m1 - m2).abs().max().item() <= 2e-3 * max(1.0, m2.abs().max().item())
+        assert ((i1 - i2).abs() / i2.abs()).max().item() <= 5e-3
+        assert (z1.float() - z2.float()).abs().max().item() <= 0.05
+        assert (rv1 - rv2).abs().max().item() <= 1e-2 and (rm1 - rm2).abs().max().item() <= 1e-3

@@ -132,3 +132,41 @@ def test_prometheus_metrics_endpoint():
     assert 'psb200_step{rank="3"} 8.0' in body and 'psb200_loss{rank="3"} 0.2' in body
     assert 'psb200_pushed_megabytes_total{rank="3"} 3.0' in body
     assert not MetricsExporter(0, 0).on
+
+
+def test_pinned_pool_never_overwrites_a_held_or_in_flight_batch(monkeypatch):
+    """the loader's pinned buffers are a pool with completion tracking.  A consumer that holds the current batch and
+    the look-ahead, and whose H2D copies complete late, must never see a buffer rewritten under it (CPU model: pin_memory patched out,
+    the 'event' is a fake whose synchronize() marks the copy as done)."""
+    import torch
+    from ps_pytorch_b200.utils import data as D
+    monkeypatch.setattr(torch.Tensor, "pin_memory", lambda self: self)
+    ds = D.synthetic_dataset("Cifar10", 16 * 23 + 5)
+    ld = D.BatchLoader(ds, 16, shuffle=True, augment=True, seed=3, pin=False, prefetch=2)
+    ld.pin = True                                   # no CUDA here: exercise the pool logic itself
+
+    class FakeEvent:
+        def __init__(self, key, log):
+            self.key, self.log = key, log
+
+        def synchronize(self):
+            self.log.add(self.key)
+
+    synced = set()
+    for epoch in range(2):
+        held = []                                   # (tensor, snapshot, batch id)
+        it = iter(ld)
+        nxt = next(it, None)
+        i = 0
+        while nxt is not None:
+            cur = nxt
+            cur[0]._psb_evt = FakeEvent((epoch, i), synced)      # "H2D copy enqueued"
+            held.append((cur[0], cur[0].clone(), (epoch, i)))
+            nxt = next(it, None)                    # look-ahead, as DistributedWorker.train does
+            for t, snap, key in held:
+                if key not in synced:               # copy not complete yet: the buffer must be untouched
+                    assert torch.equal(t, snap), ("buffer of batch %s rewritten before its copy completed" % (key,))
+            held = [h for h in held if h[2] not in synced]
+            i += 1
+        assert i == len(ld)
+    assert len(ld._pool) == ld.hold + 2 + 2
