@@ -46,7 +46,9 @@ class ResNet18(nn.Module):
         return self.linear(F.avg_pool2d(out, 4).flatten(1))
 
 
-def bench(a, rank, local, world):
+def run(a, rank, local, world, use_graph=True):
+    """Times the baseline; returns the result dict on rank 0 (None elsewhere).  The caller owns the default process group.
+    ``use_graph``: capture the step (NCCL collectives included) in a CUDA graph like the product does; falls back to eager if capture fails."""
     dev = torch.device("cuda", local)
     torch.backends.cudnn.benchmark = True
     nccl = dist.new_group(backend="nccl") if world > 1 else None
@@ -62,6 +64,7 @@ def bench(a, rank, local, world):
     x = torch.randn(B, 3, 32, 32, device=dev, dtype=torch.bfloat16).contiguous(memory_format=torch.channels_last)
     y = torch.randint(0, 10, (B,), device=dev)
     lr, mu = 0.1, 0.9
+    zero_g = [torch.zeros_like(p) for p in params] if (world > 1 and not is_worker) else None
 
     def step(first):
         if is_worker:
@@ -70,8 +73,11 @@ def bench(a, rank, local, world):
             loss = F.cross_entropy(model(x).float(), y)
             loss.backward()
         if world > 1:
-            for p in params:                                  # per-layer push (reduce to the PS)
-                g = p.grad if is_worker else torch.zeros_like(p)
+            for i, p in enumerate(params):                    # per-layer push (reduce to the PS)
+                if is_worker:
+                    g = p.grad
+                else:
+                    g = zero_g[i].zero_()
                 dist.reduce(g, dst=0, group=nccl)
                 if is_ps:
                     p.grad = g
@@ -91,12 +97,41 @@ def bench(a, rank, local, world):
     for i in range(max(3, a.warmup)):
         step(i == 0)
     torch.cuda.synchronize()
+    graph = None
+    if use_graph:
+        try:
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                step(False)
+            torch.cuda.current_stream().wait_stream(side)
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                step(False)
+            graph = g
+        except Exception:                      # noqa: BLE001  (e.g. NCCL capture unsupported): eager, as the reference would run
+            graph = None
+            torch.cuda.synchronize()
+    ok = torch.tensor([1 if graph is not None else 0])
+    if world > 1:
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)          # all ranks must take the same path
+    if int(ok[0]) == 0:
+        graph = None
+
+    def one():
+        if graph is not None:
+            graph.replay()
+        else:
+            step(False)
+    for _ in range(2):
+        one()
+    torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(a.steps):
-        step(False)
+        one()
     e1.record()
     torch.cuda.synchronize()
     if world > 1:
@@ -104,13 +139,21 @@ def bench(a, rank, local, world):
     t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    if rank != 0:
+        return None
+    ms = float(t[0])
+    return {"impl": "nccl-baseline", "metric": "ResNet-18/CIFAR-10 images/sec (whole box, device-timed, max over ranks)",
+            "value": nworkers * B * a.steps / (ms * 1e-3), "unit": "images/s", "n_gpus": world, "steps": a.steps,
+            "warmup": a.warmup, "ms_per_step": ms / a.steps, "higher_is_better": True, "scaling": "weak", "dtype": "bf16",
+            "data": "synthetic", "cuda_graph": graph is not None,
+            "config": {"model": "ResNet18", "global_batch": nworkers * B,
+                       "parallelism": "1 PS + %d workers, NCCL reduce/broadcast per layer, stock torch.nn" % nworkers}}
+
+
+def bench(a, rank, local, world):
+    out = run(a, rank, local, world, use_graph=not getattr(a, "no_graph", False))
     if rank == 0:
-        ms = float(t[0])
-        print(json.dumps({"impl": "nccl-baseline", "metric": "ResNet-18/CIFAR-10 images/sec (whole box, device-timed, max over ranks)",
-                          "value": nworkers * B * a.steps / (ms * 1e-3), "unit": "images/s", "n_gpus": world, "steps": a.steps,
-                          "warmup": a.warmup, "ms_per_step": ms / a.steps, "higher_is_better": True, "scaling": "weak", "dtype": "bf16",
-                          "data": "synthetic", "config": {"model": "ResNet18", "global_batch": nworkers * B,
-                                                          "parallelism": "1 PS + %d workers, NCCL reduce/broadcast per layer, stock torch.nn" % nworkers}}))
+        print(json.dumps(out))
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()

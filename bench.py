@@ -53,6 +53,9 @@ def parse():
     ap.add_argument("--optimizer", type=str, default="sgd")
     ap.add_argument("--skip-e2e", action="store_true")
     ap.add_argument("--no-stage", dest="stage", action="store_false", help="do not prefetch the next batch's H2D copy")
+    ap.add_argument("--global-batch", type=int, default=0, help="strong scaling: fix the GLOBAL batch (per-worker batch = global / workers)")
+    ap.add_argument("--no-baseline", action="store_true", help="skip the in-job NCCL-baseline measurement")
+    ap.add_argument("--num-aggregate", type=int, default=0, help="K of P (default: all workers)")
     return ap.parse_args()
 
 
@@ -145,18 +148,27 @@ def main():
     from ps_pytorch_b200.engine import PSJob
     from ps_pytorch_b200.config import input_shape_for, num_classes_for
     colocate = not a.no_colocate
+    nw_expected = world if (colocate or world == 1 or a.topology == "sharded") else world - 1
+    if a.global_batch:
+        assert a.global_batch % nw_expected == 0, "--global-batch must divide by the number of workers"
+        a.batch_size = a.global_batch // nw_expected
     job = PSJob(network=a.network, dataset=a.dataset, batch_size=a.batch_size, device=dev, dtype="bf16", lr=0.1, momentum=0.9,
                 optimizer=a.optimizer, topology=a.topology, colocate=colocate, grad_dtype=a.grad_dtype, overlap=a.overlap,
-                cuda_graph=not a.no_graph, backend=a.backend)
+                cuda_graph=not a.no_graph, backend=a.backend, num_aggregate=a.num_aggregate or None)
     nworkers = job.comm.num_workers
     c, h, w = input_shape_for(a.dataset)
     B = a.batch_size
-    # synthetic data of the named shape, resident in PINNED host memory; 8 distinct batches rotate so no step re-reads
-    # the previous step's input (and the ~3 GB/step activation working set is >> the 126 MB L2 anyway)
+    ncls = num_classes_for(a.dataset)
+    # Synthetic data of the named shape, resident in PINNED host memory; 8 distinct batches rotate so no step re-reads the previous
+    # step's input (and the ~3 GB/step activation working set is >> the 126 MB L2 anyway).  The images are CLASS-SEPARABLE (a fixed
+    # random template per class, shared by all ranks, plus unit noise), so the loss has to fall well below ln(#classes): a dead
+    # broadcast, a skipped reduce or diverging replicas would show up in first_loss/final_loss and in the replica check below.
     nb = 8
+    tg = torch.Generator().manual_seed(7)
+    templates = torch.randn(ncls, c, h, w, generator=tg)
     g = torch.Generator().manual_seed(1234 + rank)
-    xs = [torch.randn(B, c, h, w, generator=g).to(torch.bfloat16).contiguous(memory_format=torch.channels_last).pin_memory() for _ in range(nb)]
-    ys = [torch.randint(0, num_classes_for(a.dataset), (B,), generator=g).pin_memory() for _ in range(nb)]
+    ys = [torch.randint(0, ncls, (B,), generator=g).pin_memory() for _ in range(nb)]
+    xs = [(0.7 * templates[y] + torch.randn(B, c, h, w, generator=g)).to(torch.bfloat16).contiguous(memory_format=torch.channels_last).pin_memory() for y in ys]
     h2d = xs[0].numel() * xs[0].element_size() + ys[0].numel() * 8 if job.is_worker else 0
 
     def run(nsteps, read_loss):
@@ -193,7 +205,8 @@ def main():
     sampler = ClockSampler()
     if rank == 0:
         sampler.start()                   # nvidia-smi needs ~1 s to start streaming: launch it before the warm-up
-    run(max(a.warmup, 3), False)          # untimed warm-up (includes CUDA-graph capture)
+    first = run(1, True)                  # step 1 (also the CUDA-graph capture): the loss of the untrained net, ~ln(#classes)
+    run(max(a.warmup, 3) - 1, False)      # rest of the untimed warm-up
     barrier()
     if hasattr(job.comm, "check_error"):
         job.comm.check_error()
@@ -219,12 +232,63 @@ def main():
                "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4 if job.is_worker else 0}
     if hasattr(job.comm, "check_error"):
         job.comm.check_error()
+    # ---- exposed communication, measured directly: CUDA events around wait-weights / push / reduce+update+broadcast (engine.PSJob.time_comm)
+    exposed = None
+    if hasattr(job, "time_comm"):
+        job.time_comm(True)
+        loss2 = run(min(a.steps, 20), False)
+        barrier()
+        cm = job.comm_ms_per_step()
+        job.time_comm(False)
+        t = torch.tensor([cm if cm is not None else 0.0], dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        exposed = float(t[0])
+        loss = loss2 if loss2 is not None else loss
+    # ---- self-verification: every replica must hold exactly the bf16 rounding of rank 0's fp32 master, and the loss must have fallen
+    barrier()
+    check = {}
+    if job.worker is not None:
+        rep = job.worker.compute.weights.flat
+        csum = int(rep.view(torch.int16).to(torch.int64).sum().item())
+        cabs = float(rep.float().abs().sum().item())
+    else:
+        csum, cabs = None, None
+    sums = [None] * world
+    if world > 1:
+        dist.all_gather_object(sums, (csum, cabs))
+    else:
+        sums = [(csum, cabs)]
+    if rank == 0:
+        m = job.master
+        want = m.master.flat.to(torch.bfloat16)
+        wsum = int(want.view(torch.int16).to(torch.int64).sum().item())
+        have = [s_[0] for s_ in sums if s_[0] is not None]
+        check = {"replicas": len(have), "replicas_identical": len(set(have)) == 1, "replicas_equal_bf16_of_master": all(v == wsum for v in have),
+                 "weight_abs_sum": sums[-1][1]}
     lt = torch.tensor([float(loss) if loss is not None else float("nan")])
+    lf = float(first) if first is not None else float("nan")
+    if world > 1:                             # a pure-PS rank 0 (--no-colocate) has no loss of its own: take worker 1's
+        both = [None] * world
+        dist.all_gather_object(both, (lf, float(lt[0])))
+        good = [b for b in both if b[1] == b[1]]
+        lf, lt = good[0][0], torch.tensor([good[0][1]])
+    nccl_base = None
+    if not a.no_baseline and a.network == "ResNet18" and a.dataset == "Cifar10" and not a.global_batch:
+        try:
+            job.close()
+            job = None
+            sys.path.insert(0, os.path.join(ROOT, "baseline"))
+            import nccl_ps
+            nccl_base = nccl_ps.run(a, rank, local, world, use_graph=(world == 1))
+        except Exception as e:  # noqa: BLE001
+            nccl_base = {"error": repr(e)[:200]}
     if rank == 0:
         value = nworkers * B * a.steps / (ms * 1e-3)
         out = {"metric": "ResNet-18/CIFAR-10 images/sec (whole box, device-timed, max over ranks)" if a.network == "ResNet18" else a.network + " images/sec",
                "value": value, "unit": "images/s", "n_gpus": world, "steps": a.steps, "warmup": a.warmup, "ms_per_step": ms / a.steps,
-               "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic (random images of the dataset shape, random-init weights)",
+               "higher_is_better": True, "scaling": "strong" if a.global_batch else "weak", "vs_baseline": None, "dtype": "bf16",
+               "data": "synthetic (class-separable images of the dataset shape: per-class template + noise; random-init weights)",
                "impl": "ours",
                "config": {"model": a.network, "dataset_shape": "%s %dx%dx%d" % (a.dataset, c, h, w), "global_batch": nworkers * B,
                           "per_worker_batch": B, "seq_len": None,
@@ -235,9 +299,13 @@ def main():
                           "conv": "tcgen05 implicit-GEMM (ours)" if _tc_conv() else "cuDNN (library); all other layers + PS kernels ours",
                           "l2": "inputs rotate over 8 distinct pinned host batches; per-step activation working set (~3 GB) >> 126 MB L2"},
                "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "wall_ms_per_step": wall_ms / a.steps,
-               "final_loss": float(lt[0])}
+               "first_loss": lf, "final_loss": float(lt[0]), "loss_fell": bool(float(lt[0]) < 0.8 * lf) if lf == lf else None,
+               "replica_check": check, "exposed_comm_ms": exposed,
+               "nccl_baseline": nccl_base,
+               "vs_nccl_baseline": (value / nccl_base["value"]) if (nccl_base and nccl_base.get("value")) else None}
         print(json.dumps(out))
-    job.close()
+    if job is not None:
+        job.close()
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()

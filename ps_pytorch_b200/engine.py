@@ -71,6 +71,35 @@ class PSJob:
         self.batch_size = batch_size
         self.step_id = 0
         self.last_loss = None
+        self._comm_events = None          # set by time_comm(True): CUDA-event pairs around the communication kernels of every step
+
+    # ---- exposed communication, measured directly ------------------------------------------------------------------------
+    def time_comm(self, on: bool = True) -> None:
+        """Bracket the communication kernels of every following step (weights wait, gradient push, PS reduce+update+broadcast) with
+        CUDA events on the step's stream.  Those kernels run serialised with the compute on that stream, so the bracketed device time —
+        spins included — IS the communication the step is exposed to."""
+        self._comm_events = [] if on else None
+
+    def comm_ms_per_step(self) -> Optional[float]:
+        """Mean exposed communication per step (ms) on this rank since ``time_comm(True)``; call after a device synchronize."""
+        ev = self._comm_events
+        if not ev:
+            return None
+        steps = max(1, len({s for s, _, _ in ev}))
+        return sum(a.elapsed_time(b) for _, a, b in ev) / steps
+
+    def _bracket(self):
+        if self._comm_events is None or self.device.type != "cuda":
+            return None
+        e = torch.cuda.Event(enable_timing=True)
+        e.record()
+        return e
+
+    def _close_bracket(self, e0):
+        if e0 is not None:
+            e1 = torch.cuda.Event(enable_timing=True)
+            e1.record()
+            self._comm_events.append((self.step_id, e0, e1))
 
     def step(self, x_host: Optional[torch.Tensor] = None, y_host: Optional[torch.Tensor] = None):
         """One PS iteration.  Returns this rank's loss tensor (device, async) or None on a pure-PS rank."""
@@ -79,13 +108,21 @@ class PSJob:
         if m is not None and self.rank == 0 or (m is not None and self.topology == "sharded"):
             m.async_bcast_step()
         if w is not None:
+            e = self._bracket()
             w.sync_fetch_step()
+            self._close_bracket(e)
             w.update_step()
             loss, _ = w.compute.train_step(x_host, y_host, w.cur_step)
+            e = self._bracket()
+            for b in w.compute.captured_buckets:
+                self.comm.mark_pushed(b)
             w._send_grads()
+            self._close_bracket(e)
             self.last_loss = loss
         if m is not None:
+            e = self._bracket()
             self.comm.ps_reduce_update(m.cur_step, self.k, m.optimizer, m.master, **m._ru_kwargs())
+            self._close_bracket(e)
             if m.lowp is not m.master and not getattr(self.comm, "fused_lowp", False):
                 m.lowp.flat.copy_(m.master.flat)
             m.cur_step += 1

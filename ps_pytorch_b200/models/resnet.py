@@ -99,7 +99,7 @@ class ResNet(tnn.Module):
         return tnn.Sequential(*layers)
 
     def forward(self, x):
-        out = self.bn1(self.conv1(x), relu=True)
+        out = self.bn1(self.conv1(x, bn=self.bn1), relu=True)
         if self.imagenet:
             out = F.max_pool2d(out, 3, 2, 1)
         out = self.layer4(self.layer3(self.layer2(self.layer1(out))))

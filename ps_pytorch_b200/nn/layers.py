@@ -27,13 +27,18 @@ class Conv2d(nn.Conv2d):
         if use_sm100(x):
             from ..ops import conv as _conv
             why = _conv.unsupported_reason(x, self.weight, self.stride, self.padding, self.dilation, self.groups)
-            if why is None:
+            stem = why is not None and _conv.stem_supported(x, self.weight, self.stride, self.padding, self.dilation, self.groups)
+            if why is None or stem:
                 stats = None
                 if bn is not None and not relu and (bn.training or not bn.track_running_stats) and torch.is_grad_enabled():
                     from ..ops import norm as _norm
                     if x.dtype == torch.bfloat16 and bn.num_features == self.out_channels and self.out_channels % 8 == 0 \
                             and (self.out_channels // 8) & (self.out_channels // 8 - 1) == 0 and self.out_channels // 8 <= 256:
                         stats = _conv.stats_buffer(self, self.out_channels, x.device)
+                if stem:
+                    if grad_holder is not None:
+                        grad_holder.consumed = True
+                    return _conv.stem_conv2d(x, self.weight, self.bias, relu, stats)
                 return _conv.conv2d(x, self.weight, self.bias, self.stride, self.padding, relu, grad_holder, stats)
             note_fallback("conv2d", why)
         if grad_holder is not None:

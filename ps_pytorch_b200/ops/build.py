@@ -15,7 +15,7 @@ CSRC = os.path.join(HERE, "csrc")
 BUILD = os.path.join(HERE, "_build")
 
 CUDA_SOURCES = ["bindings.cpp", "arena.cpp", "optim_kernels.cu", "comm_kernels.cu", "bn_kernels.cu", "elementwise.cu",
-                "gemm_tcgen05.cu", "conv2_tcgen05.cu", "wgrad_halo_tcgen05.cu", "gemm_bindings.cpp", "stem_wgrad.cu"]
+                "gemm_tcgen05.cu", "conv2_tcgen05.cu", "wgrad_halo_tcgen05.cu", "wgrad2_tcgen05.cu", "stem_tcgen05.cu", "gemm_bindings.cpp", "stem_wgrad.cu"]
 HOST_SOURCES = ["host_ext.cpp"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "--use_fast_math", "-std=c++17",
               "--expt-relaxed-constexpr", "-Xptxas", "-v"]

@@ -115,15 +115,62 @@ def stats_buffer(module, cout, device):
     return buf
 
 
+# ---- dgrad operands ---------------------------------------------------------------------------------------------------------------
+# The data gradient needs the filter as [Cin][R][S][Cout] (rotated by 180 degrees for the halo form).  Transposing per layer costs a
+# 4-9 us launch in front of every dgrad (measured: d_ours vs d_pair_kernel_only, profiles/run25_conv_per_layer.md).  A training loop that
+# owns the step (WorkerCompute) instead opts in to ONE batched transpose of all registered weights at the start of each step:
+# enable_batched_dgrad_operands(True) + refresh_dgrad_operands() before every backward.
+_wt_reg = {}            # id(weight) -> [weight, flip, buf, data_ptr]
+_wt_plan = None         # (table, n, blocks, number of registered entries)
+_wt_batched = False
+_wt_fresh = False
+
+
+def enable_batched_dgrad_operands(on: bool) -> None:
+    global _wt_batched, _wt_fresh, _wt_plan
+    _wt_batched, _wt_fresh = bool(on), False
+    _wt_reg.clear()                  # a new owner (one model per process): forget the previous model's filters
+    _wt_plan = None
+
+
+def refresh_dgrad_operands() -> None:
+    """One launch: re-transpose every registered conv weight (call once per step, after the weights of the step are in place)."""
+    global _wt_plan, _wt_fresh
+    if not _wt_batched or not _wt_reg:
+        _wt_fresh = False
+        return
+    ext = require()
+    ents = list(_wt_reg.values())
+    if _wt_plan is None or _wt_plan[3] != len(ents) or any(e[0].data_ptr() != e[3] for e in ents):
+        for e in ents:
+            e[3] = e[0].data_ptr()
+        table, meta = ext.weight_transpose_plan([e[0].detach() for e in ents], [e[2] for e in ents], [int(e[1]) for e in ents])
+        _wt_plan = (table, int(meta[0]), int(meta[1]), len(ents))
+    ext.weight_transpose_run(_wt_plan[0], _wt_plan[1], _wt_plan[2])
+    count_launch()
+    _wt_fresh = True
+
+
+def _dgrad_operand(ext, weight, flip: bool):
+    ent = _wt_reg.get(id(weight)) if _wt_batched else None
+    if ent is not None and ent[1] == flip and _wt_fresh and _wt_plan is not None and _wt_plan[3] == len(_wt_reg) and ent[3] == weight.data_ptr():
+        return ent[2]
+    w = _krsc(weight)
+    count_launch()
+    out = ext.weight_transpose(w.detach(), flip)
+    if _wt_batched and w is weight and weight.is_leaf:          # arena-backed parameter with a stable address: batch it from the next step on
+        _wt_reg[id(weight)] = [weight, flip, out.clone() if ent is None else ent[2], weight.data_ptr()]
+    return out
+
+
 def dgrad(ext, dy, weight, in_h, in_w, stride, pad, residual=None):
     """dX of conv(x, weight, stride, pad) from dY; ``residual`` (shape of dX) is added in the kernel epilogue."""
     r, s = weight.size(2), weight.size(3)
-    w = _krsc(weight)
-    count_launch(2)
+    count_launch()
     if stride == 1 and _halo_ok(in_h, in_w, r, s, 1) and r == s and in_h == dy.size(2) + r - 1 - 2 * pad:
         # dX = conv(dY, rot180(W)^T, pad = R-1-pad): the halo kernel on the transformed filter
-        return ext.conv_fprop(dy, ext.weight_transpose(w, True), None, 1, r - 1 - pad, False, residual)
-    return ext.conv2(dy, ext.weight_transpose(w, False), None, stride, pad, False, residual, True, in_h, in_w)
+        return ext.conv_fprop(dy, _dgrad_operand(ext, weight, True), None, 1, r - 1 - pad, False, residual)
+    return ext.conv2(dy, _dgrad_operand(ext, weight, False), None, stride, pad, False, residual, True, in_h, in_w)
 
 
 class GradHolder:
@@ -158,6 +205,7 @@ def stash_grad(x, holder):
 
 
 _SKIP_FUSION = os.environ.get("PSB200_SKIP_GRAD_FUSION", "1") != "0"
+_WGRAD_SIDE = os.environ.get("PSB200_TC_WGRAD_STREAM", "1") != "0"
 
 
 def set_skip_fusion(on: bool) -> None:
@@ -208,7 +256,21 @@ class _ConvFn(torch.autograd.Function):
                 dx = dx + h.grad.to(dx.dtype)
                 h.grad = None
         if need_dw and weight.size(1) % 64 == 0:
-            dw = ext.conv_wgrad(dy, x, _wgrad_scratch(weight), r, weight.size(3), s, p)
+            # The weight gradient is tensor-bound and nobody needs it until the gradients are pushed, while the next thing on the critical
+            # path after dgrad is a memory-bound BatchNorm backward: issue wgrad on a side stream (fork after dy is ready; WorkerCompute joins
+            # before it gathers the gradients: libconv.join).  Inside a CUDA-graph capture this becomes a fork/join in the graph.
+            from . import libconv as _lc
+            if _WGRAD_SIDE and _lc.enabled():
+                dev = dy.device
+                main, side = torch.cuda.current_stream(dev), _lc._side(dev)
+                side.wait_stream(main)
+                with torch.cuda.stream(side):
+                    dw = ext.conv_wgrad(dy, x, _wgrad_scratch(weight), r, weight.size(3), s, p)
+                _lc._forked[dev] = True
+                for t in (dy, x, dw):
+                    t.record_stream(side)
+            else:
+                dw = ext.conv_wgrad(dy, x, _wgrad_scratch(weight), r, weight.size(3), s, p)
             count_launch(2)
             need_dw = False
         if need_dw:
@@ -217,6 +279,52 @@ class _ConvFn(torch.autograd.Function):
         if ctx.has_bias and ctx.needs_input_grad[2]:
             db = dy.float().sum((0, 2, 3)).to(dy.dtype)
         return dx, dw, db, None, None, None, None, None
+
+
+# ---- network stem (Cin <= 3): im2col rows built by threads, tensor-core forward + weight gradient (csrc/stem_tcgen05.cu) ---------------
+def stem_supported(x, weight, stride, padding, dilation, groups) -> bool:
+    if not _ENABLED or x.requires_grad or groups != 1 or isinstance(padding, str):
+        return False
+    if x.dtype != torch.bfloat16 or weight.dtype != torch.bfloat16 or tuple(dilation) != (1, 1):
+        return False
+    ext = require()
+    return hasattr(ext, "stem_conv") and bool(ext.stem_eligible(x.size(2), x.size(3), x.size(1), weight.size(0), weight.size(2), weight.size(3),
+                                                                int(stride[0]) if stride[0] == stride[1] else 0, int(padding[0]) if padding[0] == padding[1] else -1))
+
+
+class _StemFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, weight, bias, relu, stats):
+        ext = require()
+        x = x.contiguous(memory_format=torch.channels_last)
+        y = ext.stem_conv(x, _krsc(weight), bias, relu, stats)
+        count_launch()
+        ctx.save_for_backward(x, weight, y if relu else None)
+        ctx.relu, ctx.has_bias = relu, bias is not None
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, weight, y = ctx.saved_tensors
+        ext = require()
+        dy = dy.contiguous(memory_format=torch.channels_last)
+        if ctx.relu:
+            dy = ext.relu_backward(dy, y)
+            count_launch()
+        dw = db = None
+        if ctx.needs_input_grad[1]:
+            dw = ext.stem_wgrad_tc(dy, x, _wgrad_scratch(weight))
+            count_launch(2)
+        if ctx.has_bias and ctx.needs_input_grad[2]:
+            db = dy.float().sum((0, 2, 3)).to(dy.dtype)
+        return None, dw, db, None, None
+
+
+def stem_conv2d(x, weight, bias, relu=False, stats=None):
+    y = _StemFn.apply(x, weight, bias, bool(relu), stats)
+    if stats is not None:
+        y._psb_stats = stats
+    return y
 
 
 def conv2d(x, weight, bias, stride, padding, relu=False, grad_holder=None, stats=None):

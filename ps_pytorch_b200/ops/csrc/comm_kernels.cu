@@ -161,6 +161,9 @@ struct RUArgs {
     unsigned long long timeout_ns;
     int advance_step;                     // last CTA bumps *step_ptr and hp->steps
     const void* mc_src;                   // NVLS variant only: multicast mapping of the (symmetric) gradient arenas
+    unsigned long long* sel;              // [kMaxBuckets] published arrival decision per bucket: (step << 16) | (count << 8) | mask
+    int partial_ok;                       // --mode timeout: after timeout_ns proceed with the >= 1 gradients that did arrive
+    long long* abort_w[kMaxPeers];        // --mode kill: abort word of source k's worker (set to the step id for the laggards), or null
 };
 
 // raw wire words of 8 elements from source k (kept packed in registers so that all K loads can be in flight at once)
@@ -199,7 +202,7 @@ __device__ __forceinline__ void accum_raw8(const Raw8& r, float* g) {
 // are replaced by one multimem.ld_reduce through the switch, so the server receives one reduced stream instead of P.
 template <int MODE, bool NVLS = false>
 __global__ void __launch_bounds__(256, 2) reduce_update_kernel(RUArgs a) {
-    __shared__ unsigned s_mask;
+    __shared__ unsigned s_mask, s_cnt;
     const long long step = *a.step_ptr;
     const OptHP hp = *a.hp;
     const bool first = hp.steps == 0;
@@ -207,23 +210,47 @@ __global__ void __launch_bounds__(256, 2) reduce_update_kernel(RUArgs a) {
     const long long stride = (long long)gridDim.x * blockDim.x * 8;
 
     for (int b = a.NB - 1; b >= 0; --b) {          // gradients arrive last-layer-first
+        // ONE arrival decision per (step, bucket) for the whole grid: every CTA polls, the first one that sees `take` arrivals (or, in
+        // timeout mode, the deadline with >= 1 arrival) publishes (step, count, mask) with a CAS and everybody uses the published set —
+        // with K < P different CTAs would otherwise average different subsets of workers in different tiles of the same update.
         if (threadIdx.x == 0) {
-            unsigned mask = 0;
+            const unsigned long long tag = (unsigned long long)step << 16;
             const unsigned long long t0 = globaltimer_ns();
+            unsigned long long v;
+            bool winner = false;
             while (true) {
-                mask = 0;
+                v = *reinterpret_cast<volatile unsigned long long*>(a.sel + b);
+                if ((v >> 16) == (unsigned long long)step) break;                   // already decided
+                unsigned mask = 0;
                 int cnt = 0;
                 for (int k = 0; k < a.P && cnt < a.take; ++k)
                     if (ld_acquire_sys(a.g_ready + k * kMaxBuckets + b) == step) { mask |= 1u << k; ++cnt; }
-                if (cnt >= a.take) break;
-                if (globaltimer_ns() - t0 > a.timeout_ns) { mask = 0; atomicExch((unsigned long long*)a.err, 1ull + (unsigned long long)b); break; }
+                const bool timed = globaltimer_ns() - t0 > a.timeout_ns;
+                if (cnt >= a.take || (timed && a.partial_ok && cnt >= 1)) {
+                    const unsigned long long nv = tag | ((unsigned long long)cnt << 8) | mask;
+                    if (atomicCAS(a.sel + b, v, nv) == v) { v = nv; winner = true; break; }
+                    continue;                                                       // lost the race: read the winner's decision
+                }
+                if (timed) {                                                        // nobody (or, without partial_ok, too few) arrived
+                    atomicExch((unsigned long long*)a.err, 1ull + (unsigned long long)b);
+                    atomicCAS(a.sel + b, v, tag);                                   // publish "failed" (mask 0) so the grid leaves together
+                    v = tag;
+                    break;
+                }
                 __nanosleep(200);
             }
-            s_mask = mask;
+            s_mask = (unsigned)(v & 0xffu);
+            s_cnt = (unsigned)((v >> 8) & 0xffu);
+            if (winner) {
+                __threadfence();
+                for (int k = 0; k < a.P; ++k)                                       // straggler kill: tell the laggards to abandon this step
+                    if (!((v >> k) & 1ull) && a.abort_w[k] != nullptr) st_release_sys(a.abort_w[k], step);
+            }
         }
         __syncthreads();
         const unsigned mask = s_mask;
         if (mask == 0) return;                     // timed out: error word is set, host raises
+        const float inv_div = ((int)s_cnt < a.take) ? 1.f / (float)max(1u, s_cnt) : a.inv_div;     // partial set: mean of what arrived
         for (long long i = a.lo[b] + ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 8; i < a.hi[b]; i += stride) {
             float g[8] = {0, 0, 0, 0, 0, 0, 0, 0};
             if (NVLS) {
@@ -261,17 +288,17 @@ __global__ void __launch_bounds__(256, 2) reduce_update_kernel(RUArgs a) {
             if (hp.kind == 2) {
                 // all-reduce mode (DDP): no optimizer, the averaged gradient itself is stored back to every peer
 #pragma unroll
-                for (int j = 0; j < 8; ++j) wf[j] = g[j] * a.inv_div;
+                for (int j = 0; j < 8; ++j) wf[j] = g[j] * inv_div;
             } else if (hp.kind == 0) {
                 if (hp.momentum != 0.f && !first) ldf(a.s0, x0);
 #pragma unroll
-                for (int j = 0; j < 8; ++j) wf[j] = sgd_update(wf[j], g[j] * a.inv_div, x0[j], hp, first);
+                for (int j = 0; j < 8; ++j) wf[j] = sgd_update(wf[j], g[j] * inv_div, x0[j], hp, first);
                 if (hp.momentum != 0.f) stf(a.s0, x0);
             } else {
                 ldf(a.s0, x0); ldf(a.s1, x1);
                 if (a.s2) ldf(a.s2, x2);
 #pragma unroll
-                for (int j = 0; j < 8; ++j) wf[j] = adam_update(wf[j], g[j] * a.inv_div, x0[j], x1[j], a.s2 ? &x2[j] : nullptr, hp, adam_ss);
+                for (int j = 0; j < 8; ++j) wf[j] = adam_update(wf[j], g[j] * inv_div, x0[j], x1[j], a.s2 ? &x2[j] : nullptr, hp, adam_ss);
                 stf(a.s0, x0); stf(a.s1, x1);
                 if (a.s2) stf(a.s2, x2);
             }
@@ -330,15 +357,21 @@ __global__ void __launch_bounds__(256) bcast_kernel(BcastArgs a) {
     }
 }
 
-// acquire-spin until flags[0..n) >= *step_ptr (weights for this worker's step have landed), with timeout
-__global__ void wait_flag_kernel(const long long* flags, int n, const long long* step_ptr, long long* err, unsigned long long timeout_ns) {
-    if (threadIdx.x >= n) return;
+// acquire-spin until flags[0..n) >= *step_ptr (weights for this worker's step have landed), with timeout.  A worker that fell behind
+// (its gradient missed a K-of-P decision, or it abandoned a step) finds a flag value AHEAD of its own counter: it adopts the server's step
+// (the reference's workers learn the step id from the PS, distributed_worker.py:193-199) — otherwise every later push of this worker
+// would carry a stale step id and be ignored for the rest of the job.
+__global__ void wait_flag_kernel(const long long* flags, int n, long long* step_ptr, long long* err, unsigned long long timeout_ns) {
     const long long want = *step_ptr;
+    __syncthreads();
+    if (threadIdx.x >= n) return;
     const unsigned long long t0 = globaltimer_ns();
-    while (ld_acquire_sys(flags + threadIdx.x) < want) {
+    long long f;
+    while ((f = ld_acquire_sys(flags + threadIdx.x)) < want) {
         if (globaltimer_ns() - t0 > timeout_ns) { atomicExch((unsigned long long*)err, 100ull + threadIdx.x); return; }
         __nanosleep(100);
     }
+    if (threadIdx.x == 0 && f > want) *step_ptr = f;
 }
 
 __global__ void add_step_kernel(long long* p, long long v) { *p += v; }
@@ -369,8 +402,11 @@ void reduce_update(std::vector<int64_t> src, std::vector<int64_t> src_scale, int
                    int64_t g_ready, int64_t step_ptr, std::vector<int64_t> lo, std::vector<int64_t> hi, at::Tensor w,
                    c10::optional<at::Tensor> s0, c10::optional<at::Tensor> s1, c10::optional<at::Tensor> s2, int64_t hp,
                    std::vector<int64_t> dst, int64_t mc_dst, std::vector<int64_t> w_ready, int64_t counters, int64_t err,
-                   double timeout_s, bool advance_step) {
+                   double timeout_s, bool advance_step, int64_t sel, bool partial_ok, std::vector<int64_t> abort_words) {
     RUArgs a{};
+    TORCH_CHECK(sel != 0, "reduce_update needs the per-bucket decision words");
+    a.sel = (unsigned long long*)P(sel); a.partial_ok = partial_ok ? 1 : 0;
+    for (size_t k = 0; k < kMaxPeers; ++k) a.abort_w[k] = k < abort_words.size() ? (long long*)P(abort_words[k]) : nullptr;
     TORCH_CHECK(src.size() <= kMaxPeers && dst.size() <= kMaxPeers + 1 && lo.size() <= kMaxBuckets && lo.size() == hi.size());
     a.P = (int)src.size(); a.take = (int)take; a.mode = (int)mode; a.inv_div = (float)inv_div;
     for (size_t k = 0; k < src.size(); ++k) { a.src[k] = P(src[k]); a.src_scale[k] = (const uint8_t*)P(k < src_scale.size() ? src_scale[k] : 0); }
@@ -416,7 +452,7 @@ void bcast(int64_t src, std::vector<int64_t> dst, int64_t mc_dst, int64_t nbytes
 
 void wait_flag(int64_t flags, int64_t n, int64_t step_ptr, int64_t err, double timeout_s) {
     TORCH_CHECK(n >= 1 && n <= kMaxBuckets);
-    wait_flag_kernel<<<1, 32, 0, at::cuda::getCurrentCUDAStream()>>>((const long long*)P(flags), (int)n, (const long long*)P(step_ptr),
+    wait_flag_kernel<<<1, 32, 0, at::cuda::getCurrentCUDAStream()>>>((const long long*)P(flags), (int)n, (long long*)P(step_ptr),
                                                                       (long long*)P(err), (unsigned long long)(timeout_s * 1e9));
     C10_CUDA_KERNEL_LAUNCH_CHECK();
 }

@@ -299,6 +299,34 @@ __global__ void weight_transpose_kernel(const __nv_bfloat16* __restrict__ w, __n
         if (co < Cout && ci < Cin) out[((long long)ci * T + to) * Cout + co] = tile[threadIdx.x][i];
     }
 }
+// All convolution weights of a model in ONE launch (per step: the dgrad operands of every layer, ~20 launches -> 1).
+// table[i] = {src, dst, Cout, T, Cin, flip, first_block, blocks_x, blocks_y}; block -> tensor by linear search over n <= 256 entries.
+struct WtEntry { const __nv_bfloat16* src; __nv_bfloat16* dst; int Cout, T, Cin, flip, first_block, bx, by, pad; };
+__global__ void weight_transpose_batched_kernel(const WtEntry* __restrict__ table, int n) {
+    __shared__ __nv_bfloat16 tile[32][33];
+    int i = 0;
+    while (i + 1 < n && (int)blockIdx.x >= table[i + 1].first_block) ++i;
+    const WtEntry e = table[i];
+    int rel = blockIdx.x - e.first_block;
+    const int bx = rel % e.bx; rel /= e.bx;
+    const int by = rel % e.by; const int t = rel / e.by;
+    const int to = e.flip ? e.T - 1 - t : t;
+    const int ci0 = bx * 32, co0 = by * 32;
+    for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+        const int co = co0 + r, ci = ci0 + threadIdx.x;
+        if (co < e.Cout && ci < e.Cin) tile[r][threadIdx.x] = e.src[((long long)co * e.T + t) * e.Cin + ci];
+    }
+    __syncthreads();
+    for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+        const int ci = ci0 + r, co = co0 + threadIdx.x;
+        if (co < e.Cout && ci < e.Cin) e.dst[((long long)ci * e.T + to) * e.Cout + co] = tile[threadIdx.x][r];
+    }
+}
+const char* weight_transpose_batched(const void* table, int n, int total_blocks, cudaStream_t stream) {
+    weight_transpose_batched_kernel<<<total_blocks, dim3(32, 8), 0, stream>>>((const WtEntry*)table, n);
+    return cudaGetLastError() == cudaSuccess ? nullptr : "weight_transpose_batched launch failed";
+}
+
 const char* weight_transpose(const void* w, void* out, int Cout, int T, int Cin, int flip, cudaStream_t stream) {
     dim3 grid((Cin + 31) / 32, (Cout + 31) / 32, T), block(32, 8);
     weight_transpose_kernel<<<grid, block, 0, stream>>>((const __nv_bfloat16*)w, (__nv_bfloat16*)out, Cout, T, Cin, flip);

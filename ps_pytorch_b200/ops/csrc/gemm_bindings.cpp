@@ -9,6 +9,7 @@ const char* tc_conv_fprop(const void*, const void*, void*, const void*, const vo
 const char* tc_conv2(const void*, const void*, void*, const void*, const void*, int, int, int, int, int, int, int, int, int, int, int, int, int, float*, cudaStream_t);
 int num_sms();
 const char* weight_transpose(const void*, void*, int, int, int, int, cudaStream_t);
+const char* weight_transpose_batched(const void*, int, int, cudaStream_t);
 void tc_set_conv2_bn(int);
 void tc_set_conv_algo(int);
 void tc_set_halo_desc_mode(int);
@@ -17,11 +18,16 @@ void tc_set_halo_pair(int);
 void tc_set_halo_resident(int);
 void tc_set_gemm_bn(int);
 int tc_check_error();
+const char* stem_fprop(const void*, const void*, void*, const void*, int, int, int, int, int, int, float*, cudaStream_t);
+const char* stem_wgrad_tc(const void*, const void*, void*, float*, int, int, int, int, int, cudaStream_t);
+bool stem_tc_eligible(int, int, int, int, int, int, int, int);
 const char* stem_wgrad_launch(const void*, const void*, void*, float*, int, int, int, int, int, cudaStream_t);
 const char* tc_conv_wgrad(const void*, const void*, void*, float*, int, int, int, int, int, int, int, int, int, cudaStream_t);
 const char* tc_conv_wgrad_halo(const void*, const void*, void*, float*, int, int, int, int, int, cudaStream_t);
 bool tc_wgrad_halo_eligible(int, int, int, int, int, int, int, int);
-static int g_wgrad_algo = -1;          // -1 auto (halo form where eligible), 0 per-tap, 1 halo
+const char* tc_conv_wgrad2(const void*, const void*, void*, float*, int, int, int, int, int, int, int, int, int, cudaStream_t);
+bool tc_wgrad2_eligible(int, int);
+static int g_wgrad_algo = -1;          // -1 auto, 0 per-tap, 1 halo (tap sharing), 2 CTA pair (256 x 256 tiles)
 void tc_set_wgrad_algo(int a) { g_wgrad_algo = a; }
 
 static const void* opt_ptr(const c10::optional<at::Tensor>& t, int64_t n) {
@@ -110,6 +116,36 @@ at::Tensor weight_transpose_t(at::Tensor w, bool flip) {
     return out;
 }
 
+// Batched form: `srcs[i]` ([Cout,Cin,R,S] channels_last) -> `dsts[i]` ([Cin,Cout,R,S] channels_last), flips[i] rotates the taps.  Returns the device
+// table (uint8) to be passed to weight_transpose_run every step; tensors must keep their addresses (arena views).
+std::vector<at::Tensor> weight_transpose_plan(std::vector<at::Tensor> srcs, std::vector<at::Tensor> dsts, std::vector<int64_t> flips) {
+    struct E { const void* src; void* dst; int Cout, T, Cin, flip, first_block, bx, by, pad; };
+    static_assert(sizeof(E) == 48, "table entry layout");
+    TORCH_CHECK(srcs.size() == dsts.size() && srcs.size() == flips.size() && !srcs.empty() && srcs.size() <= 1024);
+    std::vector<E> tab(srcs.size());
+    int blocks = 0;
+    for (size_t i = 0; i < srcs.size(); ++i) {
+        const at::Tensor &w = srcs[i], &o = dsts[i];
+        TORCH_CHECK(w.is_cuda() && w.scalar_type() == at::kBFloat16 && w.dim() == 4 && w.is_contiguous(at::MemoryFormat::ChannelsLast));
+        TORCH_CHECK(o.is_cuda() && o.scalar_type() == at::kBFloat16 && o.dim() == 4 && o.is_contiguous(at::MemoryFormat::ChannelsLast));
+        const int Cout = w.size(0), Cin = w.size(1), T = w.size(2) * w.size(3);
+        TORCH_CHECK(o.size(0) == Cin && o.size(1) == Cout && o.size(2) == w.size(2) && o.size(3) == w.size(3));
+        E e{w.data_ptr(), o.data_ptr(), Cout, T, Cin, (int)flips[i], blocks, (Cin + 31) / 32, (Cout + 31) / 32, 0};
+        blocks += e.bx * e.by * T;
+        tab[i] = e;
+    }
+    at::Tensor host = at::empty({(int64_t)(tab.size() * sizeof(E))}, at::TensorOptions().dtype(at::kByte));
+    memcpy(host.data_ptr(), tab.data(), tab.size() * sizeof(E));
+    at::Tensor dev = host.to(srcs[0].device());
+    at::Tensor meta = at::empty({2}, at::TensorOptions().dtype(at::kLong));
+    meta.data_ptr<int64_t>()[0] = (int64_t)tab.size(); meta.data_ptr<int64_t>()[1] = blocks;
+    return {dev, meta};
+}
+void weight_transpose_run(at::Tensor table, int64_t n, int64_t blocks) {
+    const char* e = weight_transpose_batched(table.data_ptr(), (int)n, (int)blocks, at::cuda::getCurrentCUDAStream());
+    TORCH_CHECK(e == nullptr, e);
+}
+
 // dW [Cout,Cin,R,S] channels_last (physically [Cout][R][S][Cin]) from dy (NHWC) and x (NHWC).  `scratch` is a persistent fp32 buffer of
 // Cout*R*S*Cin floats that must be zero on entry and is left zeroed.
 at::Tensor conv_wgrad(at::Tensor dy, at::Tensor x, at::Tensor scratch, int64_t R, int64_t S, int64_t stride, int64_t pad) {
@@ -119,13 +155,45 @@ at::Tensor conv_wgrad(at::Tensor dy, at::Tensor x, at::Tensor scratch, int64_t R
     TORCH_CHECK(scratch.scalar_type() == at::kFloat && scratch.is_contiguous() && scratch.numel() >= (int64_t)Cout * R * S * Cin);
     at::Tensor dw = at::empty({Cout, Cin, R, S}, x.options().memory_format(at::MemoryFormat::ChannelsLast));
     const char* e;
-    if (g_wgrad_algo != 0 && tc_wgrad_halo_eligible(H, W, Cin, Cout, (int)R, (int)S, (int)stride, (int)pad))
+    // measured (profiles/run25_conv_per_layer.md): the tap-sharing kernel wins where the per-tap one is L2->SM bound, i.e. 64 output channels
+    // (175 vs 235 us on 64->64 @32x32); with 128-wide tiles the per-tap kernel is faster (98 vs 108, 92 vs 149 us)
+    const bool halo_auto = Cout % 128 != 0;
+    if ((g_wgrad_algo == 1 || (g_wgrad_algo == -1 && halo_auto)) && tc_wgrad_halo_eligible(H, W, Cin, Cout, (int)R, (int)S, (int)stride, (int)pad))
         e = tc_conv_wgrad_halo(dy.data_ptr(), x.data_ptr(), dw.data_ptr(), scratch.data_ptr<float>(), NB, H, W, Cin, Cout, at::cuda::getCurrentCUDAStream());
+    else if ((g_wgrad_algo == 2 || g_wgrad_algo == -1) && tc_wgrad2_eligible(Cin, Cout))
+        e = tc_conv_wgrad2(dy.data_ptr(), x.data_ptr(), dw.data_ptr(), scratch.data_ptr<float>(), NB, H, W, Cin, Cout, (int)R, (int)S, (int)stride, (int)pad,
+                           at::cuda::getCurrentCUDAStream());
     else
         e = tc_conv_wgrad(dy.data_ptr(), x.data_ptr(), dw.data_ptr(), scratch.data_ptr<float>(), NB, H, W, Cin, Cout, (int)R, (int)S, (int)stride, (int)pad,
                           at::cuda::getCurrentCUDAStream());
     TORCH_CHECK(e == nullptr, "tc_conv_wgrad: ", e);
     return dw;
+}
+
+// network stem on the tensor cores (stem_tcgen05.cu): y = conv3x3/s1/p1(x [NB,Cin<=3,H,W] NHWC, w [64,Cin,3,3] channels_last) (+bias)(+relu)
+at::Tensor stem_conv(at::Tensor x, at::Tensor w, c10::optional<at::Tensor> bias, bool relu, c10::optional<at::Tensor> stats) {
+    TORCH_CHECK(x.is_cuda() && x.scalar_type() == at::kBFloat16 && w.scalar_type() == at::kBFloat16 && x.dim() == 4 && w.dim() == 4);
+    TORCH_CHECK(x.is_contiguous(at::MemoryFormat::ChannelsLast) && w.is_contiguous(at::MemoryFormat::ChannelsLast), "x and w must be channels_last");
+    const int NB = x.size(0), Cin = x.size(1), H = x.size(2), W = x.size(3), Cout = w.size(0);
+    TORCH_CHECK(w.size(1) == Cin && stem_tc_eligible(H, W, Cin, Cout, w.size(2), w.size(3), 1, 1), "shape not eligible for the stem kernel");
+    at::Tensor y = at::empty({NB, Cout, H, W}, x.options().memory_format(at::MemoryFormat::ChannelsLast));
+    const char* e = stem_fprop(x.data_ptr(), w.data_ptr(), y.data_ptr(), opt_ptr(bias, Cout), NB, H, W, Cin, Cout, relu, stats_ptr(stats, Cout),
+                               at::cuda::getCurrentCUDAStream());
+    TORCH_CHECK(e == nullptr, e);
+    return y;
+}
+at::Tensor stem_wgrad_tensorcore(at::Tensor dy, at::Tensor x, at::Tensor scratch) {
+    TORCH_CHECK(dy.is_cuda() && dy.scalar_type() == at::kBFloat16 && x.scalar_type() == at::kBFloat16 && dy.dim() == 4 && x.dim() == 4);
+    TORCH_CHECK(dy.is_contiguous(at::MemoryFormat::ChannelsLast) && x.is_contiguous(at::MemoryFormat::ChannelsLast), "dy and x must be NHWC");
+    const int NB = x.size(0), Cin = x.size(1), H = x.size(2), W = x.size(3), Cout = dy.size(1);
+    TORCH_CHECK(dy.size(2) == H && dy.size(3) == W && scratch.scalar_type() == at::kFloat && scratch.numel() >= (int64_t)Cout * 9 * Cin);
+    at::Tensor dw = at::empty({Cout, Cin, 3, 3}, x.options().memory_format(at::MemoryFormat::ChannelsLast));
+    const char* e = stem_wgrad_tc(dy.data_ptr(), x.data_ptr(), dw.data_ptr(), scratch.data_ptr<float>(), NB, H, W, Cin, Cout, at::cuda::getCurrentCUDAStream());
+    TORCH_CHECK(e == nullptr, e);
+    return dw;
+}
+bool stem_eligible(int64_t H, int64_t W, int64_t Cin, int64_t Cout, int64_t R, int64_t S, int64_t stride, int64_t pad) {
+    return stem_tc_eligible((int)H, (int)W, (int)Cin, (int)Cout, (int)R, (int)S, (int)stride, (int)pad);
 }
 
 // weight gradient of a 3x3/s1/p1 convolution with Cin <= 3 (network stem); dy, x NHWC bf16; scratch: zeroed fp32 [Cout*9*Cin], left zeroed
@@ -163,6 +231,8 @@ void bind_gemm(pybind11::module_& m) {
           pybind11::arg("stats") = c10::optional<at::Tensor>());
     m.def("num_sms", &psb::num_sms);
     m.def("weight_transpose", &psb::weight_transpose_t);
+    m.def("weight_transpose_plan", &psb::weight_transpose_plan);
+    m.def("weight_transpose_run", &psb::weight_transpose_run);
     m.def("tc_set_conv2_bn", &psb::tc_set_conv2_bn);
     m.def("tc_set_conv_algo", &psb::tc_set_conv_algo);
     m.def("tc_set_halo_desc_mode", &psb::tc_set_halo_desc_mode);
@@ -174,5 +244,8 @@ void bind_gemm(pybind11::module_& m) {
     m.def("conv_wgrad", &psb::conv_wgrad);
     m.def("tc_set_wgrad_algo", &psb::tc_set_wgrad_algo);
     m.def("stem_wgrad", &psb::stem_wgrad);
+    m.def("stem_conv", &psb::stem_conv);
+    m.def("stem_wgrad_tc", &psb::stem_wgrad_tensorcore);
+    m.def("stem_eligible", &psb::stem_eligible);
     m.def("tc_error", &psb::tc_error);
 }

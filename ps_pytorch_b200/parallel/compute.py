@@ -59,12 +59,18 @@ class WorkerCompute:
         self.criterion = pnn.CrossEntropyLoss()
         self.timer = PhaseTimer(self.device)
         self.use_graph = use_graph and self.device.type == "cuda"
+        if self.device.type == "cuda" and _ops.available():
+            from ..ops import conv as _conv
+            _conv.enable_batched_dgrad_operands(True)
         self._graph = None
         self._static_x = self._static_y = self._static_loss = None
         self._bucket_hooks: List = []
         self._on_bucket: Optional[Callable[[int], None]] = None
         self._kill_poll: Optional[Callable[[], bool]] = None
         self.kill_deadline: float = 0.0
+        self._warming_up = False               # graph warm-up passes: bucket hooks must not push (or poll) for real
+        self._capturing = False
+        self.captured_buckets: List[int] = []  # buckets whose push kernels were recorded inside the CUDA graph
 
     # ---- overlap: bucket-complete callbacks during backward ---------------------------------------------
     def enable_bucket_callbacks(self, buckets, on_bucket: Callable[[int], None]) -> None:
@@ -82,12 +88,16 @@ class WorkerCompute:
 
         def make(i):
             def hook(_p):
-                if self._kill_poll is not None and (self._kill_poll() or (self.kill_deadline and time.time() > self.kill_deadline)):
+                if self._warming_up:
+                    return                      # off-graph warm-up: no pushes, no kill polls (they used to push a bogus step)
+                if self._kill_poll is not None and not self._capturing and (self._kill_poll() or (self.kill_deadline and time.time() > self.kill_deadline)):
                     raise StragglerKilled()
                 b = owner[i]
                 self._pending[b] -= 1
                 if self._pending[b] == 0 and self._on_bucket is not None:
                     self._on_bucket(b)
+                    if self._capturing:
+                        self.captured_buckets.append(b)
             return hook
         for i, p in enumerate(params):
             self._bucket_hooks.append(p.register_post_accumulate_grad_hook(make(i)))
@@ -113,6 +123,9 @@ class WorkerCompute:
         if not gather and self._params[0].grad is None:
             self.grads.bind_grads(self.network)
         self._arm_buckets()
+        if self.device.type == "cuda" and _ops.available():
+            from ..ops import conv as _conv
+            _conv.refresh_dgrad_operands()          # one launch: the transposed filters every dgrad of this step reads
         if self._bn_counters and self.network.training:
             torch._foreach_add_(self._bn_counters, 1)
         with self.timer.phase("forward"):
@@ -224,9 +237,13 @@ class WorkerCompute:
         s = torch.cuda.Stream()
         s.wait_stream(torch.cuda.current_stream())
         saved = [b.detach().clone() for b in self.network.buffers()]      # warm-up must not advance BN statistics
-        with torch.cuda.stream(s):
-            for _ in range(3):   # warm-up off-graph: cuDNN autotune, lazy inits
-                self._step_body(self._static_x, self._static_y)
+        self._warming_up = True
+        try:
+            with torch.cuda.stream(s):
+                for _ in range(3):   # warm-up off-graph: cuDNN autotune, lazy inits
+                    self._step_body(self._static_x, self._static_y)
+        finally:
+            self._warming_up = False
         torch.cuda.current_stream().wait_stream(s)
         torch.cuda.synchronize()
         with torch.no_grad():
@@ -237,8 +254,13 @@ class WorkerCompute:
         self._graph = torch.cuda.CUDAGraph()
         self.timer = _NullTimer()
         n0 = _ops.launch_count
-        with torch.cuda.graph(self._graph):
-            self._static_loss, self._static_logits = self._step_body(self._static_x, self._static_y)
+        self.captured_buckets = []
+        self._capturing = True
+        try:
+            with torch.cuda.graph(self._graph):
+                self._static_loss, self._static_logits = self._step_body(self._static_x, self._static_y)
+        finally:
+            self._capturing = False
         self.graph_launches = _ops.launch_count - n0      # our kernels recorded in the graph, re-counted per replay
 
     @torch.no_grad()

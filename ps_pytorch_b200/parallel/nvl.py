@@ -84,8 +84,8 @@ class NvlTransport(Transport):
         self.slot_stride = _align(self.slot_q_bytes + self.slot_s_bytes, 256)
         nslots = P if topology == "ps" else 0
         self.off_bufs = _align(self.off_slots + nslots * self.slot_stride)
-        self.n_buffers = n_buffers
-        total = self.off_bufs + _align(max(n_buffers, 1) * 4 + 64)
+        self.n_buffers = int(n_buffers)
+        total = self.off_bufs + _align(max(self.n_buffers, 1) * 4 + 64)
         self.arena = SymmetricArena(total, self.device, tag="ps")
         A = self.arena
         # flag words (int64) inside the flags page
@@ -99,6 +99,7 @@ class NvlTransport(Transport):
         self.p_psstep = self.ctl.data_ptr() + 8
         self.p_err = self.ctl.data_ptr() + 16
         self.p_counters = self.ctl.data_ptr() + 64           # int32 counters: [0..MAXB) reduce, [MAXB..2MAXB) push, [2MAXB] bcast
+        self.p_sel = self.ctl.data_ptr() + 256               # [MAXB] int64: the grid-wide arrival decision per bucket (reduce_update_kernel)
         self._host_wstep = 0
         self._host_psstep = 0
         self._published = 0
@@ -121,6 +122,17 @@ class NvlTransport(Transport):
 
     ps_weight_storage = lambda self: self.arena.view(self.off_w, self.T * 2, torch.bfloat16)   # noqa: E731
 
+    def ps_slot_storage(self):
+        """The P gradient slots the push kernel writes on the PS, as one strided ``[P, total]`` tensor in the wire dtype (bf16 / fp32;
+        uint8 payload for the fp8 wire): ``GradientAccumulator`` addresses "layer l from worker k" as views of THIS memory instead of
+        owning a second P x total slab."""
+        if self.topology != "ps":
+            return None
+        dt = {0: torch.bfloat16, 1: torch.uint8, 2: torch.float32}[self.wire]
+        es = {0: 2, 1: 1, 2: 4}[self.wire]
+        flat = self.arena.view(self.off_slots, self.num_workers * self.slot_stride, dt)
+        return flat.as_strided((self.num_workers, self.T), (self.slot_stride // es, 1))
+
     def worker_grad_storage(self, dtype):
         nb = self.T * (2 if dtype == torch.bfloat16 else 4)
         return self.arena.view(self.off_grads, nb, dtype)
@@ -130,6 +142,23 @@ class NvlTransport(Transport):
 
     def _flag(self, rank, word_off):
         return self.arena.peer_ptrs[rank] + self.off_flags + word_off
+
+    def sync_start_step(self, step=None):
+        """Collective (every rank, once, before the first step): rank 0 announces the step it starts from (1, or last+1 after
+        ``--resume``) and every rank seeds its device step counters with it — the flag protocol compares flag values with these
+        counters, so a worker that restarted at 1 against a PS resumed at last+1 would wait forever."""
+        start = [int(step) if step is not None else 1]
+        if dist.is_initialized() and self.world_size > 1:
+            dist.broadcast_object_list(start, src=0)
+        st = int(start[0])
+        if st != 1:
+            torch.cuda.synchronize(self.device)
+            self.ctl[0] = st
+            self.ctl[1] = st
+            self._host_wstep = st - 1
+            self._host_psstep = st - 1
+            torch.cuda.synchronize(self.device)
+        return st
 
     # ---- PS side ---------------------------------------------------------------------------------------------------------
     def _dests(self):
@@ -205,11 +234,15 @@ class NvlTransport(Transport):
         nvls = self._nvls_reduce_ok(mode, take, len(src))
         if nvls:
             self.ext.ru_set_mc_src(self.arena.mc_ptr + self.off_grads)
+        # --mode kill: the kernel raises the abort word of every worker whose gradient is not part of the decision (C10);
+        # --mode timeout: after timeout_s it proceeds with the >= 1 gradients that arrived instead of failing the job
+        abort_words = [self._flag(r, self.F_ABORT) for r in self.worker_ranks] if (kill_stragglers and self.topology == "ps") else []
+        partial_ok = bool(timeout_s) and float(timeout_s) > 0.0
         try:
             self.ext.reduce_update(src, scl, int(take), 1.0 / float(k), int(mode), self.arena.local_ptr + self.off_flags + self.F_GREADY,
                                    self.p_psstep, lo, hi, master.flat, s0, s1, s2, hp_ptr, self._ru_dst(d),
                                    (self.arena.mc_ptr + self.off_w) if use_mc else 0, wready, self.p_counters, self.p_err,
-                                   float(timeout_s or self.timeout_s), True)
+                                   float(timeout_s or self.timeout_s), True, self.p_sel, partial_ok, abort_words)
         finally:
             if nvls:
                 self.ext.ru_set_mc_src(0)
@@ -314,8 +347,22 @@ class NvlTransport(Transport):
         self.ext.add_step(self.p_wstep, 1)
         ops.count_launch()
 
-    def worker_push_killed(self, step):
+    def mark_pushed(self, b: int) -> None:
+        """Bucket ``b`` was pushed by kernels inside a replayed CUDA graph (the Python hook that normally records it does not run)."""
+        self._pushed[b] = True
+
+    def worker_push_killed(self, step, grads: FlatBuffer = None):
+        """The worker abandoned this step (kill signal / own deadline).  Gradients accumulate in place and are normally zeroed by the push
+        kernel, so whatever backward produced before it was cut short must be cleared here or it would leak into the next step."""
+        if self._push_forked:
+            ev = torch.cuda.Event()
+            ev.record(self._push_stream)
+            torch.cuda.current_stream().wait_event(ev)
+            self._push_forked = False
+        if grads is not None:
+            grads.flat.zero_()
         self.ext.add_step(self.p_wstep, 1)
+        ops.count_launch()
 
     def _read_word(self, word_off) -> int:
         with torch.cuda.stream(self._side):
@@ -328,6 +375,7 @@ class NvlTransport(Transport):
     def worker_send_buffers(self, step, flat):
         if flat.numel() == 0:
             return
+        assert flat.numel() <= self.n_buffers, "BN statistics (%d floats) exceed the %d reserved in the arena (pass n_buffers=)" % (flat.numel(), self.n_buffers)
         dst = self.arena.peer_view(0, self.off_bufs + 64, flat.numel() * 4, torch.float32)
         dst.copy_(flat.float())
         self.ext.set_word(self._flag(0, self.F_BUFS), int(step))
@@ -364,7 +412,8 @@ class NvlTransport(Transport):
             self.ext.reduce_update([self.arena.peer_ptrs[r] + self.off_grads for r in d], [], len(d), 1.0 / len(d), 0,
                                    self.arena.local_ptr + self.off_flags + self.F_GREADY, self.p_psstep, [lo], [hi], self._ar_w, None, None, None,
                                    self._ar_hp.data_ptr(), [self.arena.peer_ptrs[r] + self.off_grads for r in d], 0,
-                                   [self._flag(r, self.F_WREADY + 8 * self.rank) for r in d], self.p_counters, self.p_err, self.timeout_s, True)
+                                   [self._flag(r, self.F_WREADY + 8 * self.rank) for r in d], self.p_counters, self.p_err, self.timeout_s, True,
+                                   self.p_sel, False, [])
         finally:
             if nvls:
                 self.ext.ru_set_mc_src(0)

@@ -29,8 +29,8 @@ STEP_START_ = 1
 class GradientAccumulator(object):
     """Per-layer arrival counters + per-(layer, worker) staging views — the TF "ConditionalAccumulator"
     analogue of the reference (``sync_replicas_master_nn.py:49-93``).  With flat arenas the staging buffers are
-    views into one ``[P, total]`` slab (the same slab the NVLink push kernel writes), so ``gradient_aggregator[l][k]``
-    still addresses "layer l from worker k"."""
+    views into one ``[P, total]`` slab, so ``gradient_aggregator[l][k]`` still addresses "layer l from worker k".  On the NVLink tier
+    ``storage`` is ``NvlTransport.ps_slot_storage()``: the very slots the workers' push kernels store into (wire dtype), nothing is copied."""
 
     def __init__(self, layout: ParamLayout, num_worker: int, mode: str = 'None', device="cpu", dtype=torch.float32,
                  storage: Optional[torch.Tensor] = None):
@@ -102,11 +102,15 @@ class SyncReplicasMaster_NN(object):
         else:
             self.lowp = FlatBuffer(self.layout, self._lowp_dtype, self._device, storage=lowp_storage)
             self.lowp.flat.copy_(self.master.flat)
+        # On the NVLink tier the accumulator's staging buffers ARE the slots the push kernel writes (no second P x total slab on the PS GPU);
+        # on the CPU tier it owns a host slab like the reference's numpy buffers.
         slab = self.comm.ps_slot_storage() if hasattr(self.comm, "ps_slot_storage") else None
         nslot = max(1, self._num_grad_to_collect)
         self.grad_accumulator = None
-        if slab is not None or self.layout.total * nslot * 4 < (1 << 31):
-            self.grad_accumulator = GradientAccumulator(self.layout, nslot, self._compress_grad, device=self._device, storage=slab)
+        if slab is not None:
+            self.grad_accumulator = GradientAccumulator(self.layout, slab.size(0), self._compress_grad, device=self._device, storage=slab)
+        elif self._device.type == "cpu" and self.layout.total * nslot * 4 < (1 << 31):
+            self.grad_accumulator = GradientAccumulator(self.layout, nslot, self._compress_grad, device=self._device)
         self.init_model_shapes()
         self._n_buffers = sum(b.numel() for b in self.network.buffers())
         if self._resume:

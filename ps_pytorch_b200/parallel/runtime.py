@@ -55,7 +55,7 @@ def init_process_group(use_cuda: bool, timeout_s: int = 600):
     return rank, local_rank, world
 
 
-def make_transport(args, layout: ParamLayout, device: torch.device, world: int):
+def make_transport(args, layout: ParamLayout, device: torch.device, world: int, n_buffers: int = 0):
     kind = args.transport
     if kind == "auto":
         kind = "local" if world == 1 else ("nvl" if device.type == "cuda" else "gloo")
@@ -70,7 +70,7 @@ def make_transport(args, layout: ParamLayout, device: torch.device, world: int):
         if gd == "auto":
             gd = "fp8" if compress else "bf16"
         return NvlTransport(layout, device, grad_dtype=gd, colocate=args.colocate_worker, num_buckets=(args.num_buckets if args.overlap else 1),
-                            pull_weights=str(args.comm_type).lower() == "async")
+                            pull_weights=str(args.comm_type).lower() == "async", n_buffers=n_buffers)
     raise ValueError(kind)
 
 
@@ -191,7 +191,7 @@ def run_distributed(args):
     dtype = resolve_dtype(args.dtype, device)
     proto = build_model(args.network, num_classes)
     layout = ParamLayout.from_module(proto, channels_last=(device.type == "cuda"))
-    comm = make_transport(args, layout, device, world)
+    comm = make_transport(args, layout, device, world, n_buffers=sum(b.numel() for b in proto.buffers()))
     stragglers = parse_stragglers(args.inject_straggler)
     failures = {int(r): int(st) for r, st in (item.split(":") for item in filter(None, (getattr(args, "inject_failure", "") or "").split(",")))}
     common = dict(batch_size=args.batch_size, learning_rate=args.lr, max_epochs=args.epochs, momentum=args.momentum,
@@ -222,6 +222,7 @@ def run_distributed(args):
             w.attach_loader(train_loader)
             master._colocated_worker = w
             result["worker"] = w
+        comm.sync_start_step(master.cur_step)                    # collective: 1, or last+1 after --resume
         master.start()
         print("Done sending messages to workers!")
         result["master"] = master
@@ -229,6 +230,7 @@ def run_distributed(args):
         w = DistributedWorker(comm=comm, **kwargs_worker)
         w.build_model(num_classes=num_classes)
         print("I am worker: {} in all {} workers, next step: {}".format(w.rank, comm.num_workers, w.next_step))
+        comm.sync_start_step(None)
         w.train(train_loader=train_loader, test_loader=test_loader)
         print("Now the next step is: {}".format(w.next_step))
         result["worker"] = w

@@ -56,8 +56,10 @@ class Transport:
     # worker side
     def worker_fetch(self, weights: FlatBuffer, timeout_s: float = 0.0) -> int: raise NotImplementedError
     def worker_push(self, step: int, grads: FlatBuffer, lo: int = 0, hi: Optional[int] = None, last: bool = True) -> None: raise NotImplementedError
-    def worker_push_killed(self, step: int) -> None: pass
+    def worker_push_killed(self, step: int, grads: Optional[FlatBuffer] = None) -> None: pass
     def worker_poll_kill(self, step: int) -> bool: return False
+    def mark_pushed(self, b: int) -> None: pass
+    def sync_start_step(self, step: Optional[int] = None) -> int: return int(step or 1)      # collective on tiers with device step counters
     def worker_send_buffers(self, step: int, flat: torch.Tensor) -> None: pass
     def ps_recv_buffers(self, step: int, numel: int) -> Optional[torch.Tensor]: return None
     def barrier(self) -> None: pass
@@ -298,7 +300,9 @@ class GlooTransport(Transport):
         self._keep = (hdr, payload)
         self.stats["push_bytes"] += payload.numel()
 
-    def worker_push_killed(self, step):
+    def worker_push_killed(self, step, grads=None):
+        if grads is not None:
+            grads.flat.zero_()          # a partial backward must not leak into the next step's accumulation
         if self.rank == 0:
             return
         hdr = torch.tensor([0, HDR_KILLED], dtype=torch.int64)

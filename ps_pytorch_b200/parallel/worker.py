@@ -170,9 +170,11 @@ class DistributedWorker(object):
             killed = True
         c0 = time.time()
         if killed:
-            self.comm.worker_push_killed(self.cur_step)
+            self.comm.worker_push_killed(self.cur_step, self.compute.grads)
             logger.info("Worker %d: step %d abandoned on kill signal", self.rank, self.cur_step)
         else:
+            for b in self.compute.captured_buckets:      # pushed by kernels inside the replayed CUDA graph, not by the Python hook
+                self.comm.mark_pushed(b)
             self._send_grads()
         if self.cur_step % self._eval_freq == 0 and self._is_ckpt_source:
             self.comm.worker_send_buffers(self.cur_step, self.compute.buffers_flat())

@@ -84,8 +84,9 @@ for (Cin, H, W, Cout, R, st, pad) in SHAPES:
     res["w_cudnn_us"] = timeit(lambda: torch.ops.aten.convolution_backward(dy, x, w, None, (st, st), (pad, pad), (1, 1), False, (0, 0), 1, (False, True, False)))
     scratch = torch.zeros(Cout * R * R * Cin, device="cuda")
     attempt(res, "w_ours", lambda: ext.conv_wgrad(dy, x, scratch, R, R, st, pad), g0)
-    ext.tc_set_wgrad_algo(0)
-    attempt(res, "w_tap", lambda: ext.conv_wgrad(dy, x, scratch, R, R, st, pad), g0)
+    for nm, al in (("w_tap", 0), ("w_halo", 1), ("w_pair", 2)):
+        ext.tc_set_wgrad_algo(al)
+        attempt(res, nm, lambda: ext.conv_wgrad(dy, x, scratch, R, R, st, pad), g0)
     ext.tc_set_wgrad_algo(-1)
     for k in list(res):
         if k.endswith("_us"):
@@ -94,7 +95,7 @@ for (Cin, H, W, Cout, R, st, pad) in SHAPES:
     print(json.dumps(res), flush=True)
 os.makedirs("gpurun_out", exist_ok=True)
 json.dump(rows, open("gpurun_out/bench_conv2.json", "w"), indent=1)
-hdr = ["f_cudnn", "f_pair", "f_pair_bn128", "f_tap1", "f_halo2", "f_halo1", "d_cudnn", "d_ours", "d_pair_kernel_only", "w_cudnn", "w_ours", "w_tap"]
+hdr = ["f_cudnn", "f_pair", "f_pair_bn128", "f_tap1", "f_halo2", "f_halo1", "d_cudnn", "d_ours", "d_pair_kernel_only", "w_cudnn", "w_ours", "w_tap", "w_halo", "w_pair"]
 print("| shape | " + " | ".join(hdr) + " |")
 for r in rows:
     print("| %s | " % "x".join(map(str, r["shape"])) + " | ".join(("%.1f" % r[h + "_us"]) if h + "_us" in r else (r.get(h + "_err", "-")[:20]) for h in hdr) + " |")
