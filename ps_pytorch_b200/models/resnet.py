@@ -42,11 +42,13 @@ class BasicBlock(tnn.Module):
                 nn.BatchNorm2d(self.expansion * planes))
 
     def forward(self, x):
-        # the gradient arriving through the skip path is parked and added inside conv1's dgrad epilogue (ops/conv.py:stash_grad)
+        # The gradient arriving through the skip path is parked and added inside conv1's dgrad epilogue (ops/conv.py:stash_grad).  The stash node
+        # is created AFTER conv2: autograd runs ready nodes newest-first, so the skip gradient is parked before conv1's backward looks for it.
         h = _conv.new_grad_holder(x) if use_sm100(x) else None
-        xs = _conv.stash_grad(x, h) if h is not None else x
         out = self.bn1(self.conv1(x, grad_holder=h, bn=self.bn1), relu=True)
-        return self.bn2(self.conv2(out, bn=self.bn2), residual=self.shortcut(xs), relu=True)
+        out = self.conv2(out, bn=self.bn2)
+        xs = _conv.stash_grad(x, h) if h is not None else x
+        return self.bn2(out, residual=self.shortcut(xs), relu=True)
 
 
 class Bottleneck(tnn.Module):
@@ -68,10 +70,11 @@ class Bottleneck(tnn.Module):
 
     def forward(self, x):
         h = _conv.new_grad_holder(x) if use_sm100(x) else None
-        xs = _conv.stash_grad(x, h) if h is not None else x
         out = self.bn1(self.conv1(x, grad_holder=h, bn=self.bn1), relu=True)
         out = self.bn2(self.conv2(out, bn=self.bn2), relu=True)
-        return self.bn3(self.conv3(out, bn=self.bn3), residual=self.shortcut(xs), relu=True)
+        out = self.conv3(out, bn=self.bn3)
+        xs = _conv.stash_grad(x, h) if h is not None else x          # created last: runs first in backward (see BasicBlock)
+        return self.bn3(out, residual=self.shortcut(xs), relu=True)
 
 
 class ResNet(tnn.Module):

@@ -41,6 +41,8 @@ def _apply_switches(ext):
         return
     if os.environ.get("PSB200_TC_HALO_PAIR", "") != "":
         ext.tc_set_halo_pair(int(os.environ["PSB200_TC_HALO_PAIR"]))
+    if os.environ.get("PSB200_TC_HALO_PITCH", "") != "":           # 16 = 2 KB patch rows, 0 = tight (8 + S - 1 pixels)
+        ext.tc_set_halo_pitch(int(os.environ["PSB200_TC_HALO_PITCH"]))
     if os.environ.get("PSB200_TC_CONV_ALGO", "") != "":            # -1 auto (halo where eligible), 0 per-tap, 1 halo
         ext.tc_set_conv_algo(int(os.environ["PSB200_TC_CONV_ALGO"]))
     _applied = True
@@ -204,6 +206,7 @@ def stash_grad(x, holder):
     return _StashGrad.apply(x, holder)
 
 
+skip_fused_count = 0             # how many skip gradients were added inside a dgrad epilogue (tests assert the fusion really happens)
 _SKIP_FUSION = os.environ.get("PSB200_SKIP_GRAD_FUSION", "1") != "0"
 _WGRAD_SIDE = os.environ.get("PSB200_TC_WGRAD_STREAM", "1") != "0"
 
@@ -248,6 +251,8 @@ class _ConvFn(torch.autograd.Function):
             if need_dx and h.grad is not None and h.grad.shape == x.shape and h.grad.dtype == dy.dtype:
                 skip = h.grad.contiguous(memory_format=torch.channels_last)
                 h.grad = None
+                global skip_fused_count
+                skip_fused_count += 1
             else:
                 h.consumed = True                     # from now on the stash hands its gradient to autograd itself
         if need_dx:

@@ -15,6 +15,7 @@ void tc_set_conv_algo(int);
 void tc_set_halo_desc_mode(int);
 void tc_set_halo_cluster(int);
 void tc_set_halo_pair(int);
+void tc_set_halo_pitch(int);
 void tc_set_halo_resident(int);
 void tc_set_gemm_bn(int);
 int tc_check_error();
@@ -238,6 +239,7 @@ void bind_gemm(pybind11::module_& m) {
     m.def("tc_set_halo_desc_mode", &psb::tc_set_halo_desc_mode);
     m.def("tc_set_halo_cluster", &psb::tc_set_halo_cluster);
     m.def("tc_set_halo_pair", &psb::tc_set_halo_pair);
+    m.def("tc_set_halo_pitch", &psb::tc_set_halo_pitch);
     m.def("tc_set_halo_resident", &psb::tc_set_halo_resident);
     m.def("tc_set_gemm_bn", &psb::tc_set_gemm_bn);
     m.def("conv_unsupported_reason", &psb::conv_unsupported_reason);

@@ -354,7 +354,7 @@ tc_conv_halo_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
             for (int cb = 0; cb < p.cblocks; ++cb) {
                 if (!mbar_wait(a_empty + as, aph ^ 1)) { *p.err = 11; return; }
                 if (elect_one()) {
-                    mbar_arrive_expect_tx(a_full + as, p.a_stage_bytes);
+                    mbar_arrive_expect_tx(a_full + as, p.a_tx_bytes);
                     tma_load_4d(smem_a + as * p.a_stage_bytes, &tmap_a, a_full + as, cb * BK, tw * 8 - p.pad, th * 16 - p.pad, n);
                 }
                 __syncwarp();
@@ -390,11 +390,11 @@ tc_conv_halo_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                     if (elect_one()) {
                         for (int s = 0; s < p.S; ++s) {
                             // shifted window: the swizzle XOR is a function of the absolute smem address, so base_offset stays 0
-                            const uint32_t sa = sa0 + (uint32_t)((r * 16 + s) * 128);
+                            const uint32_t sa = sa0 + (uint32_t)((r * p.halo_w + s) * 128);
                             const uint32_t sb = sb0 + (uint32_t)(s * Cfg::kBTapBytes);
 #pragma unroll
                             for (int k = 0; k < BK / 16; ++k)
-                                tc_mma_bf16(tmem_d, umma_desc_k_sw128_sbo(sa + k * 32, 2048), umma_desc_k_sw128(sb + k * 32), idesc, (cb | r | s | k) != 0);
+                                tc_mma_bf16(tmem_d, umma_desc_k_sw128_sbo(sa + k * 32, (uint32_t)p.halo_w * 128u), umma_desc_k_sw128(sb + k * 32), idesc, (cb | r | s | k) != 0);
                         }
                         if (!p.b_resident) { if (CL == 1) tc_commit(b_empty + bs); else tc_commit_mcast(b_empty + bs, kMask); }
                     }
@@ -503,7 +503,7 @@ tc_conv_halo2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
             for (int cb = 0; cb < p.cblocks; ++cb) {
                 if (!mbar_wait(a_empty + as, aph ^ 1)) { *p.err = 21; goto teardown; }
                 if (elect_one()) {
-                    if (leader) mbar_arrive_expect_tx(a_full + as, 2 * p.a_stage_bytes);
+                    if (leader) mbar_arrive_expect_tx(a_full + as, 2 * p.a_tx_bytes);
                     tma_load_4d_2sm(smem_a + as * p.a_stage_bytes, &tmap_a, mapa_u32(smem_u32(a_full + as), 0), cb * BK, tw * 8 - p.pad, th * 16 - p.pad, n);
                 }
                 __syncwarp();
@@ -538,11 +538,11 @@ tc_conv_halo2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
                     const uint32_t sb0 = smem_u32(smem_b + bs * b_stage_bytes);
                     if (elect_one()) {
                         for (int s = 0; s < p.S; ++s) {
-                            const uint32_t sa = sa0 + (uint32_t)((r * 16 + s) * 128);
+                            const uint32_t sa = sa0 + (uint32_t)((r * p.halo_w + s) * 128);
                             const uint32_t sb = sb0 + (uint32_t)(s * kHalfTapBytes);
 #pragma unroll
                             for (int k = 0; k < BK / 16; ++k)
-                                tc_mma2_bf16(tmem_d, umma_desc_k_sw128_sbo(sa + k * 32, 2048), umma_desc_k_sw128(sb + k * 32), idesc, (cb | r | s | k) != 0);
+                                tc_mma2_bf16(tmem_d, umma_desc_k_sw128_sbo(sa + k * 32, (uint32_t)p.halo_w * 128u), umma_desc_k_sw128(sb + k * 32), idesc, (cb | r | s | k) != 0);
                         }
                         if (!p.b_resident) tc_commit2_mcast(b_empty + bs, 0b11);
                     }
@@ -846,6 +846,8 @@ static const char* launch_halo(const CUtensorMap& ta, const CUtensorMap& tb, con
     return cudaLaunchKernelEx(&cfg, tc_conv_halo_kernel<BN, CL>, ta, tb, p) == cudaSuccess ? nullptr : "kernel launch failed";
 }
 
+static int g_halo_pitch = 16;         // 16, or 0 = tight (8 + S - 1 pixels); tc_set_halo_pitch
+void tc_set_halo_pitch(int v) { g_halo_pitch = v == 16 ? 16 : 0; }
 static int g_halo_pair = 1;           // CTA-pair halo kernel (validated on B200 in round 2); tc_set_halo_pair(0) selects the 1-CTA variants
 void tc_set_halo_pair(int v) { g_halo_pair = v ? 1 : 0; }
 
@@ -932,7 +934,10 @@ const char* tc_conv_fprop(const void* X, const void* Wt, void* Y, const void* bi
         CUtensorMap ta, tb;
         uint64_t da[4] = {(uint64_t)Cin, (uint64_t)Win, (uint64_t)Hin, (uint64_t)NB};
         uint64_t sa[3] = {(uint64_t)Cin * 2, (uint64_t)Win * Cin * 2, (uint64_t)Hin * Win * Cin * 2};
-        uint32_t boxa[4] = {BK, 16, (uint32_t)(16 + R - 1), 1}, esa[4] = {1, 1, 1, 1};
+        // patch pitch: 16 pixels (2 KB rows), or exactly the 8 + S - 1 columns a tile needs (g_halo_pitch = 0: 10 pixels for 3x3 -> 37 % less
+        // L2->SM traffic per tile; the 8-pixel row groups are then 1280 bytes apart, which the address-based swizzle tolerates)
+        const int pitch = g_halo_pitch == 16 ? 16 : 8 + S - 1;
+        uint32_t boxa[4] = {BK, (uint32_t)pitch, (uint32_t)(16 + R - 1), 1}, esa[4] = {1, 1, 1, 1};
         const int Ktot = R * S * Cin;
         // weights [Cout][R*S][Cin] as a 3-D tensor (Cin, Cout, taps): one box = S taps of one filter row
         uint64_t db[3] = {(uint64_t)Cin, (uint64_t)Cout, (uint64_t)(R * S)}, sb[2] = {(uint64_t)Ktot * 2, (uint64_t)Cin * 2};
@@ -944,7 +949,7 @@ const char* tc_conv_fprop(const void* X, const void* Wt, void* Y, const void* bi
         p.Hout = Hout; p.Wout = Wout; p.NB = NB; p.stride = 1; p.pad = pad; p.S = S; p.R = R; p.cblocks = Cin / BK;
         p.tiles_w = (Wout + 7) / 8; p.tiles_h = (Hout + 15) / 16;
         p.n_tiles_m = p.tiles_w * p.tiles_h * NB; p.n_tiles_n = (Cout + BN - 1) / BN;
-        p.halo_w = 16; p.a_stage_bytes = (16 + R - 1) * 16 * 128;
+        p.halo_w = pitch; p.a_tx_bytes = (16 + R - 1) * pitch * 128; p.a_stage_bytes = (p.a_tx_bytes + 1023) / 1024 * 1024;      // stages stay 1024-byte aligned
         // weight-stationary: with one channel block and one N tile the R filter-row stages hold ALL the weights this CTA ever needs
         p.b_resident = (g_halo_resident && p.cblocks == 1 && p.n_tiles_n == 1 && R <= HaloCfg<64>::kBStages && BN == 64) ? 1 : 0;
         p.a_stages = 2;

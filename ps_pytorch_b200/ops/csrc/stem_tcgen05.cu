@@ -32,7 +32,7 @@ struct StemParams {
     // geometry
     const __nv_bfloat16* x;              // [NB,H,W,Cin]
     const __nv_bfloat16* w;              // [64][3][3][Cin]
-    int NB, H, W, Cin, TR, n_tiles;      // TR = 128 / W image rows per tile
+    int NB, H, W, Cin, TR, n_tiles, lw;  // TR = 128 / W image rows per tile, lw = log2(W)
     float* dW32;                         // wgrad: fp32 [64][9*Cin] accumulator (zero on entry)
     int* err;
 };
@@ -40,37 +40,49 @@ struct StemParams {
 constexpr int kStemRowBytes = 128, kStemTile = 128 * kStemRowBytes;      // one operand tile: 128 rows of 128 bytes
 constexpr int kStemXinMax = 6 * 34 * 3;                                  // staged patch elements (W = 32, Cin = 3)
 
-// stage the zero-padded input patch of tile (n, h0) into xin[(TR+2)][(W+2)][Cin]; `tid` in [0, 128)
-__device__ __forceinline__ void stem_stage_patch(const StemParams& p, int n, int h0, __nv_bfloat16* xin, int tid) {
-    const int pw = p.W + 2, rowlen = pw * p.Cin, total = (p.TR + 2) * rowlen;
-    const __nv_bfloat16 zero = __float2bfloat16_rn(0.f);
-    for (int e = tid; e < total; e += 128) {
-        const int row = e / rowlen, rem = e - row * rowlen, px = rem / p.Cin, c = rem - px * p.Cin;
-        const int h = h0 + row - 1, wq = px - 1;
-        xin[e] = (h >= 0 && h < p.H && wq >= 0 && wq < p.W) ? p.x[(((long long)n * p.H + h) * p.W + wq) * p.Cin + c] : zero;
+// ---- patch staging: one 16-byte global load per thread and tile, issued one tile AHEAD (register prefetch) ------------------------------
+// A patch row is W * CIN contiguous bf16 in global memory (a multiple of 16 bytes for W >= 8); vector t of a tile is (row = t / nvr, v = t % nvr).
+// xin[(TR+2)][(W+2) * CIN]: CIN zero elements left and right of every row (written once), rows outside the image arrive as zero vectors.
+__device__ __forceinline__ uint4 stem_load_vec(const StemParams& p, int n, int h0, int t, int nvr) {
+    uint4 v = make_uint4(0, 0, 0, 0);
+    if (t < (p.TR + 2) * nvr) {
+        const int row = t / nvr, vi = t - row * nvr, h = h0 + row - 1;
+        if (h >= 0 && h < p.H) v = __ldg(reinterpret_cast<const uint4*>(p.x + ((long long)n * p.H + h) * p.W * p.Cin) + vi);
+    }
+    return v;
+}
+__device__ __forceinline__ void stem_store_vec(const StemParams& p, uint16_t* xin, int t, int nvr, const uint4& v) {
+    if (t < (p.TR + 2) * nvr) {
+        const int row = t / nvr, vi = t - row * nvr;
+        uint16_t* d = xin + row * (p.W + 2) * p.Cin + p.Cin + vi * 8;          // 2-byte aligned only (CIN may be odd)
+        d[0] = (uint16_t)(v.x & 0xffffu); d[1] = (uint16_t)(v.x >> 16); d[2] = (uint16_t)(v.y & 0xffffu); d[3] = (uint16_t)(v.y >> 16);
+        d[4] = (uint16_t)(v.z & 0xffffu); d[5] = (uint16_t)(v.z >> 16); d[6] = (uint16_t)(v.w & 0xffffu); d[7] = (uint16_t)(v.w >> 16);
     }
 }
 
-// thread `pix` writes the im2col row of its pixel: bytes [0, 64) = 32 bf16 (k = r * 3 * Cin + s * Cin + c, zero beyond 9 * Cin) as swizzled
-// 16-byte chunks; zero_upper also clears bytes [64, 128) (needed when the tile is read as an N = 64 operand)
-__device__ __forceinline__ void stem_build_row(const StemParams& p, const __nv_bfloat16* xin, uint8_t* tile, int pix, bool zero_upper) {
-    const int tr = pix / p.W, wq = pix - tr * p.W;
-    const int run = 3 * p.Cin, rowlen = (p.W + 2) * p.Cin;
-    const uint16_t* xs = reinterpret_cast<const uint16_t*>(xin);
-    uint32_t packed[16];
+// thread `pix` writes the im2col row of its pixel: bytes [0, 64) = 32 bf16 (k = r * 3 * CIN + s * CIN + c, zero beyond 9 * CIN) as swizzled
+// 16-byte chunks; zero_upper also clears bytes [64, 128) (needed when the tile is read as an N = 64 operand).  CIN is a template parameter so the
+// 9 * CIN shared-memory loads have static register destinations (no division, no local memory).
+template <int CIN>
+__device__ __forceinline__ void stem_build_row(const StemParams& p, const uint16_t* xs, uint8_t* tile, int pix, bool zero_upper) {
+    constexpr int RUN = 3 * CIN;
+    const int tr = pix >> p.lw, wq = pix & (p.W - 1);
+    const int rowlen = (p.W + 2) * CIN;
+    uint32_t v[32];
 #pragma unroll
-    for (int k2 = 0; k2 < 16; ++k2) {
-        uint32_t lo = 0, hi = 0;
-        const int k0 = 2 * k2, k1 = 2 * k2 + 1;
-        if (k0 < 3 * run) { const int r = k0 / run, j = k0 - r * run; lo = xs[(tr + r) * rowlen + wq * p.Cin + j]; }
-        if (k1 < 3 * run) { const int r = k1 / run, j = k1 - r * run; hi = xs[(tr + r) * rowlen + wq * p.Cin + j]; }
-        packed[k2] = lo | (hi << 16);
+    for (int k = 0; k < 32; ++k) v[k] = 0u;
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+        const uint16_t* src = xs + (tr + r) * rowlen + wq * CIN;
+#pragma unroll
+        for (int j = 0; j < RUN; ++j) v[r * RUN + j] = src[j];
     }
     uint8_t* row = tile + pix * kStemRowBytes;
     const int sw = pix & 7;
 #pragma unroll
     for (int c = 0; c < 4; ++c)
-        *reinterpret_cast<uint4*>(row + ((c ^ sw) << 4)) = make_uint4(packed[4 * c], packed[4 * c + 1], packed[4 * c + 2], packed[4 * c + 3]);
+        *reinterpret_cast<uint4*>(row + ((c ^ sw) << 4)) = make_uint4(v[8 * c] | (v[8 * c + 1] << 16), v[8 * c + 2] | (v[8 * c + 3] << 16),
+                                                                      v[8 * c + 4] | (v[8 * c + 5] << 16), v[8 * c + 6] | (v[8 * c + 7] << 16));
     if (zero_upper) {
 #pragma unroll
         for (int c = 4; c < 8; ++c) *reinterpret_cast<uint4*>(row + ((c ^ sw) << 4)) = make_uint4(0, 0, 0, 0);
@@ -80,6 +92,7 @@ __device__ __forceinline__ void stem_build_row(const StemParams& p, const __nv_b
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
 
 // =================================================================================================================== forward
+template <int CIN>
 __global__ void __launch_bounds__(kThreads, 1) stem_fprop_kernel(const StemParams p) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -111,29 +124,36 @@ __global__ void __launch_bounds__(kThreads, 1) stem_fprop_kernel(const StemParam
         for (int c = 0; c < 4; ++c)
             *reinterpret_cast<uint4*>(row + ((c ^ (co & 7)) << 4)) = make_uint4(packed[4 * c], packed[4 * c + 1], packed[4 * c + 2], packed[4 * c + 3]);
     }
+    const int xin_stride = ((kStemXinMax * 2 + 127) & ~127) / 2;
+    for (int e = threadIdx.x; e < 2 * xin_stride; e += kThreads) reinterpret_cast<uint16_t*>(xin)[e] = 0;      // the zero borders are written once
     fence_proxy_async();
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_base_smem;
     const int tiles_per_img = p.H / p.TR;
-    const int xin_stride = ((kStemXinMax * 2 + 127) & ~127) / 2;
+    const int nvr = p.W * CIN / 8;
 
     if (warp < 4) {
         // ===================================================== builders (128 threads) + MMA issue by warp 0
         const int tid = threadIdx.x;
         constexpr uint32_t idesc = umma_idesc_bf16(128, 64, 0, 0);
         int it = 0;
+        uint4 pre = make_uint4(0, 0, 0, 0);
+        if ((int)blockIdx.x < p.n_tiles) { const int n = blockIdx.x / tiles_per_img; pre = stem_load_vec(p, n, ((int)blockIdx.x - n * tiles_per_img) * p.TR, tid, nvr); }
         for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++it) {
             const int s = it & 1;
             const uint32_t ph = (uint32_t)(it >> 1) & 1u;
             const int n = tile / tiles_per_img, h0 = (tile - n * tiles_per_img) * p.TR;
+            const uint4 cur = pre;
+            const int nxt = tile + gridDim.x;
+            if (nxt < p.n_tiles) { const int nn = nxt / tiles_per_img; pre = stem_load_vec(p, nn, (nxt - nn * tiles_per_img) * p.TR, tid, nvr); }   // in flight during this tile
             if (!mbar_wait(a_empty + s, ph ^ 1)) *p.err = 61;                      // the MMAs that read this A buffer have retired (a timeout is
                                                                                    // reported and the loop goes on: nobody may skip the named barriers)
-            __nv_bfloat16* xs = xin + s * xin_stride;
-            stem_stage_patch(p, n, h0, xs, tid);
+            uint16_t* xs = reinterpret_cast<uint16_t*>(xin) + s * xin_stride;
+            stem_store_vec(p, xs, tid, nvr, cur);
             named_bar_sync(1, 128);
-            stem_build_row(p, xs, sa + s * kStemTile, tid, false);
+            stem_build_row<CIN>(p, xs, sa + s * kStemTile, tid, false);
             fence_proxy_async();
             named_bar_sync(1, 128);
             if (warp == 0) {
@@ -183,6 +203,7 @@ __global__ void __launch_bounds__(kThreads, 1) stem_fprop_kernel(const StemParam
 // =================================================================================================================== weight gradient
 constexpr int kStemWgStages = 4;
 
+template <int CIN>
 __global__ void __launch_bounds__(kThreads, 1) stem_wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmap_dy, const StemParams p) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -205,11 +226,13 @@ __global__ void __launch_bounds__(kThreads, 1) stem_wgrad_tc_kernel(const __grid
         fence_barrier_init();
     }
     if (warp == 2) tmem_alloc(tmem_base_smem, 64);
+    for (int e = threadIdx.x; e < 2 * xin_stride; e += kThreads) reinterpret_cast<uint16_t*>(xin)[e] = 0;      // zero borders, written once
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_base_smem;
     const int tiles_per_img = p.H / p.TR;
+    const int nvr = p.W * CIN / 8;
     const int my_tiles = blockIdx.x < p.n_tiles ? (p.n_tiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
 
     if (warp == 0) {
@@ -251,14 +274,18 @@ __global__ void __launch_bounds__(kThreads, 1) stem_wgrad_tc_kernel(const __grid
         // ===================================================== im2col builders (128 threads), then the final drain of D
         const int tid = threadIdx.x - kEpiWarp0 * 32, q = warp & 3;
         int it = 0;
+        uint4 pre = make_uint4(0, 0, 0, 0);
+        if ((int)blockIdx.x < p.n_tiles) { const int n = blockIdx.x / tiles_per_img; pre = stem_load_vec(p, n, ((int)blockIdx.x - n * tiles_per_img) * p.TR, tid, nvr); }
         for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++it) {
             const int b = it & 1;
-            const int n = tile / tiles_per_img, h0 = (tile - n * tiles_per_img) * p.TR;
+            const uint4 cur = pre;
+            const int nxt = tile + gridDim.x;
+            if (nxt < p.n_tiles) { const int nn = nxt / tiles_per_img; pre = stem_load_vec(p, nn, (nxt - nn * tiles_per_img) * p.TR, tid, nvr); }
             if (!mbar_wait(xi_empty + b, ((uint32_t)(it >> 1) & 1u) ^ 1)) *p.err = 74;
-            __nv_bfloat16* xs = xin + b * xin_stride;
-            stem_stage_patch(p, n, h0, xs, tid);
+            uint16_t* xs = reinterpret_cast<uint16_t*>(xin) + b * xin_stride;
+            stem_store_vec(p, xs, tid, nvr, cur);
             named_bar_sync(1, 128);
-            stem_build_row(p, xs, sxi + b * kStemTile, tid, true);
+            stem_build_row<CIN>(p, xs, sxi + b * kStemTile, tid, true);
             fence_proxy_async();
             mbar_arrive(xi_full + b);                     // release: the row stores above are ordered before the arrival
         }
@@ -288,7 +315,7 @@ __global__ void stem_finish_kernel(float* __restrict__ acc, __nv_bfloat16* __res
 
 // ------------------------------------------------------------------------------------------------------------------ host
 bool stem_tc_eligible(int H, int W, int Cin, int Cout, int R, int S, int stride, int pad) {
-    return R == 3 && S == 3 && stride == 1 && pad == 1 && Cin >= 1 && Cin <= 3 && Cout == 64 && W >= 8 && W <= 32 && 128 % W == 0 && H % (128 / W) == 0;
+    return R == 3 && S == 3 && stride == 1 && pad == 1 && Cin >= 1 && Cin <= 3 && Cout == 64 && (W == 8 || W == 16 || W == 32) && H % (128 / W) == 0;
 }
 
 static int stem_smem_bytes(bool wgrad) {
@@ -303,11 +330,19 @@ const char* stem_fprop(const void* X, const void* Wt, void* Y, const void* bias,
     p.N = Cout; p.bias = (const __nv_bfloat16*)bias; p.relu = relu; p.C = (__nv_bfloat16*)Y; p.stats = stats;
     p.x = (const __nv_bfloat16*)X; p.w = (const __nv_bfloat16*)Wt; p.NB = NB; p.H = H; p.W = W; p.Cin = Cin; p.TR = 128 / W;
     p.n_tiles = NB * (H / p.TR); p.err = err_word();
+    p.lw = W == 32 ? 5 : (W == 16 ? 4 : 3);
     const int smem = stem_smem_bytes(false);
     static bool attr = false;
-    if (!attr) { if (cudaFuncSetAttribute(stem_fprop_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) return "cannot raise dynamic smem"; attr = true; }
+    if (!attr) {
+        if (cudaFuncSetAttribute(stem_fprop_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess ||
+            cudaFuncSetAttribute(stem_fprop_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess ||
+            cudaFuncSetAttribute(stem_fprop_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) return "cannot raise dynamic smem";
+        attr = true;
+    }
     const int grid = p.n_tiles < num_sms() ? p.n_tiles : num_sms();
-    stem_fprop_kernel<<<grid, kThreads, smem, stream>>>(p);
+    if (Cin == 1) stem_fprop_kernel<1><<<grid, kThreads, smem, stream>>>(p);
+    else if (Cin == 2) stem_fprop_kernel<2><<<grid, kThreads, smem, stream>>>(p);
+    else stem_fprop_kernel<3><<<grid, kThreads, smem, stream>>>(p);
     return cudaGetLastError() == cudaSuccess ? nullptr : "stem_fprop launch failed";
 }
 
@@ -317,6 +352,7 @@ const char* stem_wgrad_tc(const void* dY, const void* X, void* dW, float* scratc
     StemParams p{};
     p.N = Cout; p.x = (const __nv_bfloat16*)X; p.NB = NB; p.H = H; p.W = W; p.Cin = Cin; p.TR = 128 / W;
     p.n_tiles = NB * (H / p.TR); p.dW32 = scratch32; p.err = err_word();
+    p.lw = W == 32 ? 5 : (W == 16 ? 4 : 3);
     CUtensorMap ta;
     uint64_t da[4] = {(uint64_t)Cout, (uint64_t)W, (uint64_t)H, (uint64_t)NB};
     uint64_t sa[3] = {(uint64_t)Cout * 2, (uint64_t)W * Cout * 2, (uint64_t)H * W * Cout * 2};
@@ -324,9 +360,16 @@ const char* stem_wgrad_tc(const void* dY, const void* X, void* dW, float* scratc
     if (const char* e = make_tmap(&ta, dY, 4, da, sa, boxa, es)) return e;
     const int smem = stem_smem_bytes(true);
     static bool attr = false;
-    if (!attr) { if (cudaFuncSetAttribute(stem_wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) return "cannot raise dynamic smem"; attr = true; }
+    if (!attr) {
+        if (cudaFuncSetAttribute(stem_wgrad_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess ||
+            cudaFuncSetAttribute(stem_wgrad_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess ||
+            cudaFuncSetAttribute(stem_wgrad_tc_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) return "cannot raise dynamic smem";
+        attr = true;
+    }
     const int grid = p.n_tiles < num_sms() ? p.n_tiles : num_sms();
-    stem_wgrad_tc_kernel<<<grid, kThreads, smem, stream>>>(ta, p);
+    if (Cin == 1) stem_wgrad_tc_kernel<1><<<grid, kThreads, smem, stream>>>(ta, p);
+    else if (Cin == 2) stem_wgrad_tc_kernel<2><<<grid, kThreads, smem, stream>>>(ta, p);
+    else stem_wgrad_tc_kernel<3><<<grid, kThreads, smem, stream>>>(ta, p);
     const int n = Cout * 9 * Cin;
     stem_finish_kernel<<<(n + 255) / 256, 256, 0, stream>>>(scratch32, (__nv_bfloat16*)dW, n);
     return cudaGetLastError() == cudaSuccess ? nullptr : "stem_wgrad launch failed";

@@ -26,7 +26,8 @@ struct TcParams {
     const __nv_bfloat16* bias;
     const __nv_bfloat16* residual;      // optional [M,N] tensor added in the epilogue (dgrad + skip-gradient fusion)
     int relu;
-    int R, halo_w, a_stage_bytes;       // halo kernel: filter rows, halo box width, bytes per A stage
+    int R, halo_w, a_stage_bytes;       // halo kernel: filter rows, patch pitch in pixels, bytes reserved per A stage
+    int a_tx_bytes;                     // halo kernel: bytes one patch load actually delivers
     int b_resident, a_stages, b_stages; // weight-stationary mode: all filter rows of B stay in smem for the whole kernel (halo kernels)
     int desc_mode;
     __nv_bfloat16* C;

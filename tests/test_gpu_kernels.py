@@ -261,16 +261,16 @@ def test_k_of_p_staggered_arrivals_use_one_worker_set(ext):
     T = 128 * 1024
     tr, master, opt_, lowp, grads = _k_of_p_setup(T)
     vals = {0: 1.0, 1: 10.0, 2: 100.0}
-    ps_stream, side = torch.cuda.Stream(), torch.cuda.current_stream()
-    src = {s: torch.full((T,), v, device="cuda") for s, v in vals.items()}
+    ps_stream, push_stream = torch.cuda.Stream(), torch.cuda.Stream()      # two pool streams: neither is the (legacy) default stream
     torch.cuda.synchronize()
     with torch.cuda.stream(ps_stream):
         tr.ps_reduce_update(1, 2, opt_, master, lowp=lowp)          # starts polling: nothing has arrived yet
-    for slot in (2, 0, 1):                                            # arrivals staggered by ~2 ms each while the kernel spins
-        torch.cuda._sleep(int(3e6))
-        grads.flat.copy_(src[slot])
-        tr._slot_override = slot
-        tr.worker_push_bucket(0, grads)
+    with torch.cuda.stream(push_stream):
+        for slot in (2, 0, 1):                                        # arrivals staggered by ~2 ms each while the kernel spins
+            torch.cuda._sleep(int(3e6))
+            grads.flat.fill_(vals[slot])                              # a kernel, not a cudaMemcpy (which may wait for the spinning kernel)
+            tr._slot_override = slot
+            tr.worker_push_bucket(0, grads)
     torch.cuda.synchronize(); tr.check_error()
     u = master.flat.unique()
     assert u.numel() == 1, "tiles of one update used different worker subsets: %s" % u[:8].tolist()
@@ -546,11 +546,13 @@ def test_bn_finalize_wide_matches_default(ext, C, HW):
 
 @pytest.mark.parametrize("shape", [(8, 64, 32, 32, 64, 3, 1, 1), (4, 64, 16, 16, 128, 3, 1, 1), (2, 64, 56, 56, 64, 3, 1, 1), (3, 128, 24, 16, 256, 3, 1, 1),
                                    (1, 64, 16, 8, 64, 3, 1, 1)])
-def test_tc_conv_halo_cta_pair(ext, shape):
+@pytest.mark.parametrize("pitch", [16, 0])
+def test_tc_conv_halo_cta_pair(ext, shape, pitch):
     """tc_conv_halo2_kernel (cta_group::2): same contract as test_tc_conv_fprop; the last shape has an odd number of M tiles (ghost half)."""
     NB, Cin, H, W, Cout, R, st, pad = shape
     ext.tc_set_conv_algo(1)
     ext.tc_set_halo_pair(1)
+    ext.tc_set_halo_pitch(pitch)          # 0: patch rows of exactly 8 + S - 1 pixels (row groups 1280 B apart)
     torch.manual_seed(0)
     x = (torch.randn(NB, Cin, H, W, device="cuda") * 0.5).to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
     w = (torch.randn(Cout, Cin, R, R, device="cuda") * (1.0 / math.sqrt(Cin * R * R))).to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
@@ -559,6 +561,7 @@ def test_tc_conv_halo_cta_pair(ext, shape):
         torch.cuda.synchronize()
     finally:
         ext.tc_set_conv_algo(-1)
+        ext.tc_set_halo_pitch(16)
     assert ext.tc_error() == 0
     ref = F.conv2d(x.float(), w.float(), None, st, pad)
     assert (y.float() - ref).abs().max().item() <= 0.02 * max(1.0, ref.abs().max().item())
@@ -666,6 +669,7 @@ def test_basic_block_skip_gradient_fused_in_dgrad(ext, cin, planes, stride):
     grads, outs = [], []
     for fused in (True, False):
         C.set_skip_fusion(fused)
+        n0 = C.skip_fused_count
         try:
             x = x0.clone().requires_grad_(True)
             blk.zero_grad()
@@ -677,6 +681,7 @@ def test_basic_block_skip_gradient_fused_in_dgrad(ext, cin, planes, stride):
             torch.cuda.synchronize()
         finally:
             C.set_skip_fusion(True)
+        assert C.skip_fused_count - n0 == (1 if fused else 0), "the skip gradient must be added inside conv1's dgrad epilogue exactly when fusion is on"
         grads.append(x.grad.float()); outs.append(y.float())
     assert ext.tc_error() == 0
     xr = x0.float().requires_grad_(True)
@@ -721,7 +726,7 @@ def test_conv_epilogue_bn_statistics(ext, shape):
         assert (rv1 - rv2).abs().max().item() <= 1e-2 and (rm1 - rm2).abs().max().item() <= 1e-3
 
 
-@pytest.mark.parametrize("shape", [(16, 3, 32, 32), (5, 3, 16, 16), (7, 1, 32, 32), (3, 3, 8, 8), (4, 2, 24, 16)])
+@pytest.mark.parametrize("shape", [(16, 3, 32, 32), (5, 3, 16, 16), (7, 1, 32, 32), (3, 3, 16, 8), (4, 2, 24, 16)])
 @pytest.mark.parametrize("relu_bias", [False, True])
 def test_stem_tensorcore_fprop_and_wgrad(ext, shape, relu_bias):
     """Network stem (3x3/s1/p1, Cin <= 3 -> 64): thread-built im2col rows + tcgen05 forward and weight gradient vs an fp32 reference."""
