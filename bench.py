@@ -233,20 +233,27 @@ def main():
     if hasattr(job.comm, "check_error"):
         job.comm.check_error()
     # ---- exposed communication, measured directly: CUDA events around wait-weights / push / reduce+update+broadcast (engine.PSJob.time_comm)
-    exposed = None
+    exposed = exposed_max = None
     if hasattr(job, "time_comm"):
         job.time_comm(True)
         loss2 = run(min(a.steps, 20), False)
         barrier()
         cm = job.comm_ms_per_step()
         job.time_comm(False)
-        t = torch.tensor([cm if cm is not None else 0.0], dtype=torch.float64)
+        # Every rank has the same step period T = compute_r + C_r (synchronous training), where C_r is the bracketed time (spins included).
+        # The rank with the longest compute has the smallest C_r: MIN over ranks = the communication the critical path is exposed to;
+        # MAX additionally contains the time faster ranks spend waiting for the slowest one (skew, not communication).
+        tmin = torch.tensor([cm if cm is not None else 1e9], dtype=torch.float64)
+        tmax = torch.tensor([cm if cm is not None else 0.0], dtype=torch.float64)
         if world > 1:
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        exposed = float(t[0])
+            dist.all_reduce(tmin, op=dist.ReduceOp.MIN)
+            dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        exposed, exposed_max = float(tmin[0]), float(tmax[0])
         loss = loss2 if loss2 is not None else loss
     # ---- self-verification: every replica must hold exactly the bf16 rounding of rank 0's fp32 master, and the loss must have fallen
     barrier()
+    if hasattr(job.comm, "gather_master") and job.master is not None:
+        job.comm.gather_master(job.master.master)          # sharded topology: rank 0's master is only authoritative for its own shard
     check = {}
     if job.worker is not None:
         rep = job.worker.compute.weights.flat
@@ -273,6 +280,7 @@ def main():
         dist.all_gather_object(both, (lf, float(lt[0])))
         good = [b for b in both if b[1] == b[1]]
         lf, lt = good[0][0], torch.tensor([good[0][1]])
+    transport_name = job.comm.name + ":" + getattr(getattr(job.comm, "arena", None), "backend", "-")
     nccl_base = None
     if not a.no_baseline and a.network == "ResNet18" and a.dataset == "Cifar10" and not a.global_batch:
         try:
@@ -294,13 +302,13 @@ def main():
                           "per_worker_batch": B, "seq_len": None,
                           "parallelism": "%s: 1 server + %d workers on %d GPUs%s" % (a.topology, nworkers, world, " (worker co-located on the PS GPU)" if colocate else ""),
                           "grad_wire": a.grad_dtype, "optimizer": a.optimizer + " momentum 0.9, fused in the PS kernel", "backend": a.backend,
-                          "transport": job.comm.name + ":" + getattr(getattr(job.comm, "arena", None), "backend", "-"),
+                          "transport": transport_name,
                           "cuda_graph": not a.no_graph,
                           "conv": "tcgen05 implicit-GEMM (ours)" if _tc_conv() else "cuDNN (library); all other layers + PS kernels ours",
                           "l2": "inputs rotate over 8 distinct pinned host batches; per-step activation working set (~3 GB) >> 126 MB L2"},
                "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "wall_ms_per_step": wall_ms / a.steps,
                "first_loss": lf, "final_loss": float(lt[0]), "loss_fell": bool(float(lt[0]) < 0.8 * lf) if lf == lf else None,
-               "replica_check": check, "exposed_comm_ms": exposed,
+               "replica_check": check, "exposed_comm_ms": exposed, "comm_incl_peer_wait_ms_max": exposed_max,
                "nccl_baseline": nccl_base,
                "vs_nccl_baseline": (value / nccl_base["value"]) if (nccl_base and nccl_base.get("value")) else None}
         print(json.dumps(out))

@@ -63,9 +63,10 @@ class LayerwiseBackwardMixin:
             return self.fc2(x)
         if tag == "stem":
             out = self.bn1(self.conv1(x, bn=self.bn1), relu=True)
-            return torch.nn.functional.max_pool2d(out, 3, 2, 1) if self.imagenet else out
+            return self.stem_pool(out) if self.imagenet else out
         if tag == "head":
-            out = x.mean(dim=(2, 3)) if self.imagenet else self.pool(x).reshape(x.size(0), -1)
+            from .resnet import _global_mean
+            out = _global_mean(x) if self.imagenet else self.pool(x).reshape(x.size(0), -1)
             return self.linear(out)
         ln, i = tag.split(".")
         return getattr(self, ln)[int(i)](x)

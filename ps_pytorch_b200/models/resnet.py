@@ -93,6 +93,7 @@ class ResNet(tnn.Module):
         self.layer4 = self._make_layer(block, 512, num_blocks[3], stride=2)
         self.linear = nn.Linear(512 * block.expansion, num_classes)
         self.pool = nn.AvgPool2d(4)  # parameter-free: does not change the state_dict
+        self.stem_pool = nn.MaxPool2d(3, 2, 1) if imagenet else None
 
     def _make_layer(self, block, planes, num_blocks, stride):
         layers = []
@@ -104,13 +105,21 @@ class ResNet(tnn.Module):
     def forward(self, x):
         out = self.bn1(self.conv1(x, bn=self.bn1), relu=True)
         if self.imagenet:
-            out = F.max_pool2d(out, 3, 2, 1)
+            out = self.stem_pool(out)
         out = self.layer4(self.layer3(self.layer2(self.layer1(out))))
         if self.imagenet:
-            out = out.mean(dim=(2, 3))
+            out = _global_mean(out)
         else:
             out = self.pool(out).reshape(out.size(0), -1)
         return self.linear(out)
+
+
+def _global_mean(x):
+    """Global average pool -> [N, C] (our kernel on the sm100 backend, ATen otherwise)."""
+    if use_sm100(x) and x.dim() == 4 and x.size(1) % 8 == 0 and str(x.dtype) == "torch.bfloat16":
+        from ..ops import elementwise as _ew
+        return _ew.global_avg_pool(x).reshape(x.size(0), -1)
+    return x.mean(dim=(2, 3))
 
 
 def ResNet18(num_classes=10, imagenet=False):

@@ -119,6 +119,9 @@ class MaxPool2d(nn.MaxPool2d):
             why = _ew.pool_unsupported_reason(x, self.kernel_size, self.stride, self.padding)
             if why is None:
                 return _ew.max_pool2x2(x, relu)
+            if _ew.pool3_supported(x, self.kernel_size, self.stride, self.padding):
+                y = _ew.max_pool3x3s2(x)
+                return _ew.relu(y) if relu else y
             note_fallback("max_pool2d", why)
         y = F.max_pool2d(x, self.kernel_size, self.stride, self.padding)
         return F.relu(y) if relu else y
@@ -137,6 +140,11 @@ class AvgPool2d(nn.AvgPool2d):
 
 class Dropout(nn.Dropout):
     def forward(self, x):
+        if self.training and use_sm100(x):
+            from ..ops import elementwise as _ew
+            if _ew.dropout_supported(x, self.p):
+                return _ew.dropout(x, self.p, self)
+            note_fallback("dropout", "needs a contiguous bf16 tensor with numel % 8 == 0")
         return F.dropout(x, self.p, self.training, self.inplace)
 
 

@@ -43,6 +43,8 @@ def _apply_switches(ext):
         ext.tc_set_halo_pair(int(os.environ["PSB200_TC_HALO_PAIR"]))
     if os.environ.get("PSB200_TC_HALO_PITCH", "") != "":           # 16 = 2 KB patch rows, 0 = tight (8 + S - 1 pixels)
         ext.tc_set_halo_pitch(int(os.environ["PSB200_TC_HALO_PITCH"]))
+    if os.environ.get("PSB200_WGRAD_SMS", "") != "":               # cap the grid of the side-stream weight-gradient kernels (experiments)
+        ext.tc_set_wgrad_sms(int(os.environ["PSB200_WGRAD_SMS"]))
     if os.environ.get("PSB200_TC_CONV_ALGO", "") != "":            # -1 auto (halo where eligible), 0 per-tap, 1 halo
         ext.tc_set_conv_algo(int(os.environ["PSB200_TC_CONV_ALGO"]))
     _applied = True

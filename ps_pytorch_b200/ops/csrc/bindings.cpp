@@ -27,6 +27,11 @@ at::Tensor relu_forward(at::Tensor);
 at::Tensor relu_backward(at::Tensor, at::Tensor);
 at::Tensor maxpool2x2_forward(at::Tensor, bool);
 at::Tensor maxpool2x2_backward(at::Tensor, at::Tensor, bool);
+at::Tensor maxpool3x3s2_forward(at::Tensor);
+at::Tensor maxpool3x3s2_backward(at::Tensor, at::Tensor, at::Tensor);
+std::vector<at::Tensor> dropout_forward(at::Tensor, double, at::Tensor, int64_t);
+at::Tensor dropout_backward(at::Tensor, double, at::Tensor);
+void bump_word(at::Tensor);
 at::Tensor gap_forward(at::Tensor);
 at::Tensor gap_backward(at::Tensor, int64_t, int64_t);
 std::vector<at::Tensor> softmax_ce(at::Tensor, at::Tensor);
@@ -58,6 +63,8 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
           pybind11::arg("conv_partial") = c10::optional<at::Tensor>()); m.def("bn_backward", &bn_backward); m.def("bn_set_finalize_wide", &bn_set_finalize_wide);
     m.def("relu_forward", &relu_forward); m.def("relu_backward", &relu_backward);
     m.def("maxpool2x2_forward", &maxpool2x2_forward); m.def("maxpool2x2_backward", &maxpool2x2_backward);
+    m.def("maxpool3x3s2_forward", &maxpool3x3s2_forward); m.def("maxpool3x3s2_backward", &maxpool3x3s2_backward);
+    m.def("dropout_forward", &dropout_forward); m.def("dropout_backward", &dropout_backward); m.def("bump_word", &bump_word);
     m.def("gap_forward", &gap_forward); m.def("gap_backward", &gap_backward); m.def("softmax_ce", &softmax_ce);
     m.def("vmm_alloc", &vmm_alloc); m.def("vmm_import", &vmm_import); m.def("vmm_unmap", &vmm_unmap);
     m.def("multicast_supported", &multicast_supported); m.def("mc_granularity", &mc_granularity); m.def("mc_create", &mc_create);

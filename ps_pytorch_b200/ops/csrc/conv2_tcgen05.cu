@@ -127,6 +127,7 @@ tc_conv2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
     } else if (warp == 1 && leader) {
         // ===================================================== MMA issuer (leader CTA only)
         constexpr uint32_t idesc = umma_idesc_bf16(256, BN, 0, 0);
+        const uint64_t tmpl = umma_desc_k_sw128(0);          // descriptors are advanced by adding (byte offset >> 4) to the address field
         int stage = 0; uint32_t phase = 0; int acc = 0; uint32_t acc_phase = 0;
         for (int t = cluster_id; t < n_ptiles; t += n_clusters) {
             const int cls = (t / p.n_tiles_n) / pairs_per_cls;
@@ -138,11 +139,11 @@ tc_conv2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
                 if (!mbar_wait(full_bar + stage, phase)) { *p.err = 33; goto teardown; }
                 tc_fence_after();
                 const uint32_t sa = smem_u32(smem + stage * Cfg::kStageBytes);
-                const uint32_t sb = sa + Cfg::kABytes;
+                const uint64_t da = tmpl + (uint64_t)((sa & 0x3FFFFu) >> 4), db = da + (uint64_t)(Cfg::kABytes >> 4);
                 if (elect_one()) {
 #pragma unroll
                     for (int k = 0; k < BK / 16; ++k)
-                        tc_mma2_bf16(tmem_d, umma_desc_k_sw128(sa + k * 32), umma_desc_k_sw128(sb + k * 32), idesc, (kb | k) != 0);
+                        tc_mma2_bf16(tmem_d, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, k != 0 ? 1u : (uint32_t)(kb != 0));
                     tc_commit2_mcast(empty_bar + stage, 0b11);       // the stage is free in BOTH CTAs once these MMAs retire
                 }
                 __syncwarp();

@@ -1,5 +1,5 @@
 // Small memory-bound layers of the reference models as sm_100a streaming kernels (NHWC bf16, 16-byte vectors):
-// ReLU, MaxPool2d(2,2) (+ fused ReLU, LeNet's pool->relu), global average pool, and a fused softmax-cross-entropy
+// ReLU, MaxPool2d(2,2) (+ fused ReLU, LeNet's pool->relu), MaxPool2d(3,2,1) (ImageNet stem), Dropout, global average pool, and a fused softmax-cross-entropy
 // that produces the loss and dL/dlogits in one pass (reference ops: /root/reference/src/model_ops/lenet.py:26-31,
 // vgg.py:51, resnet.py:94, distributed_worker.py:98).
 #include <torch/extension.h>
@@ -117,6 +117,156 @@ at::Tensor maxpool2x2_backward(at::Tensor dy, at::Tensor x, bool relu) {
     else maxpool_bwd_kernel<false><<<ew_grid(total), 256, 0, s>>>((const uint4*)dy.data_ptr(), (const uint4*)x.data_ptr(), (uint4*)dx.data_ptr(), N, H, W, C / 8);
     C10_CUDA_KERNEL_LAUNCH_CHECK();
     return dx;
+}
+
+// ---- MaxPool 3x3 / stride 2 / pad 1, NHWC (the ImageNet ResNet stem) ---------------------------------------------------------
+// forward: max over the (clipped) window.  backward is a GATHER over dx pixels — every input pixel belongs to at most 2 x 2 windows; it
+// receives dy of a window iff it is that window's first maximum in window order (ATen's tie rule) — so no atomics and dx is written once.
+__global__ void maxpool3s2_fwd_kernel(const uint4* __restrict__ x, uint4* __restrict__ y, int N, int H, int W, int Ho, int Wo, int LC) {
+    const long long total = (long long)N * Ho * Wo * LC;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int l = (int)(i % LC); long long p = i / LC;
+        const int wo = (int)(p % Wo); p /= Wo;
+        const int ho = (int)(p % Ho); const long long n = p / Ho;
+        float m[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) m[j] = -INFINITY;
+        for (int r = 0; r < 3; ++r) {
+            const int h = 2 * ho - 1 + r;
+            if (h < 0 || h >= H) continue;
+            for (int c = 0; c < 3; ++c) {
+                const int w = 2 * wo - 1 + c;
+                if (w < 0 || w >= W) continue;
+                float a[8];
+                unpack8(ld_nc_v4(x + ((n * H + h) * W + w) * LC + l), a);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) m[j] = fmaxf(m[j], a[j]);
+            }
+        }
+        st_v4(y + i, pack8(m));
+    }
+}
+__global__ void maxpool3s2_bwd_kernel(const uint4* __restrict__ dy, const uint4* __restrict__ x, const uint4* __restrict__ y, uint4* __restrict__ dx,
+                                      int N, int H, int W, int Ho, int Wo, int LC) {
+    const long long total = (long long)N * H * W * LC;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int l = (int)(i % LC); long long p = i / LC;
+        const int w = (int)(p % W); p /= W;
+        const int h = (int)(p % H); const long long n = p / H;
+        float xv[8], g[8];
+        unpack8(ld_nc_v4(x + i), xv);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) g[j] = 0.f;
+        // windows (ho, wo) that contain (h, w): 2*ho - 1 <= h <= 2*ho + 1
+        const int ho0 = h / 2, ho1 = (h + 1) / 2, wo0 = w / 2, wo1 = (w + 1) / 2;
+        for (int ho = ho0; ho <= ho1; ++ho) {
+            if (ho >= Ho) continue;
+            for (int wo = wo0; wo <= wo1; ++wo) {
+                if (wo >= Wo) continue;
+                const long long o = ((n * Ho + ho) * Wo + wo) * LC + l;
+                float yv[8], dv[8];
+                unpack8(ld_nc_v4(y + o), yv); unpack8(ld_nc_v4(dy + o), dv);
+                // is (h, w) the FIRST element of this window (row-major) equal to the window maximum?
+                bool first[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) first[j] = xv[j] == yv[j];
+                for (int r = 0; r < 3; ++r) {
+                    const int hh = 2 * ho - 1 + r;
+                    if (hh < 0 || hh >= H) continue;
+                    for (int c = 0; c < 3; ++c) {
+                        const int ww = 2 * wo - 1 + c;
+                        if (ww < 0 || ww >= W) continue;
+                        if (hh > h || (hh == h && ww >= w)) continue;            // only elements BEFORE (h, w) in window order
+                        float a[8];
+                        unpack8(ld_nc_v4(x + ((n * H + hh) * W + ww) * LC + l), a);
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) if (a[j] == yv[j]) first[j] = false;
+                    }
+                }
+#pragma unroll
+                for (int j = 0; j < 8; ++j) if (first[j]) g[j] += dv[j];
+            }
+        }
+        st_v4(dx + i, pack8(g));
+    }
+}
+at::Tensor maxpool3x3s2_forward(at::Tensor x) {
+    check_nhwc(x);
+    const int N = x.size(0), C = x.size(1), H = x.size(2), W = x.size(3);
+    const int Ho = (H + 2 - 3) / 2 + 1, Wo = (W + 2 - 3) / 2 + 1;
+    at::Tensor y = at::empty({N, C, Ho, Wo}, x.options().memory_format(at::MemoryFormat::ChannelsLast));
+    const long long total = (long long)N * Ho * Wo * (C / 8);
+    maxpool3s2_fwd_kernel<<<ew_grid(total), 256, 0, at::cuda::getCurrentCUDAStream()>>>((const uint4*)x.data_ptr(), (uint4*)y.data_ptr(), N, H, W, Ho, Wo, C / 8);
+    C10_CUDA_KERNEL_LAUNCH_CHECK();
+    return y;
+}
+at::Tensor maxpool3x3s2_backward(at::Tensor dy, at::Tensor x, at::Tensor y) {
+    check_nhwc(x); check_nhwc(dy); check_nhwc(y);
+    const int N = x.size(0), C = x.size(1), H = x.size(2), W = x.size(3), Ho = y.size(2), Wo = y.size(3);
+    at::Tensor dx = at::empty_like(x);
+    const long long total = (long long)N * H * W * (C / 8);
+    maxpool3s2_bwd_kernel<<<ew_grid(total), 256, 0, at::cuda::getCurrentCUDAStream()>>>((const uint4*)dy.data_ptr(), (const uint4*)x.data_ptr(), (const uint4*)y.data_ptr(),
+                                                                                         (uint4*)dx.data_ptr(), N, H, W, Ho, Wo, C / 8);
+    C10_CUDA_KERNEL_LAUNCH_CHECK();
+    return dx;
+}
+
+// ---- Dropout (VGG classifier): counter-based mask, nothing stored ---------------------------------------------------------------------
+// keep(i) = hash(seed, i) >= p * 2^32; y = keep ? x / (1 - p) : 0.  The backward pass recomputes the same mask from the same (seed, i).
+// `seed_ptr` is a device word (bumped once per training step by the owner of the step), so a CUDA graph replays with fresh masks; the
+// value used is written to `used_seed` for the backward pass.
+__device__ __forceinline__ uint32_t mix32(uint64_t v) {
+    v ^= v >> 33; v *= 0xff51afd7ed558ccdULL; v ^= v >> 33; v *= 0xc4ceb9fe1a85ec53ULL; v ^= v >> 33;
+    return (uint32_t)v;
+}
+__global__ void dropout_kernel(const uint4* __restrict__ x, uint4* __restrict__ y, long long nvec, float p, const long long* __restrict__ seed_ptr,
+                               long long salt, long long* __restrict__ used_seed) {
+    const long long seed = seed_ptr[0] * 0x9E3779B97F4A7C15LL + salt;
+    if (used_seed != nullptr && blockIdx.x == 0 && threadIdx.x == 0) used_seed[0] = seed;
+    const uint32_t thr = (uint32_t)fminf(p * 4294967296.f, 4294967295.f);
+    const float scale = 1.f / (1.f - p);
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += (long long)gridDim.x * blockDim.x) {
+        float a[8];
+        unpack8(ld_nc_v4(x + i), a);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) a[j] = mix32((uint64_t)seed ^ (uint64_t)(i * 8 + j) * 0xD6E8FEB86659FD93ULL) >= thr ? a[j] * scale : 0.f;
+        st_v4(y + i, pack8(a));
+    }
+}
+__global__ void dropout_bwd_kernel(const uint4* __restrict__ dy, uint4* __restrict__ dx, long long nvec, float p, const long long* __restrict__ used_seed) {
+    const long long seed = used_seed[0];
+    const uint32_t thr = (uint32_t)fminf(p * 4294967296.f, 4294967295.f);
+    const float scale = 1.f / (1.f - p);
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += (long long)gridDim.x * blockDim.x) {
+        float a[8];
+        unpack8(ld_nc_v4(dy + i), a);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) a[j] = mix32((uint64_t)seed ^ (uint64_t)(i * 8 + j) * 0xD6E8FEB86659FD93ULL) >= thr ? a[j] * scale : 0.f;
+        st_v4(dx + i, pack8(a));
+    }
+}
+std::vector<at::Tensor> dropout_forward(at::Tensor x, double p, at::Tensor seed_state, int64_t salt) {
+    TORCH_CHECK(x.is_cuda() && x.scalar_type() == at::kBFloat16 && x.is_contiguous() && x.numel() % 8 == 0, "dropout: contiguous bf16 tensor with numel % 8 == 0");
+    TORCH_CHECK(seed_state.is_cuda() && seed_state.scalar_type() == at::kLong && seed_state.numel() >= 1);
+    at::Tensor y = at::empty_like(x), used = at::empty({1}, seed_state.options());
+    dropout_kernel<<<ew_grid(x.numel() / 8), 256, 0, at::cuda::getCurrentCUDAStream()>>>((const uint4*)x.data_ptr(), (uint4*)y.data_ptr(), x.numel() / 8, (float)p,
+                                                                                       (const long long*)seed_state.data_ptr(), salt, (long long*)used.data_ptr());
+    C10_CUDA_KERNEL_LAUNCH_CHECK();
+    return {y, used};
+}
+at::Tensor dropout_backward(at::Tensor dy, double p, at::Tensor used_seed) {
+    TORCH_CHECK(dy.is_cuda() && dy.scalar_type() == at::kBFloat16 && dy.is_contiguous() && dy.numel() % 8 == 0);
+    at::Tensor dx = at::empty_like(dy);
+    dropout_bwd_kernel<<<ew_grid(dy.numel() / 8), 256, 0, at::cuda::getCurrentCUDAStream()>>>((const uint4*)dy.data_ptr(), (uint4*)dx.data_ptr(), dy.numel() / 8, (float)p,
+                                                                                           (const long long*)used_seed.data_ptr());
+    C10_CUDA_KERNEL_LAUNCH_CHECK();
+    return dx;
+}
+__global__ void bump_word_kernel(long long* p) { p[0] += 1; }
+void bump_word(at::Tensor t) {
+    TORCH_CHECK(t.is_cuda() && t.scalar_type() == at::kLong && t.numel() >= 1);
+    bump_word_kernel<<<1, 1, 0, at::cuda::getCurrentCUDAStream()>>>((long long*)t.data_ptr());
+    C10_CUDA_KERNEL_LAUNCH_CHECK();
 }
 
 // ---- global average pool: [N,H,W,C] -> [N,1,1,C] ---------------------------------------------------------------------------

@@ -16,6 +16,7 @@ void tc_set_halo_desc_mode(int);
 void tc_set_halo_cluster(int);
 void tc_set_halo_pair(int);
 void tc_set_halo_pitch(int);
+void tc_set_wgrad_sms(int);
 void tc_set_halo_resident(int);
 void tc_set_gemm_bn(int);
 int tc_check_error();
@@ -156,9 +157,9 @@ at::Tensor conv_wgrad(at::Tensor dy, at::Tensor x, at::Tensor scratch, int64_t R
     TORCH_CHECK(scratch.scalar_type() == at::kFloat && scratch.is_contiguous() && scratch.numel() >= (int64_t)Cout * R * S * Cin);
     at::Tensor dw = at::empty({Cout, Cin, R, S}, x.options().memory_format(at::MemoryFormat::ChannelsLast));
     const char* e;
-    // measured (profiles/run25_conv_per_layer.md): the tap-sharing kernel wins where the per-tap one is L2->SM bound, i.e. 64 output channels
-    // (175 vs 235 us on 64->64 @32x32); with 128-wide tiles the per-tap kernel is faster (98 vs 108, 92 vs 149 us)
-    const bool halo_auto = Cout % 128 != 0;
+    // measured (profiles/run28_conv_per_layer.md, after the MMA-issue fix): the CTA-pair kernel wins on 256-wide tiles (81 vs 105 us on 256->256 @8x8),
+    // the tap-sharing kernel everywhere else it applies (110 vs 223 us on 64->64 @32x32, 81 vs 94 on 128->128 @16x16)
+    const bool halo_auto = !tc_wgrad2_eligible(Cin, Cout);
     if ((g_wgrad_algo == 1 || (g_wgrad_algo == -1 && halo_auto)) && tc_wgrad_halo_eligible(H, W, Cin, Cout, (int)R, (int)S, (int)stride, (int)pad))
         e = tc_conv_wgrad_halo(dy.data_ptr(), x.data_ptr(), dw.data_ptr(), scratch.data_ptr<float>(), NB, H, W, Cin, Cout, at::cuda::getCurrentCUDAStream());
     else if ((g_wgrad_algo == 2 || g_wgrad_algo == -1) && tc_wgrad2_eligible(Cin, Cout))
@@ -240,6 +241,7 @@ void bind_gemm(pybind11::module_& m) {
     m.def("tc_set_halo_cluster", &psb::tc_set_halo_cluster);
     m.def("tc_set_halo_pair", &psb::tc_set_halo_pair);
     m.def("tc_set_halo_pitch", &psb::tc_set_halo_pitch);
+    m.def("tc_set_wgrad_sms", &psb::tc_set_wgrad_sms);
     m.def("tc_set_halo_resident", &psb::tc_set_halo_resident);
     m.def("tc_set_gemm_bn", &psb::tc_set_gemm_bn);
     m.def("conv_unsupported_reason", &psb::conv_unsupported_reason);

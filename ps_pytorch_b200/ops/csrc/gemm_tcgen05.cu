@@ -523,6 +523,7 @@ tc_conv_halo2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
         }
     } else if (warp == 1 && leader) {
         constexpr uint32_t idesc = umma_idesc_bf16(256, BN, 0, 0);
+        const uint64_t a_tmpl = umma_desc_k_sw128_sbo(0, (uint32_t)p.halo_w * 128u), b_tmpl = umma_desc_k_sw128(0);
         int as = 0; uint32_t aph = 0; int bs = 0; uint32_t bph = 0; int acc = 0; uint32_t acc_phase = 0;
         for (int pt = cluster_id; pt < n_ptiles; pt += n_clusters) {
             if (!mbar_wait(tmem_empty + acc, acc_phase ^ 1)) { *p.err = 23; goto teardown; }
@@ -530,19 +531,29 @@ tc_conv_halo2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
             const uint32_t tmem_d = tmem_base + acc * BN;
             for (int cb = 0; cb < p.cblocks; ++cb) {
                 if (!mbar_wait(a_full + as, aph)) { *p.err = 24; goto teardown; }
-                const uint32_t sa0 = smem_u32(smem_a + as * p.a_stage_bytes);
+                // Descriptors are advanced by ADDING to the 14-bit address field (byte offset >> 4; shared memory is < 256 KB, no carry out of the
+                // field): with N = 64 an MMA retires every 32 cycles, and rebuilding two 64-bit descriptors per instruction (~20 dependent
+                // integer ops in one thread) made the ISSUE loop the bound — 49 cycles per MMA measured (profiles/run28_mma_issue.md).
+                const uint64_t a0 = a_tmpl + (uint64_t)((smem_u32(smem_a + as * p.a_stage_bytes) & 0x3FFFFu) >> 4);
                 for (int r = 0; r < p.R; ++r) {
                     if (p.b_resident) { bs = cb * p.R + r; bph = 0; }        // phase 0 of a resident stage stays complete
                     if (!mbar_wait(b_full + bs, bph)) { *p.err = 25; goto teardown; }
                     tc_fence_after();
-                    const uint32_t sb0 = smem_u32(smem_b + bs * b_stage_bytes);
+                    const uint64_t ar = a0 + (uint64_t)(r * p.halo_w * 8);
+                    const uint64_t b0 = b_tmpl + (uint64_t)((smem_u32(smem_b + bs * b_stage_bytes) & 0x3FFFFu) >> 4);
                     if (elect_one()) {
-                        for (int s = 0; s < p.S; ++s) {
-                            const uint32_t sa = sa0 + (uint32_t)((r * p.halo_w + s) * 128);
-                            const uint32_t sb = sb0 + (uint32_t)(s * kHalfTapBytes);
+                        if (p.S == 3) {
 #pragma unroll
-                            for (int k = 0; k < BK / 16; ++k)
-                                tc_mma2_bf16(tmem_d, umma_desc_k_sw128_sbo(sa + k * 32, (uint32_t)p.halo_w * 128u), umma_desc_k_sw128(sb + k * 32), idesc, (cb | r | s | k) != 0);
+                            for (int s = 0; s < 3; ++s)
+#pragma unroll
+                                for (int k = 0; k < BK / 16; ++k)
+                                    tc_mma2_bf16(tmem_d, ar + (uint64_t)(s * 8 + k * 2), b0 + (uint64_t)(s * (kHalfTapBytes >> 4) + k * 2), idesc,
+                                                 (s | k) != 0 ? 1u : (uint32_t)((cb | r) != 0));
+                        } else {
+                            for (int s = 0; s < p.S; ++s)
+#pragma unroll
+                                for (int k = 0; k < BK / 16; ++k)
+                                    tc_mma2_bf16(tmem_d, ar + (uint64_t)(s * 8 + k * 2), b0 + (uint64_t)(s * (kHalfTapBytes >> 4) + k * 2), idesc, (cb | r | s | k) != 0);
                         }
                         if (!p.b_resident) tc_commit2_mcast(b_empty + bs, 0b11);
                     }
@@ -680,6 +691,7 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmap_dy, const __grid_consta
         }
     } else if (warp == 1) {
         constexpr uint32_t idesc = umma_idesc_bf16(MM, BN, 1, 1);          // both operands MN-major
+        const uint64_t wg_tmpl = umma_desc_mn_sw128(0, kWgBoxBytes);
         int stage = 0; uint32_t phase = 0; int acc = 0; uint32_t acc_phase = 0;
         for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
             int tap, ks, nt, mt; decode(item, tap, ks, nt, mt);
@@ -691,12 +703,11 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmap_dy, const __grid_consta
                 if (!mbar_wait(full_bar + stage, phase)) { *p.err = 23; return; }
                 tc_fence_after();
                 const uint32_t sa = smem_u32(smem + stage * Cfg::kStageBytes);
-                const uint32_t sb = sa + Cfg::kGroupsA * kWgBoxBytes;
+                const uint64_t da = wg_tmpl + (uint64_t)((sa & 0x3FFFFu) >> 4), db = da + (uint64_t)((Cfg::kGroupsA * kWgBoxBytes) >> 4);
                 if (elect_one()) {
 #pragma unroll
-                    for (int j = 0; j < KP / 16; ++j)            // 16 pixels per MMA = two 8-row atoms = 2048 bytes
-                        tc_mma_bf16(tmem_d, umma_desc_mn_sw128(sa + j * 2048, kWgBoxBytes), umma_desc_mn_sw128(sb + j * 2048, kWgBoxBytes), idesc,
-                                    (kb > kb0 || j > 0) ? 1u : 0u);
+                    for (int j = 0; j < KP / 16; ++j)            // 16 pixels per MMA = two 8-row atoms = 2048 bytes (descriptor address field += 128)
+                        tc_mma_bf16(tmem_d, da + (uint64_t)(j * 128), db + (uint64_t)(j * 128), idesc, j > 0 ? 1u : (uint32_t)(kb > kb0));
                     tc_commit(empty_bar + stage);
                 }
                 __syncwarp();
@@ -798,6 +809,9 @@ int tc_check_error() {
     return h;
 }
 
+static int g_wgrad_sms = 0;          // 0 = all; otherwise cap the grid of the weight-gradient kernels (they run on a side stream next to the critical path)
+void tc_set_wgrad_sms(int n) { g_wgrad_sms = n > 0 ? n : 0; }
+int wgrad_sms() { const int n = num_sms(); return g_wgrad_sms > 0 && g_wgrad_sms < n ? g_wgrad_sms : n; }
 int num_sms() {
     static int n = 0;
     if (!n) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev); }
@@ -1005,7 +1019,7 @@ static const char* launch_wgrad(const CUtensorMap& ta, const CUtensorMap& tb, co
         if (cudaFuncSetAttribute(tc_wgrad_kernel<BN, MM, KP>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes) != cudaSuccess) return "cannot raise dynamic smem";
         attr = true;
     }
-    const int grid = p.n_items < num_sms() ? p.n_items : num_sms();
+    const int grid = p.n_items < wgrad_sms() ? p.n_items : wgrad_sms();
     tc_wgrad_kernel<BN, MM, KP><<<grid, kThreads, Cfg::kSmemBytes, stream>>>(ta, tb, p);
     return cudaGetLastError() == cudaSuccess ? nullptr : "kernel launch failed";
 }
@@ -1039,7 +1053,7 @@ const char* tc_conv_wgrad(const void* dY, const void* X, void* dW, float* scratc
     p.kb_total = p.tiles_w * p.tiles_h * ((NB + BNI - 1) / BNI);
     p.co_tiles = Cout / MM; p.ci_tiles = Cin / BN;
     const int base_items = p.taps * p.co_tiles * p.ci_tiles;
-    int ksplit = (2 * num_sms() + base_items - 1) / base_items;
+    int ksplit = (2 * wgrad_sms() + base_items - 1) / base_items;
     if (ksplit < 1) ksplit = 1;
     if (ksplit > p.kb_total) ksplit = p.kb_total;
     p.kb_per_split = (p.kb_total + ksplit - 1) / ksplit;

@@ -173,5 +173,6 @@ const char* make_tmap(CUtensorMap* m, const void* base, int rank, const uint64_t
                       const uint32_t* estrides);
 int* err_word();                        // one device word shared by all launches; checked by tc_check_error()
 int num_sms();
+int wgrad_sms();                        // SMs the weight-gradient kernels may use (tc_set_wgrad_sms)
 
 }  // namespace psb

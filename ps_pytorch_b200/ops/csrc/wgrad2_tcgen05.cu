@@ -103,6 +103,7 @@ tc_wgrad2_kernel(const __grid_constant__ CUtensorMap tmap_dy, const __grid_const
         }
     } else if (warp == 1 && leader) {
         constexpr uint32_t idesc = umma_idesc_bf16(256, BN2, 1, 1);          // both operands MN-major
+        const uint64_t tmpl = umma_desc_mn_sw128(0, kWg2Box);
         int stage = 0; uint32_t phase = 0; int acc = 0; uint32_t acc_phase = 0;
         for (int item = cluster_id; item < p.n_items; item += n_clusters) {
             int tap, ks, nt, mt; decode(item, tap, ks, nt, mt);
@@ -114,12 +115,11 @@ tc_wgrad2_kernel(const __grid_constant__ CUtensorMap tmap_dy, const __grid_const
                 if (!mbar_wait(full_bar + stage, phase)) { *p.err = 53; goto teardown; }
                 tc_fence_after();
                 const uint32_t sa = smem_u32(smem + stage * Cfg::kStageBytes);
-                const uint32_t sb = sa + Cfg::kGroupsA * kWg2Box;
+                const uint64_t da = tmpl + (uint64_t)((sa & 0x3FFFFu) >> 4), db = da + (uint64_t)((Cfg::kGroupsA * kWg2Box) >> 4);
                 if (elect_one()) {
 #pragma unroll
-                    for (int j = 0; j < kWg2KP / 16; ++j)            // 16 pixels per MMA = two 8-row atoms = 2048 bytes
-                        tc_mma2_bf16(tmem_d, umma_desc_mn_sw128(sa + j * 2048, kWg2Box), umma_desc_mn_sw128(sb + j * 2048, kWg2Box), idesc,
-                                     (kb > kb0 || j > 0) ? 1u : 0u);
+                    for (int j = 0; j < kWg2KP / 16; ++j)            // 16 pixels per MMA = two 8-row atoms = 2048 bytes (address field += 128)
+                        tc_mma2_bf16(tmem_d, da + (uint64_t)(j * 128), db + (uint64_t)(j * 128), idesc, j > 0 ? 1u : (uint32_t)(kb > kb0));
                     tc_commit2_mcast(empty_bar + stage, 0b11);
                 }
                 __syncwarp();
@@ -174,7 +174,7 @@ static const char* launch_wg2(const CUtensorMap& ta, const CUtensorMap& tb, cons
         if (cudaFuncSetAttribute(tc_wgrad2_kernel<BN2>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes) != cudaSuccess) return "cannot raise dynamic smem";
         attr = true;
     }
-    int pairs = num_sms() / 2;
+    int pairs = wgrad_sms() / 2;
     if (p.n_items < pairs) pairs = p.n_items;
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(2 * pairs); cfg.blockDim = dim3(kThreads); cfg.dynamicSmemBytes = Cfg::kSmemBytes; cfg.stream = stream;
@@ -214,7 +214,7 @@ const char* tc_conv_wgrad2(const void* dY, const void* X, void* dW, float* scrat
     p.kb_total = p.tiles_w * p.tiles_h * ((NB + BNI - 1) / BNI);
     p.co_tiles = Cout / 256; p.ci_tiles = Cin / BN2;
     const int base_items = p.taps * p.co_tiles * p.ci_tiles;
-    const int pairs = num_sms() / 2;
+    const int pairs = wgrad_sms() / 2;
     int ksplit = (2 * pairs + base_items - 1) / base_items;
     if (ksplit < 1) ksplit = 1;
     if (ksplit > p.kb_total) ksplit = p.kb_total;

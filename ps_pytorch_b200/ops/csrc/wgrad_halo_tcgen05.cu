@@ -103,6 +103,7 @@ tc_wgrad_halo_kernel(const __grid_constant__ CUtensorMap tmap_dy, const __grid_c
         }
     } else if (warp == 1) {
         constexpr uint32_t idesc = umma_idesc_bf16(MM, 192, 1, 1);          // both operands MN-major, N = 3 taps x 64 ci
+        const uint64_t a_tmpl = umma_desc_mn_sw128(0, kABox), b_tmpl = umma_desc_mn_sw128_ex(0, 128, 2048);
         int stage = 0; uint32_t phase = 0; uint32_t acc_phase = 0;
         for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
             int rg, nt, mt, ks; decode(item, rg, nt, mt, ks);
@@ -114,16 +115,23 @@ tc_wgrad_halo_kernel(const __grid_constant__ CUtensorMap tmap_dy, const __grid_c
                 if (!mbar_wait(full_bar + stage, phase)) { *p.err = 43; return; }
                 tc_fence_after();
                 const uint32_t sa = smem_u32(smem + stage * stage_bytes);
-                const uint32_t sb = sa + p.a_bytes;
+                // descriptors advance by adding (byte offset >> 4) to the address field: one patch row = 2048 B = +128
+                const uint64_t da = a_tmpl + (uint64_t)((sa & 0x3FFFFu) >> 4);
+                const uint64_t db = b_tmpl + (uint64_t)(((sa + (uint32_t)p.a_bytes) & 0x3FFFFu) >> 4) + (uint64_t)(r0 * 128);
+                const uint32_t acc0 = kb > kb0 ? 1u : 0u;
                 if (elect_one()) {
-#pragma unroll 1
-                    for (int j = 0; j < 8; ++j) {                        // 16 pixels = rows 2j, 2j+1 of the 16-row rectangle
-                        const int row = 2 * j, img = row / p.BH, rin = row - img * p.BH;
-                        const uint32_t prow = (uint32_t)(img * (p.BH + 2) + rin);      // patch row of tap row r = 0
-                        const uint64_t adesc = umma_desc_mn_sw128(sa + j * 2048, kABox);
-                        for (int rr = 0; rr < nrows; ++rr) {
-                            const uint32_t bw = sb + (prow + (uint32_t)(r0 + rr)) * 2048u;      // window of (r0+rr, s=0); s groups +128 B each
-                            tc_mma_bf16(tmem_base + (uint32_t)(rr * 192), adesc, umma_desc_mn_sw128_ex(bw, 128, 2048), idesc, (kb > kb0 || j > 0) ? 1u : 0u);
+                    if (p.BH == 16) {
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) {                    // 16 pixels = rows 2j, 2j+1 of the 16-row rectangle (one image)
+                            tc_mma_bf16(tmem_base, da + (uint64_t)(j * 128), db + (uint64_t)(2 * j * 128), idesc, j > 0 ? 1u : acc0);
+                            if (nrows == 2) tc_mma_bf16(tmem_base + 192u, da + (uint64_t)(j * 128), db + (uint64_t)((2 * j + 1) * 128), idesc, j > 0 ? 1u : acc0);
+                        }
+                    } else {                                             // BH = 8: rows 8..15 belong to the second image, whose patch starts BH + 2 rows later
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) {
+                            const int prow = 2 * j + (j >= 4 ? 2 : 0);
+                            tc_mma_bf16(tmem_base, da + (uint64_t)(j * 128), db + (uint64_t)(prow * 128), idesc, j > 0 ? 1u : acc0);
+                            if (nrows == 2) tc_mma_bf16(tmem_base + 192u, da + (uint64_t)(j * 128), db + (uint64_t)((prow + 1) * 128), idesc, j > 0 ? 1u : acc0);
                         }
                     }
                     tc_commit(empty_bar + stage);
@@ -183,7 +191,7 @@ static const char* launch_wgh(const CUtensorMap& ta, const CUtensorMap& tb, cons
         if (cudaFuncSetAttribute(tc_wgrad_halo_kernel<MM>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes) != cudaSuccess) return "cannot raise dynamic smem";
         attr = smem_bytes;
     }
-    int grid = p.n_items < num_sms() ? p.n_items : num_sms();
+    int grid = p.n_items < wgrad_sms() ? p.n_items : wgrad_sms();
     grid &= ~1;                                       // even: the two row groups of a pixel range stay in the same round (decode)
     if (grid < 2) grid = 2;
     tc_wgrad_halo_kernel<MM><<<grid, kThreads, smem_bytes, stream>>>(ta, tb, p);
@@ -214,7 +222,7 @@ const char* tc_conv_wgrad_halo(const void* dY, const void* X, void* dW, float* s
     p.kb_total = p.tiles_w * p.tiles_h * p.tiles_n;
     p.co_tiles = Cout / MM; p.ci_tiles = Cin / 64;
     const int base_items = 2 * p.co_tiles * p.ci_tiles;
-    int ksplit = (2 * num_sms() + base_items - 1) / base_items;
+    int ksplit = (2 * wgrad_sms() + base_items - 1) / base_items;
     if (ksplit < 1) ksplit = 1;
     if (ksplit > p.kb_total) ksplit = p.kb_total;
     p.kb_per_split = (p.kb_total + ksplit - 1) / ksplit;

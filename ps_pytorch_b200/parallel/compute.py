@@ -68,6 +68,7 @@ class WorkerCompute:
         self._on_bucket: Optional[Callable[[int], None]] = None
         self._kill_poll: Optional[Callable[[], bool]] = None
         self.kill_deadline: float = 0.0
+        self.after_backward: Optional[Callable[[], None]] = None
         self._warming_up = False               # graph warm-up passes: bucket hooks must not push (or poll) for real
         self._capturing = False
         self.captured_buckets: List[int] = []  # buckets whose push kernels were recorded inside the CUDA graph
@@ -95,6 +96,9 @@ class WorkerCompute:
                 b = owner[i]
                 self._pending[b] -= 1
                 if self._pending[b] == 0 and self._on_bucket is not None:
+                    if self.device.type == "cuda":
+                        from ..ops import libconv as _lc
+                        _lc.join(self.device)          # weight gradients of this bucket may still be in flight on the side stream
                     self._on_bucket(b)
                     if self._capturing:
                         self.captured_buckets.append(b)
@@ -126,6 +130,8 @@ class WorkerCompute:
         if self.device.type == "cuda" and _ops.available():
             from ..ops import conv as _conv
             _conv.refresh_dgrad_operands()          # one launch: the transposed filters every dgrad of this step reads
+            from ..ops import elementwise as _ew
+            _ew.bump_dropout_seed(self.device)      # (only when a Dropout layer has run on this device) fresh masks on every graph replay
         if self._bn_counters and self.network.training:
             torch._foreach_add_(self._bn_counters, 1)
         with self.timer.phase("forward"):
@@ -150,6 +156,8 @@ class WorkerCompute:
             if self.device.type == "cuda":
                 from ..ops import libconv as _lc
                 _lc.join(self.device)                  # side-stream weight gradients land before anyone reads .grad
+            if self.after_backward is not None:
+                self.after_backward()                  # e.g. join the transport's bucket-push stream (must happen inside a graph capture)
             if gather:
                 torch._foreach_copy_(self.grads.views, [p.grad if p.grad is not None else torch.zeros_like(v)
                                                         for p, v in zip(self._params, self.grads.views)])
@@ -234,7 +242,13 @@ class WorkerCompute:
     def _capture(self, x, y):
         xs, ys = self.prepare_input(x, y)
         self._static_x, self._static_y = xs.clone(memory_format=torch.preserve_format), ys.clone()
-        s = torch.cuda.Stream()
+        # The step is captured from a HIGH-priority stream; the weight gradients are forked to the default-priority side stream
+        # (ops/libconv.py:_side).  Graph kernel nodes inherit the priority of the stream they were captured from, so whenever a critical-path
+        # kernel (dgrad / BN backward) and a weight gradient are both ready, the block scheduler serves the critical path first and the weight
+        # gradients fill in behind the memory-bound BatchNorm kernels.  PSB200_STEP_PRIORITY=0 disables.
+        import os as _os
+        prio = -1 if _os.environ.get("PSB200_STEP_PRIORITY", "1") != "0" else 0
+        s = torch.cuda.Stream(priority=prio)
         s.wait_stream(torch.cuda.current_stream())
         saved = [b.detach().clone() for b in self.network.buffers()]      # warm-up must not advance BN statistics
         self._warming_up = True
@@ -257,7 +271,7 @@ class WorkerCompute:
         self.captured_buckets = []
         self._capturing = True
         try:
-            with torch.cuda.graph(self._graph):
+            with torch.cuda.graph(self._graph, stream=s):
                 self._static_loss, self._static_logits = self._step_body(self._static_x, self._static_y)
         finally:
             self._capturing = False

@@ -113,6 +113,13 @@ class NvlTransport(Transport):
         # --comm-type Async: the PS only publishes a version; every worker PULLS the weights from the PS replica with P2P loads
         # (the reference's point-to-point weight fetch, distributed_worker.py:201-219, which has no sender in that snapshot)
         self.pull_weights = bool(pull_weights) and topology == "ps" and world > 1
+        # Central PS in PULL mode (PSB200_PS_PULL=1): workers do not push; they only raise "gradients ready" on the server, and the server's
+        # reduce kernel reads the gradient arenas of all workers itself — with the NVLS multicast mapping as ONE in-switch-reduced stream
+        # (multimem.ld_reduce) instead of W-1 incast streams into its slots.  Needs bf16 gradients, every rank a worker (co-located) and K = P.
+        self.pull_grads = (os.environ.get("PSB200_PS_PULL", "0") == "1" and topology == "ps" and world > 1 and self.wire == 0
+                           and colocate and self.NB == 1)
+        if self.pull_grads:
+            self.zeroes_grads = False
         torch.cuda.synchronize(self.device)
 
     # ---- storage handed to the roles -------------------------------------------------------------------------------
@@ -211,7 +218,12 @@ class NvlTransport(Transport):
     def ps_reduce_update(self, step, k, optimizer, master, strict_reference=False, kill_stragglers=False, timeout_s=0.0, lowp=None):
         hp_ptr, kind, fs = self._hp(optimizer)
         P = self.num_workers
-        if self.topology == "ps":
+        if self.topology == "ps" and self.pull_grads:
+            src = [self.arena.peer_ptrs[r] + self.off_grads for r in self.worker_ranks]
+            scl, mode = [], (2 if getattr(self, "_grad_is_fp32", False) else 0)
+            lo, hi = [0], [self.T]
+            wready = [self._flag(r, self.F_WREADY) for r in self._dests()]
+        elif self.topology == "ps":
             src = [self.arena.local_ptr + self.off_slots + s * self.slot_stride for s in range(P)]
             scl = [p + self.slot_q_bytes for p in src] if self.wire == 1 else []
             lo = [b[0] for b in self.buckets]
@@ -253,10 +265,12 @@ class NvlTransport(Transport):
         self.stats["bcast_bytes"] += self.T * 2
 
     def _nvls_reduce_ok(self, mode, take, nsrc) -> bool:
-        """EXPERIMENTAL (``PSB200_NVLS_REDUCE=1``; not yet run on hardware): in pull mode the gradient arenas sit at the same symmetric offset
-        on every rank, so the server can read ONE in-switch-reduced stream (``multimem.ld_reduce``) instead of one stream per peer.  Valid only
-        when every device of the multicast group contributes: bf16 gradients, sharded topology, take == P == world size."""
-        return (os.environ.get("PSB200_NVLS_REDUCE", "0") == "1" and self.topology == "sharded" and bool(self.arena.mc_ptr) and mode == 0
+        """In pull mode (sharded topology, or the central PS with ``PSB200_PS_PULL=1``) the gradient arenas sit at the same symmetric offset on every
+        rank, so the server can read ONE in-switch-reduced stream (``multimem.ld_reduce``) instead of one stream per peer.  Valid only when every
+        device of the multicast group contributes: bf16 gradients, take == P == world size.  Validated on hardware in round 2
+        (``profiles/run27_multi_gpu.md``); ``PSB200_NVLS_REDUCE=0`` selects the per-peer loads."""
+        return (os.environ.get("PSB200_NVLS_REDUCE", "1") == "1"
+                and (self.topology == "sharded" or getattr(self, "pull_grads", False)) and bool(self.arena.mc_ptr) and mode == 0
                 and take == nsrc == self.world_size)
 
     def _ru_dst(self, d):
@@ -300,7 +314,14 @@ class NvlTransport(Transport):
         lo, hi = self.buckets[b]
         slot = self._my_slot()
         fp32 = grads.dtype == torch.float32
-        if self.topology == "ps":
+        if self.topology == "ps" and self.pull_grads:
+            self._grad_is_fp32 = fp32
+            assert grads.flat.data_ptr() == self.arena.local_ptr + self.off_grads, "pull mode: gradients must live in the arena"
+            # no data moves here: one release of "gradients of step s ready" in the server's flag page
+            self.ext.bcast(self.arena.local_ptr + self.off_grads, [self.arena.peer_ptrs[0] + self.off_grads], 0, 0,
+                           [self._flag(0, self.F_GREADY + 8 * (slot * MAXB))], 1, self.p_wstep, 0, self.p_counters + 4 * (2 * MAXB + 1))
+            ops.count_launch()
+        elif self.topology == "ps":
             base = self.arena.peer_ptrs[0] + self.off_slots + slot * self.slot_stride
             side = self.NB > 1 and not last_bucket
             if side:
@@ -346,6 +367,15 @@ class NvlTransport(Transport):
             self._push_forked = False
         self.ext.add_step(self.p_wstep, 1)
         ops.count_launch()
+
+    def join_push_stream(self) -> None:
+        """Make the current stream wait for bucket pushes issued on the side push stream (called at the end of backward: inside a CUDA-graph
+        capture every forked stream has to be joined before the capture ends)."""
+        if self._push_forked:
+            ev = torch.cuda.Event()
+            ev.record(self._push_stream)
+            torch.cuda.current_stream().wait_event(ev)
+            self._push_forked = False
 
     def mark_pushed(self, b: int) -> None:
         """Bucket ``b`` was pushed by kernels inside a replayed CUDA graph (the Python hook that normally records it does not run)."""

@@ -101,6 +101,7 @@ class DistributedWorker(object):
             self._buckets = self.compute.layout.buckets(self._num_buckets)
             self.compute.enable_bucket_callbacks(
                 self._buckets, lambda b: self.comm.worker_push(self.cur_step, self.compute.grads, self._buckets[b][0], self._buckets[b][1], last=False))
+            self.compute.after_backward = getattr(self.comm, "join_push_stream", None)
         if self._mode in ('kill', 'timeout') and not isinstance(self.network, LayerwiseBackwardMixin):
             self.compute.enable_kill_poll(lambda: self.comm.worker_poll_kill(self.cur_step))
         return self

@@ -262,6 +262,9 @@ def test_k_of_p_staggered_arrivals_use_one_worker_set(ext):
     tr, master, opt_, lowp, grads = _k_of_p_setup(T)
     vals = {0: 1.0, 1: 10.0, 2: 100.0}
     ps_stream, push_stream = torch.cuda.Stream(), torch.cuda.Stream()      # two pool streams: neither is the (legacy) default stream
+    # CUDA loads kernels lazily, and loading one while another kernel spins on the device can dead-lock: touch every kernel used below first
+    torch.cuda._sleep(10); grads.flat.fill_(0.0)
+    tr._slot_override = 1; tr.ctl[0] = 0; tr.worker_push_bucket(0, grads); tr.ctl[0] = 1          # a push with a stale step id: ignored by the PS
     torch.cuda.synchronize()
     with torch.cuda.stream(ps_stream):
         tr.ps_reduce_update(1, 2, opt_, master, lowp=lowp)          # starts polling: nothing has arrived yet
@@ -754,3 +757,37 @@ def test_stem_tensorcore_fprop_and_wgrad(ext, shape, relu_bias):
     err = (dw.float() - wr.grad).abs().max().item()
     assert err <= 0.02 * max(1.0, wr.grad.abs().max().item()), err
     assert torch.equal(dw, dw2)
+
+
+@pytest.mark.parametrize("shape", [(4, 64, 16, 16), (3, 64, 15, 9), (2, 8, 7, 7)])
+def test_maxpool3x3s2(ext, shape):
+    """MaxPool2d(3, 2, 1) forward + gather-style backward (first maximum wins, like ATen) vs torch."""
+    from ps_pytorch_b200.ops import elementwise as E
+    torch.manual_seed(0)
+    x = _nhwc(*shape).requires_grad_(True)
+    y = E.max_pool3x3s2(x)
+    g = torch.randn_like(y)
+    y.backward(g)
+    xr = x.detach().float().requires_grad_(True)
+    yr = F.max_pool2d(xr, 3, 2, 1)
+    yr.backward(g.float())
+    assert torch.equal(y.float(), yr)
+    assert (x.grad.float() - xr.grad).abs().max().item() <= 0.02 * max(1.0, xr.grad.abs().max().item())
+
+
+def test_dropout_kernel(ext):
+    """Counter-based dropout: keep rate ~ 1 - p, survivors scaled by 1/(1-p), backward uses the identical mask, a seed bump changes the mask."""
+    from ps_pytorch_b200.ops import elementwise as E
+    x = torch.ones(64, 512, device="cuda", dtype=torch.bfloat16).requires_grad_(True)
+    y = E.dropout(x, 0.5)
+    y.backward(torch.ones_like(y))
+    keep = (y != 0).float().mean().item()
+    assert 0.47 < keep < 0.53
+    assert torch.equal(y[y != 0].float(), torch.full_like(y[y != 0].float(), 2.0))
+    assert torch.equal(x.grad, y.detach())                      # same mask, same scale
+    m = torch.nn.Module(); m.p = 0.5
+    y1 = E.dropout(x.detach(), 0.5, m); y2 = E.dropout(x.detach(), 0.5, m)
+    assert torch.equal(y1, y2)                                  # same layer, same step: same mask
+    E.bump_dropout_seed(x.device)
+    y3 = E.dropout(x.detach(), 0.5, m)
+    assert not torch.equal(y1, y3)
