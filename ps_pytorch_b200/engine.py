@@ -105,7 +105,7 @@ class PSJob:
         """One PS iteration.  Returns this rank's loss tensor (device, async) or None on a pure-PS rank."""
         self.step_id += 1
         m, w = self.master, self.worker
-        if m is not None and self.rank == 0 or (m is not None and self.topology == "sharded"):
+        if m is not None and (self.rank == 0 or self.topology == "sharded"):
             m.async_bcast_step()
         if w is not None:
             e = self._bracket()

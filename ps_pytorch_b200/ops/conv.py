@@ -267,7 +267,9 @@ class _ConvFn(torch.autograd.Function):
             # path after dgrad is a memory-bound BatchNorm backward: issue wgrad on a side stream (fork after dy is ready; WorkerCompute joins
             # before it gathers the gradients: libconv.join).  Inside a CUDA-graph capture this becomes a fork/join in the graph.
             from . import libconv as _lc
-            if _WGRAD_SIDE and _lc.enabled():
+            # Only when autograd will merely HAND OVER the gradient (weight.grad is None: gather mode).  With a bound .grad (overlap / DDP modes)
+            # autograd accumulates `grad += dw` on the main stream right after this function returns — before a side-stream kernel has run.
+            if _WGRAD_SIDE and _lc.enabled() and weight.grad is None:
                 dev = dy.device
                 main, side = torch.cuda.current_stream(dev), _lc._side(dev)
                 side.wait_stream(main)

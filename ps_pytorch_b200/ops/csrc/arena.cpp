@@ -143,6 +143,20 @@ int64_t mc_map(int64_t mc, int64_t size, int64_t dev, int64_t gran) {
     return (int64_t)va;
 }
 
+// Tear-down of the multicast side (the order the driver requires): unmap + free the multicast VA, unbind this device's memory from the object,
+// release this process's reference to the object.  After this the local allocation can be unmapped/released like any other.
+void mc_unmap(int64_t mc_va, int64_t mc, int64_t size, int64_t dev) {
+    DRV(cuMemUnmap); DRV(cuMemAddressFree); DRV(cuMulticastUnbind); DRV(cuMemRelease);
+    if (mc_va) {
+        CU_OK(fn_cuMemUnmap((CUdeviceptr)mc_va, (size_t)size));
+        CU_OK(fn_cuMemAddressFree((CUdeviceptr)mc_va, (size_t)size));
+    }
+    if (mc) {
+        CU_OK(fn_cuMulticastUnbind((CUmemGenericAllocationHandle)mc, (CUdevice)dev, 0, (size_t)size));
+        CU_OK(fn_cuMemRelease((CUmemGenericAllocationHandle)mc));
+    }
+}
+
 void close_fd(int64_t fd) { if (fd >= 0) ::close((int)fd); }
 
 // A uint8 view over raw device memory owned by the arena (never freed by torch).

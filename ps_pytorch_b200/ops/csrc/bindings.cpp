@@ -46,6 +46,7 @@ int64_t mc_import(int64_t);
 void mc_add_device(int64_t, int64_t);
 void mc_bind(int64_t, int64_t, int64_t);
 int64_t mc_map(int64_t, int64_t, int64_t, int64_t);
+void mc_unmap(int64_t, int64_t, int64_t, int64_t);
 void close_fd(int64_t);
 at::Tensor tensor_from_ptr(int64_t, int64_t, int64_t);
 }  // namespace psb
@@ -68,6 +69,6 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
     m.def("gap_forward", &gap_forward); m.def("gap_backward", &gap_backward); m.def("softmax_ce", &softmax_ce);
     m.def("vmm_alloc", &vmm_alloc); m.def("vmm_import", &vmm_import); m.def("vmm_unmap", &vmm_unmap);
     m.def("multicast_supported", &multicast_supported); m.def("mc_granularity", &mc_granularity); m.def("mc_create", &mc_create);
-    m.def("mc_import", &mc_import); m.def("mc_add_device", &mc_add_device); m.def("mc_bind", &mc_bind); m.def("mc_map", &mc_map);
+    m.def("mc_import", &mc_import); m.def("mc_add_device", &mc_add_device); m.def("mc_bind", &mc_bind); m.def("mc_map", &mc_map); m.def("mc_unmap", &mc_unmap);
     m.def("close_fd", &close_fd); m.def("tensor_from_ptr", &tensor_from_ptr);
 }

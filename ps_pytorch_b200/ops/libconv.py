@@ -59,7 +59,11 @@ class _LibConvFn(torch.autograd.Function):
         dx = dw = db = None
         dev = dy.device
         main = torch.cuda.current_stream(dev)
-        if need_dw or need_db:
+        if (need_dw or need_db) and (weight.grad is not None):
+            # a bound .grad is accumulated on the main stream as soon as backward returns: no side stream in that mode
+            _, dw, db = torch.ops.aten.convolution_backward(dy, x, weight, [weight.size(0)] if need_db else None, stride, padding, dilation,
+                                                            False, [0, 0], groups, [False, need_dw, need_db])
+        elif need_dw or need_db:
             side = _side(dev)
             side.wait_stream(main)                      # dy is complete on the main stream at this point
             with torch.cuda.stream(side):

@@ -85,7 +85,7 @@ class NvlTransport(Transport):
         nslots = P if topology == "ps" else 0
         self.off_bufs = _align(self.off_slots + nslots * self.slot_stride)
         self.n_buffers = int(n_buffers)
-        total = self.off_bufs + _align(max(self.n_buffers, 1) * 4 + 64)
+        total = self.off_bufs + _align(max(self.n_buffers, 1) * 4 + 64 + 64)
         self.arena = SymmetricArena(total, self.device, tag="ps")
         A = self.arena
         # flag words (int64) inside the flags page
@@ -403,12 +403,20 @@ class NvlTransport(Transport):
         return self._read_word(self.F_ABORT) == step
 
     def worker_send_buffers(self, step, flat):
+        """BN running statistics -> the PS (checkpoint steps).  One launch of the copy kernel over raw peer pointers: it stores the payload into the
+        PS's buffer region and then releases F_BUFS = step (a torch tensor cannot wrap peer-mapped memory: from_blob checks the owning device)."""
         if flat.numel() == 0:
             return
         assert flat.numel() <= self.n_buffers, "BN statistics (%d floats) exceed the %d reserved in the arena (pass n_buffers=)" % (flat.numel(), self.n_buffers)
-        dst = self.arena.peer_view(0, self.off_bufs + 64, flat.numel() * 4, torch.float32)
-        dst.copy_(flat.float())
-        self.ext.set_word(self._flag(0, self.F_BUFS), int(step))
+        n = (flat.numel() + 3) // 4 * 4
+        stage = getattr(self, "_buf_stage", None)
+        if stage is None or stage.numel() < n:
+            stage = self._buf_stage = torch.zeros(n, dtype=torch.float32, device=self.device)
+        stage[: flat.numel()].copy_(flat.float())
+        # worker_push already advanced the step word: flag value = *p_wstep - 1 = step
+        self.ext.bcast(stage.data_ptr(), [self.arena.peer_ptrs[0] + self.off_bufs + 64], 0, n * 4, [self._flag(0, self.F_BUFS)], 1,
+                       self.p_wstep, -1, self.p_counters + 4 * (2 * MAXB + 3))
+        ops.count_launch()
 
     def gather_master(self, master: FlatBuffer) -> None:
         """Sharded topology: every rank holds the authoritative fp32 master only for its shard.  Collective (all ranks):

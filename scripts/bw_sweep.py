@@ -25,7 +25,7 @@ dist.init_process_group("gloo", rank=rank, world_size=world)
 nccl = dist.new_group(backend="nccl")
 LINK = 770e9
 sizes = [1 << k for k in range(10, 31, 2)]            # bytes per worker (bf16 payload)
-wires = os.environ.get("WIRES", "bf16,fp8").split(",")
+wires = os.environ.get("WIRES", "bf16,fp8,pull").split(",")
 rows = []
 
 
@@ -54,7 +54,9 @@ for nbytes in sizes:
     row = {"bytes": T * 2, "world": world}
     lay = ParamLayout(["w"], [(T,)], [T], [0], [False], T)
     for wire in wires:
-        tr = NvlTransport(lay, dev, grad_dtype=wire, colocate=True)
+        # "pull": central PS in pull mode — workers only raise a flag, the PS kernel reads ONE in-switch-reduced stream (multimem.ld_reduce)
+        os.environ["PSB200_PS_PULL"] = "1" if wire == "pull" else "0"
+        tr = NvlTransport(lay, dev, grad_dtype="bf16" if wire == "pull" else wire, colocate=True)
         grads = FlatBuffer(lay, torch.bfloat16, dev, storage=tr.worker_grad_storage(torch.bfloat16))
         lowp = FlatBuffer(lay, torch.bfloat16, dev, storage=tr.worker_weight_storage(torch.bfloat16))
         master = opt = None
@@ -100,6 +102,7 @@ for nbytes in sizes:
     row["nccl_ps_ingress_GBs"] = (world - 1) * T * 2 / (ms * 1e-3) / 1e9
     row["ours_bf16_frac_of_link"] = row.get("ours_bf16_ps_ingress_GBs", 0) * 1e9 / LINK
     row["speedup_vs_nccl_bf16"] = row["nccl_us"] / row["ours_bf16_us"] if "ours_bf16_us" in row else None
+    row["speedup_vs_nccl_pull"] = row["nccl_us"] / row["ours_pull_us"] if "ours_pull_us" in row else None
     rows.append(row)
     if rank == 0:
         print(json.dumps(row), flush=True)

@@ -791,3 +791,31 @@ def test_dropout_kernel(ext):
     E.bump_dropout_seed(x.device)
     y3 = E.dropout(x.detach(), 0.5, m)
     assert not torch.equal(y1, y3)
+
+
+@pytest.mark.parametrize("backend", ["sm100", "library"])
+def test_bound_gradients_accumulate_correctly(ext, backend):
+    """Overlap and DDP modes keep ``p.grad`` bound to the arena, so autograd ACCUMULATES the weight gradient on the main stream the moment
+    backward returns it: a wgrad still running on the side stream at that point would be read half-written.  Gradients accumulated into
+    bound zero buffers must equal the ones gathered with ``p.grad = None``."""
+    from ps_pytorch_b200 import nn as pnn
+    from ps_pytorch_b200.models import build_model
+    from ps_pytorch_b200.ops import libconv
+    torch.manual_seed(0)
+    m = build_model("ResNet18", 10).cuda().to(torch.bfloat16).to(memory_format=torch.channels_last)
+    x = torch.randn(64, 3, 32, 32, device="cuda").to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
+    y = torch.randint(0, 10, (64,), device="cuda")
+    ps = [p for p in m.parameters()]
+    res = []
+    for bound in (False, True):
+        for p in ps:
+            p.grad = torch.zeros_like(p) if bound else None
+        torch.manual_seed(1)
+        with pnn.backend(backend):
+            loss = torch.nn.functional.cross_entropy(m(x).float(), y)
+            loss.backward()
+        libconv.join(x.device)
+        torch.cuda.synchronize()
+        res.append([p.grad.float().clone() for p in ps])
+    for a, b in zip(*res):
+        assert torch.allclose(a, b, rtol=1e-2, atol=1e-3 * max(1.0, a.abs().max().item())), (a - b).abs().max().item()
