@@ -79,6 +79,8 @@ class PSJob:
         CUDA events on the step's stream.  Those kernels run serialised with the compute on that stream, so the bracketed device time —
         spins included — IS the communication the step is exposed to."""
         self._comm_events = [] if on else None
+        if self.worker is not None:        # the weights wait must be a kernel of its own to be bracketed (the one fused into the step then passes at once)
+            self.worker.compute.unfused_wait = bool(on)
 
     def comm_ms_per_step(self) -> Optional[float]:
         """Mean exposed communication per step (ms) on this rank since ``time_comm(True)``; call after a device synchronize."""

@@ -137,12 +137,19 @@ def enable_batched_dgrad_operands(on: bool) -> None:
     _wt_plan = None
 
 
-def refresh_dgrad_operands() -> None:
-    """One launch: re-transpose every registered conv weight (call once per step, after the weights of the step are in place)."""
+def refresh_ready() -> bool:
+    """True when the next ``refresh_dgrad_operands`` call will launch the batched kernel (so it can carry the weights-ready wait)."""
+    return bool(_wt_batched and _wt_reg)
+
+
+def refresh_dgrad_operands(wait=None) -> bool:
+    """One launch: re-transpose every registered conv weight (call once per step, after the weights of the step are in place).
+    ``wait = (flags_ptr, nflags, step_ptr, err_ptr, timeout_s)``: the kernel first acquires the transport's "weights of this step published"
+    words — it is the first reader of the weights in the step, so the separate wait kernel is not needed.  Returns True iff the wait rode along."""
     global _wt_plan, _wt_fresh
     if not _wt_batched or not _wt_reg:
         _wt_fresh = False
-        return
+        return False
     ext = require()
     ents = list(_wt_reg.values())
     if _wt_plan is None or _wt_plan[3] != len(ents) or any(e[0].data_ptr() != e[3] for e in ents):
@@ -150,9 +157,13 @@ def refresh_dgrad_operands() -> None:
             e[3] = e[0].data_ptr()
         table, meta = ext.weight_transpose_plan([e[0].detach() for e in ents], [e[2] for e in ents], [int(e[1]) for e in ents])
         _wt_plan = (table, int(meta[0]), int(meta[1]), len(ents))
-    ext.weight_transpose_run(_wt_plan[0], _wt_plan[1], _wt_plan[2])
+    if wait is not None:
+        ext.weight_transpose_run(_wt_plan[0], _wt_plan[1], _wt_plan[2], *wait)
+    else:
+        ext.weight_transpose_run(_wt_plan[0], _wt_plan[1], _wt_plan[2])
     count_launch()
     _wt_fresh = True
+    return wait is not None
 
 
 def _dgrad_operand(ext, weight, flip: bool):
@@ -213,6 +224,36 @@ _SKIP_FUSION = os.environ.get("PSB200_SKIP_GRAD_FUSION", "1") != "0"
 _WGRAD_SIDE = os.environ.get("PSB200_TC_WGRAD_STREAM", "1") != "0"
 
 
+# ---- gradient sinks: in gather mode (p.grad is None) the weight-gradient kernels write straight into the transport's gradient arena --------
+_grad_sinks = {}                 # weight.data_ptr() -> channels_last bf16 view of the gradient arena
+_sinks_active = False            # only inside WorkerCompute's step body: a stray backward elsewhere must get its gradient the normal way
+sink_writes = 0                  # weight gradients that landed in a sink (tests assert the copy-free path really runs)
+
+
+def set_grad_sinks(params, views) -> list:
+    """Register arena views as the destination of the weight gradients of `params` (4-D bf16 CUDA weights whose view is channels_last like the
+    kernels' output).  Returns the indices that got a sink; their ``.grad`` stays None after backward — read the arena instead."""
+    _grad_sinks.clear()
+    idx = []
+    for i, (p, v) in enumerate(zip(params, views)):
+        if (p.dim() == 4 and p.is_cuda and p.dtype == torch.bfloat16 and v.dtype == torch.bfloat16 and v.shape == p.shape
+                and v.is_contiguous(memory_format=torch.channels_last)):
+            _grad_sinks[p.data_ptr()] = v
+            idx.append(i)
+    return idx
+
+
+def activate_grad_sinks(on: bool) -> None:
+    global _sinks_active
+    _sinks_active = bool(on)
+
+
+def _sink_for(weight):
+    if not _sinks_active or weight.grad is not None:
+        return None
+    return _grad_sinks.get(weight.data_ptr())
+
+
 def set_skip_fusion(on: bool) -> None:
     global _SKIP_FUSION
     _SKIP_FUSION = bool(on)
@@ -269,17 +310,22 @@ class _ConvFn(torch.autograd.Function):
             from . import libconv as _lc
             # Only when autograd will merely HAND OVER the gradient (weight.grad is None: gather mode).  With a bound .grad (overlap / DDP modes)
             # autograd accumulates `grad += dw` on the main stream right after this function returns — before a side-stream kernel has run.
+            sink = _sink_for(weight)
             if _WGRAD_SIDE and _lc.enabled() and weight.grad is None:
                 dev = dy.device
                 main, side = torch.cuda.current_stream(dev), _lc._side(dev)
                 side.wait_stream(main)
                 with torch.cuda.stream(side):
-                    dw = ext.conv_wgrad(dy, x, _wgrad_scratch(weight), r, weight.size(3), s, p)
+                    dw = ext.conv_wgrad(dy, x, _wgrad_scratch(weight), r, weight.size(3), s, p, sink)
                 _lc._forked[dev] = True
                 for t in (dy, x, dw):
                     t.record_stream(side)
             else:
-                dw = ext.conv_wgrad(dy, x, _wgrad_scratch(weight), r, weight.size(3), s, p)
+                dw = ext.conv_wgrad(dy, x, _wgrad_scratch(weight), r, weight.size(3), s, p, sink)
+            if sink is not None:          # the gradient is already where the push kernel reads it: nothing to hand to autograd
+                global sink_writes
+                sink_writes += 1
+                dw = None
             count_launch(2)
             need_dw = False
         if need_dw:
@@ -322,7 +368,12 @@ class _StemFn(torch.autograd.Function):
             count_launch()
         dw = db = None
         if ctx.needs_input_grad[1]:
-            dw = ext.stem_wgrad_tc(dy, x, _wgrad_scratch(weight))
+            sink = _sink_for(weight)
+            dw = ext.stem_wgrad_tc(dy, x, _wgrad_scratch(weight), sink)
+            if sink is not None:
+                global sink_writes
+                sink_writes += 1
+                dw = None
             count_launch(2)
         if ctx.has_bias and ctx.needs_input_grad[2]:
             db = dy.float().sum((0, 2, 3)).to(dy.dtype)

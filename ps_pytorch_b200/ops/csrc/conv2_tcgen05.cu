@@ -24,6 +24,7 @@
 #include <stdint.h>
 #include <stdio.h>
 #include "tc_common.cuh"
+#include "common.cuh"
 
 namespace psb {
 
@@ -303,8 +304,27 @@ __global__ void weight_transpose_kernel(const __nv_bfloat16* __restrict__ w, __n
 // All convolution weights of a model in ONE launch (per step: the dgrad operands of every layer, ~20 launches -> 1).
 // table[i] = {src, dst, Cout, T, Cin, flip, first_block, blocks_x, blocks_y}; block -> tensor by linear search over n <= 256 entries.
 struct WtEntry { const __nv_bfloat16* src; __nv_bfloat16* dst; int Cout, T, Cin, flip, first_block, bx, by, pad; };
-__global__ void weight_transpose_batched_kernel(const WtEntry* __restrict__ table, int n) {
+// The launch is also the step's FIRST reader of the weights, so it can carry the protocol's consumer-side wait: with `wait.flags` set, one warp of
+// every CTA acquires the PS's "weights of step s published" words (system scope, peer-written) before the CTA touches a weight — the separate
+// 1-warp wait_flag_kernel disappears from the step and everything later in the stream is ordered behind this kernel as before.
+struct ReadyWait { const long long* flags; int n; long long* step_ptr; long long* err; unsigned long long timeout_ns; };
+__global__ void weight_transpose_batched_kernel(const WtEntry* __restrict__ table, int n, ReadyWait wait) {
     __shared__ __nv_bfloat16 tile[32][33];
+    if (wait.flags != nullptr) {
+        if (threadIdx.y == 0 && (int)threadIdx.x < wait.n) {
+            const long long want = *(volatile long long*)wait.step_ptr;
+            const unsigned long long t0 = globaltimer_ns();
+            long long f;
+            while ((f = ld_acquire_sys(wait.flags + threadIdx.x)) < want) {
+                if (globaltimer_ns() - t0 > wait.timeout_ns) { atomicExch((unsigned long long*)wait.err, 100ull + threadIdx.x); break; }
+                __nanosleep(100);
+            }
+            // a worker that (re)joins a running job adopts the server's step (same rule as wait_flag_kernel); flags only grow, so a CTA that
+            // reads the adopted value simply waits for the same publication
+            if (blockIdx.x == 0 && threadIdx.x == 0 && f > want) *(volatile long long*)wait.step_ptr = f;
+        }
+        __syncthreads();
+    }
     int i = 0;
     while (i + 1 < n && (int)blockIdx.x >= table[i + 1].first_block) ++i;
     const WtEntry e = table[i];
@@ -323,8 +343,11 @@ __global__ void weight_transpose_batched_kernel(const WtEntry* __restrict__ tabl
         if (co < e.Cout && ci < e.Cin) e.dst[((long long)ci * e.T + to) * e.Cout + co] = tile[threadIdx.x][r];
     }
 }
-const char* weight_transpose_batched(const void* table, int n, int total_blocks, cudaStream_t stream) {
-    weight_transpose_batched_kernel<<<total_blocks, dim3(32, 8), 0, stream>>>((const WtEntry*)table, n);
+const char* weight_transpose_batched(const void* table, int n, int total_blocks, const void* flags, int nflags, void* step_ptr, void* err, double timeout_s,
+                                     cudaStream_t stream) {
+    if (nflags > 32) return "weight_transpose_batched: at most 32 ready flags";
+    ReadyWait w{(const long long*)flags, nflags, (long long*)step_ptr, (long long*)err, (unsigned long long)(timeout_s * 1e9)};
+    weight_transpose_batched_kernel<<<total_blocks, dim3(32, 8), 0, stream>>>((const WtEntry*)table, n, w);
     return cudaGetLastError() == cudaSuccess ? nullptr : "weight_transpose_batched launch failed";
 }
 

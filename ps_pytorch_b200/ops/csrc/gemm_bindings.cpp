@@ -9,7 +9,7 @@ const char* tc_conv_fprop(const void*, const void*, void*, const void*, const vo
 const char* tc_conv2(const void*, const void*, void*, const void*, const void*, int, int, int, int, int, int, int, int, int, int, int, int, int, float*, cudaStream_t);
 int num_sms();
 const char* weight_transpose(const void*, void*, int, int, int, int, cudaStream_t);
-const char* weight_transpose_batched(const void*, int, int, cudaStream_t);
+const char* weight_transpose_batched(const void*, int, int, const void*, int, void*, void*, double, cudaStream_t);
 void tc_set_conv2_bn(int);
 void tc_set_conv_algo(int);
 void tc_set_halo_desc_mode(int);
@@ -143,19 +143,29 @@ std::vector<at::Tensor> weight_transpose_plan(std::vector<at::Tensor> srcs, std:
     meta.data_ptr<int64_t>()[0] = (int64_t)tab.size(); meta.data_ptr<int64_t>()[1] = blocks;
     return {dev, meta};
 }
-void weight_transpose_run(at::Tensor table, int64_t n, int64_t blocks) {
-    const char* e = weight_transpose_batched(table.data_ptr(), (int)n, (int)blocks, at::cuda::getCurrentCUDAStream());
+// flags != 0: the kernel first acquires `nflags` "weights published" words >= *step_ptr (the consumer-side wait of the PS protocol, see conv2_tcgen05.cu)
+void weight_transpose_run(at::Tensor table, int64_t n, int64_t blocks, int64_t flags, int64_t nflags, int64_t step_ptr, int64_t err, double timeout_s) {
+    const char* e = weight_transpose_batched(table.data_ptr(), (int)n, (int)blocks, (const void*)flags, (int)nflags, (void*)step_ptr, (void*)err, timeout_s,
+                                             at::cuda::getCurrentCUDAStream());
     TORCH_CHECK(e == nullptr, e);
 }
 
 // dW [Cout,Cin,R,S] channels_last (physically [Cout][R][S][Cin]) from dy (NHWC) and x (NHWC).  `scratch` is a persistent fp32 buffer of
 // Cout*R*S*Cin floats that must be zero on entry and is left zeroed.
-at::Tensor conv_wgrad(at::Tensor dy, at::Tensor x, at::Tensor scratch, int64_t R, int64_t S, int64_t stride, int64_t pad) {
+// `out`: write dw there instead of a fresh tensor (a channels_last view of the gradient arena: the push kernel's source, no gather copy)
+static at::Tensor wgrad_out(const c10::optional<at::Tensor>& out, const at::Tensor& x, int64_t Cout, int64_t Cin, int64_t R, int64_t S) {
+    if (!out.has_value()) return at::empty({Cout, Cin, R, S}, x.options().memory_format(at::MemoryFormat::ChannelsLast));
+    const at::Tensor& o = *out;
+    TORCH_CHECK(o.is_cuda() && o.scalar_type() == at::kBFloat16 && o.dim() == 4 && o.size(0) == Cout && o.size(1) == Cin && o.size(2) == R && o.size(3) == S &&
+                o.is_contiguous(at::MemoryFormat::ChannelsLast), "wgrad out: need a bf16 channels_last [Cout,Cin,R,S] tensor");
+    return o;
+}
+at::Tensor conv_wgrad(at::Tensor dy, at::Tensor x, at::Tensor scratch, int64_t R, int64_t S, int64_t stride, int64_t pad, c10::optional<at::Tensor> out) {
     TORCH_CHECK(dy.is_cuda() && dy.scalar_type() == at::kBFloat16 && x.scalar_type() == at::kBFloat16 && dy.dim() == 4 && x.dim() == 4);
     TORCH_CHECK(dy.is_contiguous(at::MemoryFormat::ChannelsLast) && x.is_contiguous(at::MemoryFormat::ChannelsLast), "dy and x must be NHWC");
     const int NB = x.size(0), Cin = x.size(1), H = x.size(2), W = x.size(3), Cout = dy.size(1);
     TORCH_CHECK(scratch.scalar_type() == at::kFloat && scratch.is_contiguous() && scratch.numel() >= (int64_t)Cout * R * S * Cin);
-    at::Tensor dw = at::empty({Cout, Cin, R, S}, x.options().memory_format(at::MemoryFormat::ChannelsLast));
+    at::Tensor dw = wgrad_out(out, x, Cout, Cin, R, S);
     const char* e;
     // measured (profiles/run28_conv_per_layer.md, after the MMA-issue fix): the CTA-pair kernel wins on 256-wide tiles (81 vs 105 us on 256->256 @8x8),
     // the tap-sharing kernel everywhere else it applies (110 vs 223 us on 64->64 @32x32, 81 vs 94 on 128->128 @16x16)
@@ -184,12 +194,12 @@ at::Tensor stem_conv(at::Tensor x, at::Tensor w, c10::optional<at::Tensor> bias,
     TORCH_CHECK(e == nullptr, e);
     return y;
 }
-at::Tensor stem_wgrad_tensorcore(at::Tensor dy, at::Tensor x, at::Tensor scratch) {
+at::Tensor stem_wgrad_tensorcore(at::Tensor dy, at::Tensor x, at::Tensor scratch, c10::optional<at::Tensor> out) {
     TORCH_CHECK(dy.is_cuda() && dy.scalar_type() == at::kBFloat16 && x.scalar_type() == at::kBFloat16 && dy.dim() == 4 && x.dim() == 4);
     TORCH_CHECK(dy.is_contiguous(at::MemoryFormat::ChannelsLast) && x.is_contiguous(at::MemoryFormat::ChannelsLast), "dy and x must be NHWC");
     const int NB = x.size(0), Cin = x.size(1), H = x.size(2), W = x.size(3), Cout = dy.size(1);
     TORCH_CHECK(dy.size(2) == H && dy.size(3) == W && scratch.scalar_type() == at::kFloat && scratch.numel() >= (int64_t)Cout * 9 * Cin);
-    at::Tensor dw = at::empty({Cout, Cin, 3, 3}, x.options().memory_format(at::MemoryFormat::ChannelsLast));
+    at::Tensor dw = wgrad_out(out, x, Cout, Cin, 3, 3);
     const char* e = stem_wgrad_tc(dy.data_ptr(), x.data_ptr(), dw.data_ptr(), scratch.data_ptr<float>(), NB, H, W, Cin, Cout, at::cuda::getCurrentCUDAStream());
     TORCH_CHECK(e == nullptr, e);
     return dw;
@@ -234,7 +244,8 @@ void bind_gemm(pybind11::module_& m) {
     m.def("num_sms", &psb::num_sms);
     m.def("weight_transpose", &psb::weight_transpose_t);
     m.def("weight_transpose_plan", &psb::weight_transpose_plan);
-    m.def("weight_transpose_run", &psb::weight_transpose_run);
+    m.def("weight_transpose_run", &psb::weight_transpose_run, pybind11::arg("table"), pybind11::arg("n"), pybind11::arg("blocks"), pybind11::arg("flags") = 0,
+          pybind11::arg("nflags") = 0, pybind11::arg("step_ptr") = 0, pybind11::arg("err") = 0, pybind11::arg("timeout_s") = 0.0);
     m.def("tc_set_conv2_bn", &psb::tc_set_conv2_bn);
     m.def("tc_set_conv_algo", &psb::tc_set_conv_algo);
     m.def("tc_set_halo_desc_mode", &psb::tc_set_halo_desc_mode);
@@ -245,11 +256,12 @@ void bind_gemm(pybind11::module_& m) {
     m.def("tc_set_halo_resident", &psb::tc_set_halo_resident);
     m.def("tc_set_gemm_bn", &psb::tc_set_gemm_bn);
     m.def("conv_unsupported_reason", &psb::conv_unsupported_reason);
-    m.def("conv_wgrad", &psb::conv_wgrad);
+    m.def("conv_wgrad", &psb::conv_wgrad, pybind11::arg("dy"), pybind11::arg("x"), pybind11::arg("scratch"), pybind11::arg("R"), pybind11::arg("S"),
+          pybind11::arg("stride"), pybind11::arg("pad"), pybind11::arg("out") = c10::optional<at::Tensor>());
     m.def("tc_set_wgrad_algo", &psb::tc_set_wgrad_algo);
     m.def("stem_wgrad", &psb::stem_wgrad);
     m.def("stem_conv", &psb::stem_conv);
-    m.def("stem_wgrad_tc", &psb::stem_wgrad_tensorcore);
+    m.def("stem_wgrad_tc", &psb::stem_wgrad_tensorcore, pybind11::arg("dy"), pybind11::arg("x"), pybind11::arg("scratch"), pybind11::arg("out") = c10::optional<at::Tensor>());
     m.def("stem_eligible", &psb::stem_eligible);
     m.def("tc_error", &psb::tc_error);
 }

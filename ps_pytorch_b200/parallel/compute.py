@@ -5,6 +5,7 @@ Split models, ``/root/reference/src/model_ops/resnet_split.py:365-501``, for *an
 from __future__ import annotations
 
 import time
+import os
 from typing import Callable, List, Optional
 
 import torch
@@ -16,6 +17,10 @@ from .. import ops as _ops
 from ..models.layerwise import LayerwiseBackwardMixin, StragglerKilled
 from ..utils.obs import PhaseTimer
 from ..utils.data import mark_h2d_issued
+
+
+# conv weight gradients land directly in the gradient arena (no hand-over + gather copy); PSB200_GRAD_SINKS=0 restores the gather of everything
+_GRAD_SINKS = os.environ.get("PSB200_GRAD_SINKS", "1") != "0"
 
 
 def resolve_dtype(name: str, device) -> torch.dtype:
@@ -62,6 +67,10 @@ class WorkerCompute:
         if self.device.type == "cuda" and _ops.available():
             from ..ops import conv as _conv
             _conv.enable_batched_dgrad_operands(True)
+        self._sinked = self._unsinked = None
+        self.fetch_wait_args = None            # (flags_ptr, n, step_ptr, err_ptr, timeout_s) of the transport: see will_fuse_wait
+        self._last_fused_wait = self._graph_fused_wait = False
+        self.unfused_wait = False              # True: the caller launches its own (event-bracketable) wait kernel as well; the fused one then passes at once
         self._graph = None
         self._static_x = self._static_y = self._static_loss = None
         self._bucket_hooks: List = []
@@ -106,6 +115,16 @@ class WorkerCompute:
         for i, p in enumerate(params):
             self._bucket_hooks.append(p.register_post_accumulate_grad_hook(make(i)))
 
+    def will_fuse_wait(self) -> bool:
+        """True when the NEXT train_step acquires the transport's weights-ready words inside its first kernel, so the caller must not launch
+        its own wait kernel (``worker_fetch(..., fused_wait=True)``)."""
+        if self.fetch_wait_args is None or self.unfused_wait or self.device.type != "cuda" or not _ops.available():
+            return False
+        if self.use_graph:
+            return self._graph is not None and self._graph_fused_wait
+        from ..ops import conv as _conv
+        return _conv.refresh_ready()
+
     def enable_kill_poll(self, poll: Callable[[], bool]) -> None:
         self._kill_poll = poll
         if not self._bucket_hooks:
@@ -122,6 +141,12 @@ class WorkerCompute:
         if gather:
             for p in self._params:
                 p.grad = None
+            if self.device.type == "cuda" and _ops.available() and _GRAD_SINKS:
+                from ..ops import conv as _conv
+                if self._sinked is None:           # conv weight gradients are written by the wgrad kernels straight into the push source
+                    self._sinked = set(_conv.set_grad_sinks(self._params, self.grads.views))
+                    self._unsinked = [i for i in range(len(self._params)) if i not in self._sinked]
+                _conv.activate_grad_sinks(True)
         elif self.zero_grads_in_step:
             self.grads.flat.zero_()
         if not gather and self._params[0].grad is None:
@@ -129,7 +154,9 @@ class WorkerCompute:
         self._arm_buckets()
         if self.device.type == "cuda" and _ops.available():
             from ..ops import conv as _conv
-            _conv.refresh_dgrad_operands()          # one launch: the transposed filters every dgrad of this step reads
+            # one launch: the transposed filters every dgrad of this step reads; it is also the first reader of this step's weights and carries
+            # the transport's weights-ready wait when the worker asked for that (fetch_wait_args)
+            self._last_fused_wait = _conv.refresh_dgrad_operands(self.fetch_wait_args)
             from ..ops import elementwise as _ew
             _ew.bump_dropout_seed(self.device)      # (only when a Dropout layer has run on this device) fresh masks on every graph replay
         if self._bn_counters and self.network.training:
@@ -159,8 +186,18 @@ class WorkerCompute:
             if self.after_backward is not None:
                 self.after_backward()                  # e.g. join the transport's bucket-push stream (must happen inside a graph capture)
             if gather:
-                torch._foreach_copy_(self.grads.views, [p.grad if p.grad is not None else torch.zeros_like(v)
-                                                        for p, v in zip(self._params, self.grads.views)])
+                # what is left to gather: BatchNorm / classifier parameters (and convolutions a kernel of ours did not handle); a sinked weight
+                # whose layer fell back to the library this step has a .grad after all and is copied like the rest
+                if self._sinked:
+                    from ..ops import conv as _conv
+                    _conv.activate_grad_sinks(False)
+                    todo = self._unsinked + [i for i in self._sinked if self._params[i].grad is not None]
+                else:
+                    todo = range(len(self._params))
+                dst = [self.grads.views[i] for i in todo]
+                if dst:
+                    torch._foreach_copy_(dst, [self._params[i].grad if self._params[i].grad is not None else torch.zeros_like(self.grads.views[i])
+                                               for i in todo])
         return loss.detach(), logits.detach()
 
     _layerwise_comm = None
@@ -275,6 +312,7 @@ class WorkerCompute:
                 self._static_loss, self._static_logits = self._step_body(self._static_x, self._static_y)
         finally:
             self._capturing = False
+        self._graph_fused_wait = self._last_fused_wait     # the recorded first kernel waits for the weights itself on every replay
         self.graph_launches = _ops.launch_count - n0      # our kernels recorded in the graph, re-counted per replay
 
     @torch.no_grad()

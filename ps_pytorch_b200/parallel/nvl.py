@@ -293,11 +293,23 @@ class NvlTransport(Transport):
         return self.arena.view(self.off_bufs + 64, numel * 4, torch.float32).clone()
 
     # ---- worker side -----------------------------------------------------------------------------------------------------
-    def worker_fetch(self, weights, timeout_s=0.0):
-        """Enqueue the device-side wait for this step's weights; the host does not block."""
+    def fetch_wait_args(self):
+        """What a consumer kernel needs to acquire this step's weights itself (``WorkerCompute.fetch_wait_args``): the weights-ready words of this
+        rank, how many, the worker step word, the error word, the timeout.  Not offered in pull mode (the pull copy is the first reader)."""
+        if self.pull_weights and self.rank != 0:
+            return None
         n = self.NB if self.topology == "ps" else self.world_size
-        self.ext.wait_flag(self.arena.local_ptr + self.off_flags + self.F_WREADY, n, self.p_wstep, self.p_err, self.timeout_s)
-        ops.count_launch()
+        return (self.arena.local_ptr + self.off_flags + self.F_WREADY, n, self.p_wstep, self.p_err, float(self.timeout_s))
+
+    def worker_fetch(self, weights, timeout_s=0.0, fused_wait=False):
+        """Enqueue the device-side wait for this step's weights; the host does not block.  ``fused_wait``: the first kernel of the caller's step
+        acquires the ready words itself (ops/csrc/conv2_tcgen05.cu: weight_transpose_batched_kernel) — no wait kernel is launched here."""
+        n = self.NB if self.topology == "ps" else self.world_size
+        if not (fused_wait and not (self.pull_weights and self.rank != 0)):
+            self.ext.wait_flag(self.arena.local_ptr + self.off_flags + self.F_WREADY, n, self.p_wstep, self.p_err, self.timeout_s)
+            ops.count_launch()
+        else:
+            self.stats["fused_waits"] = self.stats.get("fused_waits", 0) + 1
         if self.pull_weights and self.rank != 0:
             # P2P pull of the fresh weights from the PS replica into ours (no flags to release: nflags = 0)
             self.ext.bcast(self.arena.peer_ptrs[0] + self.off_w, [self.arena.local_ptr + self.off_w], 0, self.T * 2,

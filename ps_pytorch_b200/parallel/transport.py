@@ -54,7 +54,7 @@ class Transport:
     def ps_signal_kill(self, ranks: List[int], step: int) -> None: pass
     def ps_shutdown(self, step: int) -> None: pass
     # worker side
-    def worker_fetch(self, weights: FlatBuffer, timeout_s: float = 0.0) -> int: raise NotImplementedError
+    def worker_fetch(self, weights: FlatBuffer, timeout_s: float = 0.0, fused_wait: bool = False) -> int: raise NotImplementedError
     def worker_push(self, step: int, grads: FlatBuffer, lo: int = 0, hi: Optional[int] = None, last: bool = True) -> None: raise NotImplementedError
     def worker_push_killed(self, step: int, grads: Optional[FlatBuffer] = None) -> None: pass
     def worker_poll_kill(self, step: int) -> bool: return False
@@ -94,7 +94,7 @@ class LocalTransport(Transport):
         self._step, self._weights_src = step, weights
         self.stats["bcast_bytes"] += weights.flat.numel() * weights.flat.element_size()
 
-    def worker_fetch(self, weights, timeout_s=0.0):
+    def worker_fetch(self, weights, timeout_s=0.0, fused_wait=False):
         if self._weights_src is not None and self._weights_src.flat.data_ptr() != weights.flat.data_ptr():
             weights.flat.copy_(self._weights_src.flat)
         return self._step
@@ -274,7 +274,7 @@ class GlooTransport(Transport):
                 st.set("psb_kill_r%d" % r, str(int(step)))
 
     # -- worker -------------------------------------------------------------------------------------------
-    def worker_fetch(self, weights, timeout_s=0.0):
+    def worker_fetch(self, weights, timeout_s=0.0, fused_wait=False):
         if self.rank != 0:
             dist.broadcast(self._step_t, src=0, group=self.group)
             if int(self._step_t[1]) == 1:

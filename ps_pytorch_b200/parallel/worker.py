@@ -20,6 +20,9 @@ from ..utils import checkpoint as ckpt
 from ..utils.metrics import accuracy  # noqa: F401  (the reference defines accuracy() in this module; kept importable from here)
 from ..utils.obs import JsonlSink, MetricsExporter, format_worker_line, logger
 
+# the step's first kernel acquires the weights-ready words itself instead of a separate wait kernel (PSB200_FUSE_WAIT=0: always the wait kernel)
+_FUSE_WAIT = os.environ.get("PSB200_FUSE_WAIT", "1") != "0"
+
 STEP_START_ = 1
 
 
@@ -90,6 +93,8 @@ class DistributedWorker(object):
         self.compute = WorkerCompute(net, self._device, self._dtype, layout=self.comm.layout, weight_storage=storage,
                                      use_graph=self._use_graph, grad_storage=gstorage,
                                      zero_grads_in_step=not getattr(self.comm, "zeroes_grads", False))
+        if _FUSE_WAIT and hasattr(self.comm, "fetch_wait_args"):
+            self.compute.fetch_wait_args = self.comm.fetch_wait_args()
         self.network = self.compute.network
         self.optimizer = torch.optim.SGD(self.network.parameters(), lr=self.lr, momentum=self.momentum)  # zero_grad only, as in the reference
         self.criterion = self.compute.criterion
@@ -111,7 +116,7 @@ class DistributedWorker(object):
 
     # ------------------------------------------------------------------------------------------------------
     def sync_fetch_step(self):
-        self.next_step = self.comm.worker_fetch(self.compute.weights)
+        self.next_step = self.comm.worker_fetch(self.compute.weights, fused_wait=self.compute.will_fuse_wait())
 
     async_fetch_step = sync_fetch_step
 

@@ -1,9 +1,13 @@
 #!/bin/bash
-# compute-sanitizer passes over the kernel tests (the reference has no race detection at all).
-# memcheck on the comm + BN + elementwise kernels, racecheck on the smem-using BN reductions, synccheck on the tcgen05 kernels.
+# compute-sanitizer over one complete training step (the reference has no race detection at all).  `smoke()` runs six steps
+# of ResNet-18 (batch 64) through the engine: every tcgen05 kernel (stem, CTA-pair halo conv, tap-table conv incl. strided dgrad, the three wgrad
+# kernels, classifier GEMMs), the BN / pooling / loss kernels and the PS kernels (push, reduce-update, broadcast, wait-flag) run under the tool.
+# racecheck = shared-memory hazards, synccheck = barrier misuse, memcheck = out-of-bounds / misaligned; logs -> gpurun_out/sanitize_*.log
 mkdir -p gpurun_out
 CS=/usr/local/cuda/bin/compute-sanitizer
-timeout 900 $CS --tool memcheck --error-exitcode 7 python -m pytest tests/test_gpu_kernels.py -m gpu -q -x -k "sgd_flat or push_reduce or batchnorm_eval or maxpool or softmax or k_of_p" > gpurun_out/sanitize_memcheck.log 2>&1; echo "memcheck rc=$?" | tee -a gpurun_out/sanitize_memcheck.log
-timeout 600 $CS --tool racecheck --error-exitcode 7 python -m pytest tests/test_gpu_kernels.py -m gpu -q -x -k "batchnorm_eval or softmax" > gpurun_out/sanitize_racecheck.log 2>&1; echo "racecheck rc=$?" | tee -a gpurun_out/sanitize_racecheck.log
-timeout 600 $CS --tool memcheck --error-exitcode 7 python -m pytest tests/test_gpu_kernels.py -m gpu -q -x -k "tc_gemm and 128-64-64" > gpurun_out/sanitize_tc.log 2>&1; echo "tc memcheck rc=$?" | tee -a gpurun_out/sanitize_tc.log
-grep -hE "ERROR SUMMARY|passed|failed" gpurun_out/sanitize_*.log | tail -12
+export PYTHONPATH=.
+for tool in ${TOOLS:-synccheck racecheck memcheck}; do
+  timeout ${SAN_TIMEOUT:-420} $CS --tool $tool --error-exitcode 7 --print-limit 20 python __graft_entry__.py smoke > gpurun_out/sanitize_$tool.log 2>&1
+  echo "$tool rc=$?" | tee -a gpurun_out/sanitize_$tool.log
+  grep -hE "ERROR SUMMARY|smoke ok|Error|hazard" gpurun_out/sanitize_$tool.log | sort | uniq -c | head -12
+done

@@ -819,3 +819,53 @@ def test_bound_gradients_accumulate_correctly(ext, backend):
         res.append([p.grad.float().clone() for p in ps])
     for a, b in zip(*res):
         assert torch.allclose(a, b, rtol=1e-2, atol=1e-3 * max(1.0, a.abs().max().item())), (a - b).abs().max().item()
+
+
+def test_weight_gradients_land_in_the_arena_without_a_gather(ext):
+    """Gather mode: the wgrad kernels write conv weight gradients straight into the gradient arena (``ops.conv`` sinks); the arena must hold the
+    same gradients as the hand-over + multi-tensor-copy path (``PSB200_GRAD_SINKS=0``), and the sink path must really have run."""
+    from ps_pytorch_b200 import nn as pnn
+    from ps_pytorch_b200.models import build_model
+    from ps_pytorch_b200.ops import conv as C
+    from ps_pytorch_b200.parallel import compute as CP
+    x = torch.randn(64, 3, 32, 32, device="cuda")
+    y = torch.randint(0, 10, (64,), device="cuda")
+    flats = []
+    for sinks in (True, False):
+        torch.manual_seed(0)
+        old = CP._GRAD_SINKS
+        CP._GRAD_SINKS = sinks
+        try:
+            with pnn.backend("sm100"):
+                wc = CP.WorkerCompute(build_model("ResNet18", 10), "cuda", torch.bfloat16)
+                n0 = C.sink_writes
+                wc.train_step(x, y)
+                torch.cuda.synchronize()
+        finally:
+            CP._GRAD_SINKS = old
+            C.activate_grad_sinks(False)
+        assert (C.sink_writes - n0 > 15) == sinks
+        flats.append(wc.grads.flat.float().clone())
+    assert flats[1].abs().max() > 0
+    assert torch.allclose(flats[0], flats[1], rtol=1e-2, atol=1e-3 * flats[1].abs().max().item())
+
+
+@pytest.mark.parametrize("graph", [False, True])
+def test_weights_ready_wait_rides_in_the_first_kernel_of_the_step(ext, graph):
+    """From the second step on no wait_flag_kernel is launched: weight_transpose_batched_kernel (the step's first reader of the weights)
+    acquires the PS's weights-ready words itself.  The job must still train (every step sees the weights of the previous update) and the
+    transport must count the fused waits."""
+    from ps_pytorch_b200.engine import PSJob
+    torch.manual_seed(0)
+    job = PSJob(network="ResNet18", dataset="Cifar10", batch_size=64, device="cuda:0", dtype="bf16", cuda_graph=graph, backend="sm100")
+    x = torch.randn(64, 3, 32, 32).to(torch.bfloat16).contiguous(memory_format=torch.channels_last).pin_memory()
+    y = torch.randint(0, 10, (64,)).pin_memory()
+    losses = [float(job.step(x, y)) for _ in range(8)]
+    torch.cuda.synchronize()
+    job.comm.check_error()
+    fused = job.comm.stats.get("fused_waits", 0)
+    # every update must have been seen by the next step: the replica equals bf16(master) after the last step
+    assert torch.equal(job.worker.compute.weights.flat, job.master.master.flat.to(torch.bfloat16))
+    job.close()
+    assert fused >= 6, fused
+    assert losses[-1] < losses[0], losses
