@@ -49,6 +49,8 @@ def get():
         if _mod is None:
             try:
                 _mod = _load_so("ps_b200_C")
+                if os.environ.get("PSB200_PDL", "1") == "0" and hasattr(_mod, "set_pdl"):
+                    _mod.set_pdl(0)            # programmatic dependent launch of the step's kernels (csrc/pdl.cuh) off
             except Exception as e:  # noqa: BLE001
                 _err = e
                 raise

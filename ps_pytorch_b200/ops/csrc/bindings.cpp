@@ -22,6 +22,10 @@ std::vector<at::Tensor> bn_forward(at::Tensor, c10::optional<at::Tensor>, c10::o
 std::vector<at::Tensor> bn_backward(at::Tensor, c10::optional<at::Tensor>, at::Tensor, c10::optional<at::Tensor>, at::Tensor, at::Tensor, bool, bool, c10::optional<at::Tensor>,
                                     c10::optional<at::Tensor>, c10::optional<at::Tensor>);
 void bn_set_finalize_wide(int);
+// programmatic dependent launch of the step's kernels (pdl.cuh); PSB200_PDL=0 -> ops/__init__.py calls set_pdl(0)
+static int g_pdl = 1;
+int pdl_enabled() { return g_pdl; }
+void pdl_set(int on) { g_pdl = on ? 1 : 0; }
 // elementwise.cu
 at::Tensor relu_forward(at::Tensor);
 at::Tensor relu_backward(at::Tensor, at::Tensor);
@@ -61,7 +65,7 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
     m.def("add_step", &add_step); m.def("set_word", &set_word); m.def("make_hp", &make_hp); m.def("hp_steps", &hp_steps);
     m.def("ru_set_mc_src", &ru_set_mc_src); m.def("bn_forward", &bn_forward, pybind11::arg("x"), pybind11::arg("gamma"), pybind11::arg("beta"), pybind11::arg("running_mean"), pybind11::arg("running_var"),
           pybind11::arg("residual"), pybind11::arg("training"), pybind11::arg("momentum"), pybind11::arg("eps"), pybind11::arg("relu"), pybind11::arg("ws"),
-          pybind11::arg("conv_partial") = c10::optional<at::Tensor>()); m.def("bn_backward", &bn_backward); m.def("bn_set_finalize_wide", &bn_set_finalize_wide);
+          pybind11::arg("conv_partial") = c10::optional<at::Tensor>()); m.def("bn_backward", &bn_backward); m.def("bn_set_finalize_wide", &bn_set_finalize_wide); m.def("set_pdl", &pdl_set); m.def("pdl_enabled", &pdl_enabled);
     m.def("relu_forward", &relu_forward); m.def("relu_backward", &relu_backward);
     m.def("maxpool2x2_forward", &maxpool2x2_forward); m.def("maxpool2x2_backward", &maxpool2x2_backward);
     m.def("maxpool3x3s2_forward", &maxpool3x3s2_forward); m.def("maxpool3x3s2_backward", &maxpool3x3s2_backward);

@@ -14,6 +14,7 @@
 #include <torch/extension.h>
 #include <ATen/cuda/CUDAContext.h>
 #include "common.cuh"
+#include "pdl.cuh"
 
 namespace psb {
 
@@ -197,6 +198,7 @@ __global__ void bn_eval_coef_kernel(int C, const PT* gamma, const PT* beta, cons
 template <bool RELU, bool RES>
 __global__ void __launch_bounds__(kBnThreads) bn_apply_kernel(const uint4* __restrict__ x, const uint4* __restrict__ res, uint4* __restrict__ z,
                                                               const float* __restrict__ coef_a, const float* __restrict__ coef_b, long long nvec, int LC) {
+    pdl_trigger(); pdl_wait();      // pdl.cuh: the successor may become resident now; nothing of a predecessor is touched before this line
     const int lane = threadIdx.x % LC;
     float a[8], b[8];
 #pragma unroll
@@ -231,6 +233,7 @@ template <bool RELU, bool MASKX>
 __global__ void __launch_bounds__(kBnThreads) bn_bwd_reduce_kernel(const uint4* __restrict__ dz, const uint4* __restrict__ z, const uint4* __restrict__ x,
                                                                    const float* __restrict__ mean, long long M, int LC, float* __restrict__ partial,
                                                                    float* ws, BnBwdFin fin, const float* __restrict__ coef_a, const float* __restrict__ coef_b) {
+    pdl_trigger(); pdl_wait();      // pdl.cuh: the successor may become resident now; nothing of a predecessor is touched before this line
     extern __shared__ float sm[];
     const int lane = threadIdx.x % LC, ty = threadIdx.x / LC, RP = kBnThreads / LC;
     float mu[8], s[8], q[8], ca[8], cb[8];
@@ -360,6 +363,7 @@ __global__ void __launch_bounds__(256) bn_finalize_wide_kernel(const float* part
                                                                const PT* __restrict__ beta, float* running_mean, float* running_var,
                                                                float momentum, float eps, float* __restrict__ mean, float* __restrict__ invstd,
                                                                float* __restrict__ coef_a, float* __restrict__ coef_b, int clear) {
+    pdl_trigger(); pdl_wait();      // pdl.cuh: the successor may become resident now; nothing of a predecessor is touched before this line
     const int c = blockIdx.x * 8 + (threadIdx.x & 7);
     float s, q;
     wide_partial_sum(partial, nblk, C, c, s, q, clear != 0);
@@ -387,6 +391,7 @@ __global__ void __launch_bounds__(256) bn_bwd_finalize_wide_kernel(const float* 
                                                                    const PT* __restrict__ gamma, const float* __restrict__ invstd,
                                                                    PT* __restrict__ dgamma, PT* __restrict__ dbeta, float* __restrict__ c1,
                                                                    float* __restrict__ c2, float* __restrict__ c3) {
+    pdl_trigger(); pdl_wait();      // pdl.cuh: the successor may become resident now; nothing of a predecessor is touched before this line
     const int c = blockIdx.x * 8 + (threadIdx.x & 7);
     float s, q;
     wide_partial_sum(partial, nblk, C, c, s, q);
@@ -408,6 +413,7 @@ __global__ void __launch_bounds__(kBnThreads) bn_bwd_apply_kernel(const uint4* _
                                                                   const float* __restrict__ mean, const float* __restrict__ c1, const float* __restrict__ c2,
                                                                   const float* __restrict__ c3, uint4* __restrict__ dx, uint4* __restrict__ dres,
                                                                   long long nvec, int LC, const float* __restrict__ coef_a, const float* __restrict__ coef_b) {
+    pdl_trigger(); pdl_wait();      // pdl.cuh: the successor may become resident now; nothing of a predecessor is touched before this line
     const int lane = threadIdx.x % LC;
     float mu[8], k1[8], k2[8], k3[8], ca[8], cb[8];
 #pragma unroll
@@ -469,11 +475,11 @@ std::vector<at::Tensor> bn_forward(at::Tensor x, c10::optional<at::Tensor> gamma
                     "conv_partial must be a contiguous fp32 [rows, 2, C] tensor");
         const int rows = (int)(conv_partial->numel() / (2 * C));
         if (p_bf16)
-            bn_finalize_wide_kernel<__nv_bfloat16><<<(C + 7) / 8, 256, 0, stream>>>(conv_partial->data_ptr<float>(), rows, C, M, nullptr,
+            launch_pdl(bn_finalize_wide_kernel<__nv_bfloat16>, dim3((C + 7) / 8), dim3(256), 0, stream, conv_partial->data_ptr<float>(), rows, C, M, nullptr,
                 (const __nv_bfloat16*)gp, (const __nv_bfloat16*)bp, rm, rv, (float)momentum, (float)eps, mean.data_ptr<float>(), invstd.data_ptr<float>(),
                 ca.data_ptr<float>(), cb.data_ptr<float>(), 1);
         else
-            bn_finalize_wide_kernel<float><<<(C + 7) / 8, 256, 0, stream>>>(conv_partial->data_ptr<float>(), rows, C, M, nullptr,
+            launch_pdl(bn_finalize_wide_kernel<float>, dim3((C + 7) / 8), dim3(256), 0, stream, conv_partial->data_ptr<float>(), rows, C, M, nullptr,
                 (const float*)gp, (const float*)bp, rm, rv, (float)momentum, (float)eps, mean.data_ptr<float>(), invstd.data_ptr<float>(),
                 ca.data_ptr<float>(), cb.data_ptr<float>(), 1);
         C10_CUDA_KERNEL_LAUNCH_CHECK();
@@ -492,11 +498,11 @@ std::vector<at::Tensor> bn_forward(at::Tensor x, c10::optional<at::Tensor> gamma
         C10_CUDA_KERNEL_LAUNCH_CHECK();
         const int fb = (C + 31) / 32;
         if (g_bn_finalize_wide && p_bf16)
-            bn_finalize_wide_kernel<__nv_bfloat16><<<(C + 7) / 8, 256, 0, stream>>>(partial.data_ptr<float>(), nblk, C, M, (const __nv_bfloat16*)x.data_ptr(),
+            launch_pdl(bn_finalize_wide_kernel<__nv_bfloat16>, dim3((C + 7) / 8), dim3(256), 0, stream, partial.data_ptr<float>(), nblk, C, M, (const __nv_bfloat16*)x.data_ptr(),
                 (const __nv_bfloat16*)gp, (const __nv_bfloat16*)bp, rm, rv, (float)momentum, (float)eps, mean.data_ptr<float>(), invstd.data_ptr<float>(),
                 ca.data_ptr<float>(), cb.data_ptr<float>(), 0);
         else if (g_bn_finalize_wide)
-            bn_finalize_wide_kernel<float><<<(C + 7) / 8, 256, 0, stream>>>(partial.data_ptr<float>(), nblk, C, M, (const __nv_bfloat16*)x.data_ptr(),
+            launch_pdl(bn_finalize_wide_kernel<float>, dim3((C + 7) / 8), dim3(256), 0, stream, partial.data_ptr<float>(), nblk, C, M, (const __nv_bfloat16*)x.data_ptr(),
                 (const float*)gp, (const float*)bp, rm, rv, (float)momentum, (float)eps, mean.data_ptr<float>(), invstd.data_ptr<float>(),
                 ca.data_ptr<float>(), cb.data_ptr<float>(), 0);
         else if (p_bf16)
@@ -520,10 +526,10 @@ std::vector<at::Tensor> bn_forward(at::Tensor x, c10::optional<at::Tensor> gamma
     const uint4* rp = residual.has_value() ? reinterpret_cast<const uint4*>(residual->data_ptr()) : nullptr;
     uint4* zp = reinterpret_cast<uint4*>(z.data_ptr());
     const float *pa = ca.data_ptr<float>(), *pb = cb.data_ptr<float>();
-    if (relu && rp) bn_apply_kernel<true, true><<<grid, kBnThreads, 0, stream>>>(xp, rp, zp, pa, pb, nvec, LC);
-    else if (relu) bn_apply_kernel<true, false><<<grid, kBnThreads, 0, stream>>>(xp, rp, zp, pa, pb, nvec, LC);
-    else if (rp) bn_apply_kernel<false, true><<<grid, kBnThreads, 0, stream>>>(xp, rp, zp, pa, pb, nvec, LC);
-    else bn_apply_kernel<false, false><<<grid, kBnThreads, 0, stream>>>(xp, rp, zp, pa, pb, nvec, LC);
+    if (relu && rp) launch_pdl(bn_apply_kernel<true, true>, dim3(grid), dim3(kBnThreads), 0, stream, xp, rp, zp, pa, pb, nvec, LC);
+    else if (relu) launch_pdl(bn_apply_kernel<true, false>, dim3(grid), dim3(kBnThreads), 0, stream, xp, rp, zp, pa, pb, nvec, LC);
+    else if (rp) launch_pdl(bn_apply_kernel<false, true>, dim3(grid), dim3(kBnThreads), 0, stream, xp, rp, zp, pa, pb, nvec, LC);
+    else launch_pdl(bn_apply_kernel<false, false>, dim3(grid), dim3(kBnThreads), 0, stream, xp, rp, zp, pa, pb, nvec, LC);
     C10_CUDA_KERNEL_LAUNCH_CHECK();
     return {z, mean, invstd, ca, cb};
 }
@@ -556,22 +562,22 @@ std::vector<at::Tensor> bn_backward(at::Tensor dz, c10::optional<at::Tensor> z_o
         TORCH_CHECK(ws->scalar_type() == at::kFloat && ws->numel() >= 2 * C + 1 && ws->is_cuda(), "bn workspace must hold 2*C+1 floats");
         BnBwdFin fin{gamma.has_value() ? gamma->data_ptr() : nullptr, invstd.data_ptr<float>(), dgamma.data_ptr(), dbeta.data_ptr(),
                      c1.data_ptr<float>(), c2.data_ptr<float>(), c3.data_ptr<float>(), p_bf16 ? 1 : 0};
-        if (maskx) bn_bwd_reduce_kernel<true, true><<<nblk, kBnThreads, smem, stream>>>(dzp, zp, xp, mean.data_ptr<float>(), M, LC, nullptr, ws->data_ptr<float>(), fin, pca, pcb);
-        else if (relu) bn_bwd_reduce_kernel<true, false><<<nblk, kBnThreads, smem, stream>>>(dzp, zp, xp, mean.data_ptr<float>(), M, LC, nullptr, ws->data_ptr<float>(), fin, pca, pcb);
-        else bn_bwd_reduce_kernel<false, false><<<nblk, kBnThreads, smem, stream>>>(dzp, zp, xp, mean.data_ptr<float>(), M, LC, nullptr, ws->data_ptr<float>(), fin, pca, pcb);
+        if (maskx) launch_pdl(bn_bwd_reduce_kernel<true, true>, dim3(nblk), dim3(kBnThreads), smem, stream, dzp, zp, xp, mean.data_ptr<float>(), M, LC, nullptr, ws->data_ptr<float>(), fin, pca, pcb);
+        else if (relu) launch_pdl(bn_bwd_reduce_kernel<true, false>, dim3(nblk), dim3(kBnThreads), smem, stream, dzp, zp, xp, mean.data_ptr<float>(), M, LC, nullptr, ws->data_ptr<float>(), fin, pca, pcb);
+        else launch_pdl(bn_bwd_reduce_kernel<false, false>, dim3(nblk), dim3(kBnThreads), smem, stream, dzp, zp, xp, mean.data_ptr<float>(), M, LC, nullptr, ws->data_ptr<float>(), fin, pca, pcb);
         C10_CUDA_KERNEL_LAUNCH_CHECK();
     } else {
         at::Tensor partial = at::empty({nblk, 2, C}, fopt);
-        if (maskx) bn_bwd_reduce_kernel<true, true><<<nblk, kBnThreads, smem, stream>>>(dzp, zp, xp, mean.data_ptr<float>(), M, LC, partial.data_ptr<float>(), nullptr, BnBwdFin{}, pca, pcb);
-        else if (relu) bn_bwd_reduce_kernel<true, false><<<nblk, kBnThreads, smem, stream>>>(dzp, zp, xp, mean.data_ptr<float>(), M, LC, partial.data_ptr<float>(), nullptr, BnBwdFin{}, pca, pcb);
-        else bn_bwd_reduce_kernel<false, false><<<nblk, kBnThreads, smem, stream>>>(dzp, zp, xp, mean.data_ptr<float>(), M, LC, partial.data_ptr<float>(), nullptr, BnBwdFin{}, pca, pcb);
+        if (maskx) launch_pdl(bn_bwd_reduce_kernel<true, true>, dim3(nblk), dim3(kBnThreads), smem, stream, dzp, zp, xp, mean.data_ptr<float>(), M, LC, partial.data_ptr<float>(), nullptr, BnBwdFin{}, pca, pcb);
+        else if (relu) launch_pdl(bn_bwd_reduce_kernel<true, false>, dim3(nblk), dim3(kBnThreads), smem, stream, dzp, zp, xp, mean.data_ptr<float>(), M, LC, partial.data_ptr<float>(), nullptr, BnBwdFin{}, pca, pcb);
+        else launch_pdl(bn_bwd_reduce_kernel<false, false>, dim3(nblk), dim3(kBnThreads), smem, stream, dzp, zp, xp, mean.data_ptr<float>(), M, LC, partial.data_ptr<float>(), nullptr, BnBwdFin{}, pca, pcb);
         C10_CUDA_KERNEL_LAUNCH_CHECK();
         const int fb = (C + 31) / 32;
         if (g_bn_finalize_wide && p_bf16)
-            bn_bwd_finalize_wide_kernel<__nv_bfloat16><<<(C + 7) / 8, 256, 0, stream>>>(partial.data_ptr<float>(), nblk, C, M, (const __nv_bfloat16*)gamma->data_ptr(), invstd.data_ptr<float>(),
+            launch_pdl(bn_bwd_finalize_wide_kernel<__nv_bfloat16>, dim3((C + 7) / 8), dim3(256), 0, stream, partial.data_ptr<float>(), nblk, C, M, (const __nv_bfloat16*)gamma->data_ptr(), invstd.data_ptr<float>(),
                 (__nv_bfloat16*)dgamma.data_ptr(), (__nv_bfloat16*)dbeta.data_ptr(), c1.data_ptr<float>(), c2.data_ptr<float>(), c3.data_ptr<float>());
         else if (g_bn_finalize_wide)
-            bn_bwd_finalize_wide_kernel<float><<<(C + 7) / 8, 256, 0, stream>>>(partial.data_ptr<float>(), nblk, C, M, gamma.has_value() ? gamma->data_ptr<float>() : nullptr, invstd.data_ptr<float>(),
+            launch_pdl(bn_bwd_finalize_wide_kernel<float>, dim3((C + 7) / 8), dim3(256), 0, stream, partial.data_ptr<float>(), nblk, C, M, gamma.has_value() ? gamma->data_ptr<float>() : nullptr, invstd.data_ptr<float>(),
                 dgamma.data_ptr<float>(), dbeta.data_ptr<float>(), c1.data_ptr<float>(), c2.data_ptr<float>(), c3.data_ptr<float>());
         else if (p_bf16)
             bn_bwd_finalize_kernel<__nv_bfloat16><<<fb, 256, 0, stream>>>(partial.data_ptr<float>(), nblk, C, M, (const __nv_bfloat16*)gamma->data_ptr(), invstd.data_ptr<float>(),
@@ -589,10 +595,10 @@ std::vector<at::Tensor> bn_backward(at::Tensor dz, c10::optional<at::Tensor> z_o
     uint4* dxp = (uint4*)dx.data_ptr();
     uint4* drp = (has_res && relu) ? (uint4*)dres.data_ptr() : nullptr;
     const float *mp = mean.data_ptr<float>(), *p1 = c1.data_ptr<float>(), *p2 = c2.data_ptr<float>(), *p3 = c3.data_ptr<float>();
-    if (relu && has_res) bn_bwd_apply_kernel<true, true, false><<<grid, kBnThreads, 0, stream>>>(dzp, zp, xp, mp, p1, p2, p3, dxp, drp, nvec, LC, pca, pcb);
-    else if (maskx) bn_bwd_apply_kernel<true, false, true><<<grid, kBnThreads, 0, stream>>>(dzp, zp, xp, mp, p1, p2, p3, dxp, drp, nvec, LC, pca, pcb);
-    else if (relu) bn_bwd_apply_kernel<true, false, false><<<grid, kBnThreads, 0, stream>>>(dzp, zp, xp, mp, p1, p2, p3, dxp, drp, nvec, LC, pca, pcb);
-    else bn_bwd_apply_kernel<false, false, false><<<grid, kBnThreads, 0, stream>>>(dzp, zp, xp, mp, p1, p2, p3, dxp, drp, nvec, LC, pca, pcb);
+    if (relu && has_res) launch_pdl(bn_bwd_apply_kernel<true, true, false>, dim3(grid), dim3(kBnThreads), 0, stream, dzp, zp, xp, mp, p1, p2, p3, dxp, drp, nvec, LC, pca, pcb);
+    else if (maskx) launch_pdl(bn_bwd_apply_kernel<true, false, true>, dim3(grid), dim3(kBnThreads), 0, stream, dzp, zp, xp, mp, p1, p2, p3, dxp, drp, nvec, LC, pca, pcb);
+    else if (relu) launch_pdl(bn_bwd_apply_kernel<true, false, false>, dim3(grid), dim3(kBnThreads), 0, stream, dzp, zp, xp, mp, p1, p2, p3, dxp, drp, nvec, LC, pca, pcb);
+    else launch_pdl(bn_bwd_apply_kernel<false, false, false>, dim3(grid), dim3(kBnThreads), 0, stream, dzp, zp, xp, mp, p1, p2, p3, dxp, drp, nvec, LC, pca, pcb);
     C10_CUDA_KERNEL_LAUNCH_CHECK();
     return {dx, dres, dgamma, dbeta};
 }

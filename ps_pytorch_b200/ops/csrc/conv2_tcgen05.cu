@@ -24,6 +24,7 @@
 #include <stdint.h>
 #include <stdio.h>
 #include "tc_common.cuh"
+#include "pdl.cuh"
 #include "common.cuh"
 
 namespace psb {
@@ -90,6 +91,7 @@ tc_conv2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
     tc_fence_before();
     cluster_sync_all();
     tc_fence_after();
+    pdl_trigger(); pdl_wait();                  // pdl.cuh: prologue done; from here on the kernel touches global memory
     const uint32_t tmem_base = *tmem_base_smem;
 
     // pair tile t -> (class, pair of M tiles, N tile); N tile fastest so that the pairs of one wave share their A rectangles through L2
@@ -207,10 +209,10 @@ static const char* launch_conv2(const CUtensorMap& ta, const CUtensorMap& tb, co
     if (ptiles < pairs) pairs = ptiles;
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(2 * pairs); cfg.blockDim = dim3(kThreads); cfg.dynamicSmemBytes = Cfg::kSmemBytes; cfg.stream = stream;
-    cudaLaunchAttribute at[1];
+    cudaLaunchAttribute at[2];
     at[0].id = cudaLaunchAttributeClusterDimension;
     at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
-    cfg.attrs = at; cfg.numAttrs = 1;
+    cfg.attrs = at; cfg.numAttrs = pdl_attr(at, 1);
     return cudaLaunchKernelEx(&cfg, tc_conv2_kernel<BN>, ta, tb, p) == cudaSuccess ? nullptr : "kernel launch failed";
 }
 

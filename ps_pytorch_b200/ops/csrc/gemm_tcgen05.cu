@@ -24,6 +24,7 @@
 #include <stdio.h>
 #include <mutex>
 #include "tc_common.cuh"
+#include "pdl.cuh"
 
 namespace psb {
 
@@ -487,6 +488,7 @@ tc_conv_halo2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
     tc_fence_before();
     cluster_sync_all();
     tc_fence_after();
+    pdl_trigger(); pdl_wait();                  // pdl.cuh: prologue done; from here on the kernel touches global memory
     const uint32_t tmem_base = *tmem_base_smem;
     // pair tiles: nt slowest, pairs of neighbouring M tiles fastest; rank r takes M tile 2*pm + r (a ghost when n_tiles_m is odd)
     const int n_pairs_m = (p.n_tiles_m + 1) / 2;
@@ -655,6 +657,7 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmap_dy, const __grid_consta
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
+    pdl_trigger(); pdl_wait();                  // pdl.cuh: prologue done; from here on the kernel touches global memory
     const uint32_t tmem_base = *tmem_base_smem;
 
     // item -> (tap fastest: CTAs of one wave read the same dY / X region, L2-friendly), then K split, ci tile, co tile
@@ -757,6 +760,7 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmap_dy, const __grid_consta
 
 // scratch fp32 -> bf16 gradient, scratch left zeroed (self-cleaning)
 __global__ void wgrad_finish_kernel(float* __restrict__ acc, __nv_bfloat16* __restrict__ out, long long n) {
+    pdl_trigger(); pdl_wait();
     for (long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 4; i < n; i += (long long)gridDim.x * blockDim.x * 4) {
         float4 v = *reinterpret_cast<float4*>(acc + i);
         *reinterpret_cast<float4*>(acc + i) = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -767,7 +771,7 @@ __global__ void wgrad_finish_kernel(float* __restrict__ acc, __nv_bfloat16* __re
 }
 
 void wgrad_finish_launch(float* acc, void* out, long long n, cudaStream_t stream) {
-    wgrad_finish_kernel<<<(int)((n / 4 + 255) / 256 < 1184 ? (n / 4 + 255) / 256 : 1184), 256, 0, stream>>>(acc, (__nv_bfloat16*)out, n);
+    launch_pdl(wgrad_finish_kernel, dim3((int)((n / 4 + 255) / 256 < 1184 ? (n / 4 + 255) / 256 : 1184)), dim3(256), 0, stream, acc, (__nv_bfloat16*)out, n);
 }
 
 // ------------------------------------------------------------------------------------------------------------------ host
@@ -880,10 +884,10 @@ static const char* launch_halo_pair(const CUtensorMap& ta, const CUtensorMap& tb
     if (ptiles < pairs) pairs = ptiles;
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(2 * pairs); cfg.blockDim = dim3(kThreads); cfg.dynamicSmemBytes = smem_bytes; cfg.stream = stream;
-    cudaLaunchAttribute at[1];
+    cudaLaunchAttribute at[2];
     at[0].id = cudaLaunchAttributeClusterDimension;
     at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
-    cfg.attrs = at; cfg.numAttrs = 1;
+    cfg.attrs = at; cfg.numAttrs = pdl_attr(at, 1);
     return cudaLaunchKernelEx(&cfg, tc_conv_halo2_kernel<BN>, ta, tb, p) == cudaSuccess ? nullptr : "kernel launch failed";
 }
 
@@ -1020,7 +1024,7 @@ static const char* launch_wgrad(const CUtensorMap& ta, const CUtensorMap& tb, co
         attr = true;
     }
     const int grid = p.n_items < wgrad_sms() ? p.n_items : wgrad_sms();
-    tc_wgrad_kernel<BN, MM, KP><<<grid, kThreads, Cfg::kSmemBytes, stream>>>(ta, tb, p);
+    launch_pdl(tc_wgrad_kernel<BN, MM, KP>, dim3(grid), dim3(kThreads), Cfg::kSmemBytes, stream, ta, tb, p);
     return cudaGetLastError() == cudaSuccess ? nullptr : "kernel launch failed";
 }
 
@@ -1068,7 +1072,7 @@ const char* tc_conv_wgrad(const void* dY, const void* X, void* dW, float* scratc
     else e = launch_wgrad<64, 64, 128>(ta, tb, p, stream);
     if (e) return e;
     const long long n = (long long)Cout * R * S * Cin;
-    wgrad_finish_kernel<<<(int)((n / 4 + 255) / 256 < 1184 ? (n / 4 + 255) / 256 : 1184), 256, 0, stream>>>(scratch32, (__nv_bfloat16*)dW, n);
+    launch_pdl(wgrad_finish_kernel, dim3((int)((n / 4 + 255) / 256 < 1184 ? (n / 4 + 255) / 256 : 1184)), dim3(256), 0, stream, scratch32, (__nv_bfloat16*)dW, n);
     return cudaGetLastError() == cudaSuccess ? nullptr : "finish kernel launch failed";
 }
 

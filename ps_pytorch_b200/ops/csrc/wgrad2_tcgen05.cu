@@ -17,6 +17,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include "tc_common.cuh"
+#include "pdl.cuh"
 
 namespace psb {
 
@@ -64,6 +65,7 @@ tc_wgrad2_kernel(const __grid_constant__ CUtensorMap tmap_dy, const __grid_const
     tc_fence_before();
     cluster_sync_all();
     tc_fence_after();
+    pdl_trigger(); pdl_wait();                  // pdl.cuh: prologue done; from here on the kernel touches global memory
     const uint32_t tmem_base = *tmem_base_smem;
     const int cluster_id = blockIdx.x >> 1, n_clusters = gridDim.x >> 1;
 
@@ -178,10 +180,10 @@ static const char* launch_wg2(const CUtensorMap& ta, const CUtensorMap& tb, cons
     if (p.n_items < pairs) pairs = p.n_items;
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(2 * pairs); cfg.blockDim = dim3(kThreads); cfg.dynamicSmemBytes = Cfg::kSmemBytes; cfg.stream = stream;
-    cudaLaunchAttribute at[1];
+    cudaLaunchAttribute at[2];
     at[0].id = cudaLaunchAttributeClusterDimension;
     at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
-    cfg.attrs = at; cfg.numAttrs = 1;
+    cfg.attrs = at; cfg.numAttrs = pdl_attr(at, 1);
     return cudaLaunchKernelEx(&cfg, tc_wgrad2_kernel<BN2>, ta, tb, p) == cudaSuccess ? nullptr : "kernel launch failed";
 }
 

@@ -23,6 +23,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include "tc_common.cuh"
+#include "pdl.cuh"
 
 namespace psb {
 
@@ -69,6 +70,7 @@ tc_wgrad_halo_kernel(const __grid_constant__ CUtensorMap tmap_dy, const __grid_c
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
+    pdl_trigger(); pdl_wait();                  // pdl.cuh: prologue done; from here on the kernel touches global memory
     const uint32_t tmem_base = *tmem_base_smem;
 
     // item -> (row group fastest, then ci tile, co tile: the CTAs of one wave stream the same pixels; K split slowest)
@@ -194,7 +196,7 @@ static const char* launch_wgh(const CUtensorMap& ta, const CUtensorMap& tb, cons
     int grid = p.n_items < wgrad_sms() ? p.n_items : wgrad_sms();
     grid &= ~1;                                       // even: the two row groups of a pixel range stay in the same round (decode)
     if (grid < 2) grid = 2;
-    tc_wgrad_halo_kernel<MM><<<grid, kThreads, smem_bytes, stream>>>(ta, tb, p);
+    launch_pdl(tc_wgrad_halo_kernel<MM>, dim3(grid), dim3(kThreads), smem_bytes, stream, ta, tb, p);
     return cudaGetLastError() == cudaSuccess ? nullptr : "kernel launch failed";
 }
 

@@ -756,7 +756,8 @@ def test_stem_tensorcore_fprop_and_wgrad(ext, shape, relu_bias):
     F.conv2d(x.float(), wr, None, 1, 1).backward(dy.float())
     err = (dw.float() - wr.grad).abs().max().item()
     assert err <= 0.02 * max(1.0, wr.grad.abs().max().item()), err
-    assert torch.equal(dw, dw2)
+    # fp32 red.add across CTAs: the summation order may differ between launches, so allow one bf16 ulp
+    assert (dw.float() - dw2.float()).abs().max().item() <= 2.0 ** -7 * dw.float().abs().max().item()
 
 
 @pytest.mark.parametrize("shape", [(4, 64, 16, 16), (3, 64, 15, 9), (2, 8, 7, 7)])
