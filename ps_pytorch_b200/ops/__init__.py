@@ -49,8 +49,8 @@ def get():
         if _mod is None:
             try:
                 _mod = _load_so("ps_b200_C")
-                if os.environ.get("PSB200_PDL", "1") == "0" and hasattr(_mod, "set_pdl"):
-                    _mod.set_pdl(0)            # programmatic dependent launch of the step's kernels (csrc/pdl.cuh) off
+                if os.environ.get("PSB200_PDL", "0") == "1" and hasattr(_mod, "set_pdl"):
+                    _mod.set_pdl(1)            # programmatic dependent launch of the step's kernels (csrc/pdl.cuh): measured slower, opt-in
             except Exception as e:  # noqa: BLE001
                 _err = e
                 raise

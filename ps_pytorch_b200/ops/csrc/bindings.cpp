@@ -22,8 +22,9 @@ std::vector<at::Tensor> bn_forward(at::Tensor, c10::optional<at::Tensor>, c10::o
 std::vector<at::Tensor> bn_backward(at::Tensor, c10::optional<at::Tensor>, at::Tensor, c10::optional<at::Tensor>, at::Tensor, at::Tensor, bool, bool, c10::optional<at::Tensor>,
                                     c10::optional<at::Tensor>, c10::optional<at::Tensor>);
 void bn_set_finalize_wide(int);
-// programmatic dependent launch of the step's kernels (pdl.cuh); PSB200_PDL=0 -> ops/__init__.py calls set_pdl(0)
-static int g_pdl = 1;
+// programmatic dependent launch of the step's kernels (pdl.cuh).  OFF by default: measured 6.87 vs 6.24 ms/step (profiles/run30_pdl.md) — grids that
+// sit resident behind griddepcontrol.wait take the thread / shared-memory slots the side-stream weight gradients would have filled.  PSB200_PDL=1 enables.
+static int g_pdl = 0;
 int pdl_enabled() { return g_pdl; }
 void pdl_set(int on) { g_pdl = on ? 1 : 0; }
 // elementwise.cu

@@ -8,7 +8,9 @@
 //     predecessor may still be reading, for buffers this kernel writes) -> blocks until all predecessor grids have completed and flushed.
 // Both instructions are no-ops for a grid launched without the attribute, so a kernel is safe under either launch mode, and a kernel that was
 // NOT converted is launched the ordinary way (full stream order).  Inside a stream capture the attribute becomes a programmatic edge of the graph.
-// PSB200_PDL=0 (ops/__init__.py -> set_pdl) turns the attribute off everywhere.
+// MEASURED (profiles/run30_pdl.md): correct (whole GPU suite green with it on) but 10 % SLOWER for the ResNet-18 step, 6.87 vs 6.24 ms: the step hides its
+// weight gradients on a low-priority side stream inside the memory-bound BatchNorm kernels, and grids parked behind griddepcontrol.wait occupy exactly the
+// thread / shared-memory slots those kernels need.  The attribute is therefore OFF by default; PSB200_PDL=1 (ops/__init__.py -> set_pdl) turns it on.
 #pragma once
 #include <cuda_runtime.h>
 
