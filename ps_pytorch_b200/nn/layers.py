@@ -140,7 +140,9 @@ class AvgPool2d(nn.AvgPool2d):
 
 class Dropout(nn.Dropout):
     def forward(self, x):
-        if self.training and use_sm100(x):
+        if not self.training or self.p == 0.0:
+            return x
+        if use_sm100(x):
             from ..ops import elementwise as _ew
             if _ew.dropout_supported(x, self.p):
                 return _ew.dropout(x, self.p, self)

@@ -870,3 +870,47 @@ def test_weights_ready_wait_rides_in_the_first_kernel_of_the_step(ext, graph):
     job.close()
     assert fused >= 6, fused
     assert losses[-1] < losses[0], losses
+
+
+@pytest.mark.parametrize("name,shape", [("VGG11_plain", (64, 3, 32, 32)), ("VGG16", (64, 3, 32, 32)), ("VGG16_bn", (64, 3, 32, 32)),
+                                        ("LeNet", (64, 1, 28, 28)), ("ResNet50", (32, 3, 32, 32))])
+def test_model_zoo_step_sm100_vs_fp32(ext, name, shape):
+    """Every model family through the sm100 layers (conv with bias + fused ReLU, 2x2 max-pool, linear layers on tc_gemm, bottleneck blocks,
+    1-channel LeNet convolutions): loss and gradient of one training step against an fp32 run of the same weights; the bf16 library path
+    is the yardstick for how close bf16 can get.  Dropout is set to p = 0 (the two backends draw different masks)."""
+    import copy
+    from ps_pytorch_b200 import nn as pnn
+    from ps_pytorch_b200.models import build_model
+    torch.manual_seed(0)
+    m32 = build_model(name, 10).cuda()
+    for mod in m32.modules():
+        if isinstance(mod, (pnn.Dropout, torch.nn.Dropout)):
+            mod.p = 0.0
+    if shape[1] == 3:
+        m32 = m32.to(memory_format=torch.channels_last)
+    m = copy.deepcopy(m32).to(torch.bfloat16)
+    with torch.no_grad():
+        for p32, p in zip(m32.parameters(), m.parameters()):
+            p32.copy_(p.float())
+    x = torch.randn(*shape, device="cuda").to(torch.bfloat16)
+    if shape[1] == 3:
+        x = x.contiguous(memory_format=torch.channels_last)
+    y = torch.randint(0, 10, (shape[0],), device="cuda")
+    crit = pnn.CrossEntropyLoss()
+    with pnn.backend("library"):
+        l32 = crit(m32(x.float()), y); l32.backward()
+    ref = torch.cat([p.grad.flatten() for p in m32.parameters()])
+    out = {}
+    for be in ("library", "sm100"):
+        m.zero_grad()
+        with pnn.backend(be):
+            loss = crit(m(x), y)
+            loss.backward()
+        from ps_pytorch_b200.ops import libconv
+        libconv.join(x.device)
+        torch.cuda.synchronize()
+        g = torch.cat([p.grad.float().flatten() for p in m.parameters()])
+        out[be] = (loss.item(), torch.nn.functional.cosine_similarity(g, ref, dim=0).item())
+    assert ext.tc_error() == 0
+    assert abs(out["sm100"][0] - l32.item()) < 0.05, (out, l32.item())
+    assert out["sm100"][1] > 0.85 and out["sm100"][1] > out["library"][1] - 0.03, out
