@@ -110,6 +110,7 @@ class NvlTransport(Transport):
         self._push_forked = False
         self._pushed = [False] * self.NB
         self.zeroes_grads = topology == "ps"
+        self.zero_on_push = True              # push_kernel leaves zeros behind (accumulate-in-place modes); the worker clears it in gather mode
         # --comm-type Async: the PS only publishes a version; every worker PULLS the weights from the PS replica with P2P loads
         # (the reference's point-to-point weight fetch, distributed_worker.py:201-219, which has no sender in that snapshot)
         self.pull_weights = bool(pull_weights) and topology == "ps" and world > 1
@@ -345,7 +346,7 @@ class NvlTransport(Transport):
                 self._push_forked = True
             with torch.cuda.stream(self._push_stream if side else torch.cuda.current_stream()):
                 self.ext.push(grads.flat.data_ptr(), fp32, base, base + self.slot_q_bytes, lo, hi,
-                              self._flag(0, self.F_GREADY + 8 * (slot * MAXB + b)), self.p_wstep, self.p_counters + 4 * (MAXB + b), self.wire, True)
+                              self._flag(0, self.F_GREADY + 8 * (slot * MAXB + b)), self.p_wstep, self.p_counters + 4 * (MAXB + b), self.wire, self.zero_on_push)
             ops.count_launch()
             wbytes = {0: 2, 1: 1.03125, 2: 4}[self.wire]
             self.stats["push_bytes"] += int((hi - lo) * wbytes)

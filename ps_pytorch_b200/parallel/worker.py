@@ -109,6 +109,10 @@ class DistributedWorker(object):
             self.compute.after_backward = getattr(self.comm, "join_push_stream", None)
         if self._mode in ('kill', 'timeout') and not isinstance(self.network, LayerwiseBackwardMixin):
             self.compute.enable_kill_poll(lambda: self.comm.worker_poll_kill(self.cur_step))
+        c = self.compute
+        if hasattr(self.comm, "zero_on_push") and c.gather_grads and not c._bucket_hooks and c._layerwise_comm is None:
+            # gather mode overwrites every gradient element each step: the push kernel need not write zeros behind itself
+            self.comm.zero_on_push = False
         return self
 
     def init_recv_buf(self):
