@@ -136,9 +136,12 @@ def test_cli_resume_on_nvlink(tmp_path):
 
 
 def test_nvl_overlap_with_graph_matches_plain(tmp_path):
-    """--overlap + CUDA graph: bucket pushes recorded inside the graph must give the same weights as the plain path."""
+    """--overlap + CUDA graph: bucket pushes recorded inside the graph must give the same weights as the plain path.
+    Two steps only: the weight-gradient kernels sum their split-K partials with fp32 atomics, so two runs of the SAME configuration drift apart
+    chaotically (batch-32 BatchNorm, lr 0.1): measured cos 0.97 between identical plain runs after 4 steps (scripts/overlap_noise.py,
+    profiles/run27_multi_gpu.md) — a lost or stale bucket is an O(1) effect in the first two steps, the noise is not."""
     n = min(torch.cuda.device_count(), 2)
-    base = ["--steps", "4", "--network", "ResNet18", "--bs", "32", "--colocate", "1", "--backend", "sm100"]
+    base = ["--steps", "2", "--network", "ResNet18", "--bs", "32", "--colocate", "1", "--backend", "sm100"]
     a = _run(n, str(tmp_path / "a.pt"), base + ["--graph", "1", "--overlap", "1"])
     b = _run(n, str(tmp_path / "b.pt"), base + ["--graph", "0", "--overlap", "0"])
     init = _init("ResNet18")
