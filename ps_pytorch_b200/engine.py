@@ -54,6 +54,8 @@ class PSJob:
         self.topology = getattr(self.comm, "topology", "ps")
         P = self.comm.num_workers
         self.k = P if num_aggregate is None else max(1, min(num_aggregate, P))
+        if hasattr(self.comm, "follow_server") and (self.k < P or mode != "normal"):
+            self.comm.follow_server = True        # a worker can be left behind: its host follows the server's step (see NvlTransport.worker_fetch)
         common = dict(batch_size=batch_size, learning_rate=lr, max_epochs=10 ** 9, momentum=momentum, network=network, eval_freq=eval_freq,
                       train_dir=train_dir, max_steps=max_steps, compress_grad="compress" if compress else "None", device=self.device,
                       mode=mode, dtype=dtype)
@@ -70,6 +72,7 @@ class PSJob:
             self.worker.build_model(num_classes=nc)
         self.batch_size = batch_size
         self.step_id = 0
+        self._first_step = 1              # the step the first step() call computes (resume moves it: sync_start_step)
         self.last_loss = None
         self._comm_events = None          # set by time_comm(True): CUDA-event pairs around the communication kernels of every step
 
@@ -109,10 +112,17 @@ class PSJob:
         m, w = self.master, self.worker
         if m is not None and (self.rank == 0 or self.topology == "sharded"):
             m.async_bcast_step()
+        if w is not None and getattr(self.comm, "follow_server", False) and self.comm.next_worker_step() > self._first_step + self.step_id - 1:
+            # K < P: this worker was moved forward to the server's step earlier (it had fallen behind), so it is AHEAD of its call count; computing now
+            # would ask for weights the server only publishes in a later call — every rank calls step() the same number of times, so sit this one out
+            w = None
         if w is not None:
             e = self._bracket()
             w.sync_fetch_step()
             self._close_bracket(e)
+            if w.next_step < 0:
+                w = None
+        if w is not None:
             w.update_step()
             loss, _ = w.compute.train_step(x_host, y_host, w.cur_step)
             e = self._bracket()
@@ -135,5 +145,11 @@ class PSJob:
         if self.worker is not None:
             self.worker.compute.stage(x_host, y_host)
 
+    def finish(self) -> None:
+        """End of the job on the server side: releases every worker that still waits for a publication (K < P leaves stragglers behind)."""
+        if self.master is not None and hasattr(self.comm, "ps_shutdown") and getattr(self.comm, "follow_server", False):
+            self.comm.ps_shutdown(self.step_id)
+
     def close(self):
+        self.finish()
         self.comm.close()

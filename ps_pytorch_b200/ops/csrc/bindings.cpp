@@ -8,7 +8,7 @@ void adam_flat(at::Tensor, at::Tensor, at::Tensor, at::Tensor, c10::optional<at:
 void push(int64_t, bool, int64_t, int64_t, int64_t, int64_t, int64_t, int64_t, int64_t, int64_t, bool);
 void reduce_update(std::vector<int64_t>, std::vector<int64_t>, int64_t, double, int64_t, int64_t, int64_t, std::vector<int64_t>, std::vector<int64_t>,
                    at::Tensor, c10::optional<at::Tensor>, c10::optional<at::Tensor>, c10::optional<at::Tensor>, int64_t, std::vector<int64_t>, int64_t,
-                   std::vector<int64_t>, int64_t, int64_t, double, bool, int64_t, bool, std::vector<int64_t>);
+                   std::vector<int64_t>, int64_t, int64_t, double, bool, int64_t, bool, std::vector<int64_t>, double);
 void bcast(int64_t, std::vector<int64_t>, int64_t, int64_t, std::vector<int64_t>, int64_t, int64_t, int64_t, int64_t);
 void wait_flag(int64_t, int64_t, int64_t, int64_t, double);
 void ru_set_mc_src(int64_t);

@@ -162,7 +162,8 @@ struct RUArgs {
     int advance_step;                     // last CTA bumps *step_ptr and hp->steps
     const void* mc_src;                   // NVLS variant only: multicast mapping of the (symmetric) gradient arenas
     unsigned long long* sel;              // [kMaxBuckets] published arrival decision per bucket: (step << 16) | (count << 8) | mask
-    int partial_ok;                       // --mode timeout: after timeout_ns proceed with the >= 1 gradients that did arrive
+    int partial_ok;                       // --mode timeout: after partial_ns proceed with the >= 1 gradients that did arrive
+    unsigned long long partial_ns;        //   (nothing arrived yet: keep waiting for the first one, up to the hard timeout_ns)
     long long* abort_w[kMaxPeers];        // --mode kill: abort word of source k's worker (set to the step id for the laggards), or null
 };
 
@@ -225,8 +226,9 @@ __global__ void __launch_bounds__(256, 2) reduce_update_kernel(RUArgs a) {
                 int cnt = 0;
                 for (int k = 0; k < a.P && cnt < a.take; ++k)
                     if (ld_acquire_sys(a.g_ready + k * kMaxBuckets + b) == step) { mask |= 1u << k; ++cnt; }
-                const bool timed = globaltimer_ns() - t0 > a.timeout_ns;
-                if (cnt >= a.take || (timed && a.partial_ok && cnt >= 1)) {
+                const unsigned long long waited = globaltimer_ns() - t0;
+                const bool timed = waited > a.timeout_ns;
+                if (cnt >= a.take || (a.partial_ok && waited > a.partial_ns && cnt >= 1)) {
                     const unsigned long long nv = tag | ((unsigned long long)cnt << 8) | mask;
                     if (atomicCAS(a.sel + b, v, nv) == v) { v = nv; winner = true; break; }
                     continue;                                                       // lost the race: read the winner's decision
@@ -402,10 +404,10 @@ void reduce_update(std::vector<int64_t> src, std::vector<int64_t> src_scale, int
                    int64_t g_ready, int64_t step_ptr, std::vector<int64_t> lo, std::vector<int64_t> hi, at::Tensor w,
                    c10::optional<at::Tensor> s0, c10::optional<at::Tensor> s1, c10::optional<at::Tensor> s2, int64_t hp,
                    std::vector<int64_t> dst, int64_t mc_dst, std::vector<int64_t> w_ready, int64_t counters, int64_t err,
-                   double timeout_s, bool advance_step, int64_t sel, bool partial_ok, std::vector<int64_t> abort_words) {
+                   double timeout_s, bool advance_step, int64_t sel, bool partial_ok, std::vector<int64_t> abort_words, double partial_s) {
     RUArgs a{};
     TORCH_CHECK(sel != 0, "reduce_update needs the per-bucket decision words");
-    a.sel = (unsigned long long*)P(sel); a.partial_ok = partial_ok ? 1 : 0;
+    a.sel = (unsigned long long*)P(sel); a.partial_ok = partial_ok ? 1 : 0; a.partial_ns = (unsigned long long)(partial_s * 1e9);
     for (size_t k = 0; k < kMaxPeers; ++k) a.abort_w[k] = k < abort_words.size() ? (long long*)P(abort_words[k]) : nullptr;
     TORCH_CHECK(src.size() <= kMaxPeers && dst.size() <= kMaxPeers + 1 && lo.size() <= kMaxBuckets && lo.size() == hi.size());
     a.P = (int)src.size(); a.take = (int)take; a.mode = (int)mode; a.inv_div = (float)inv_div;

@@ -31,6 +31,7 @@ from .. import ops
 WIRE = {"bf16": 0, "fp8": 1, "fp32": 2}
 MAXB = 16          # kMaxBuckets in comm_kernels.cu
 MAXP = 8
+DONE_STEP = 1 << 40  # "training is over": published as a weights-ready value by ps_shutdown; every waiter passes, every follower stops
 
 
 def _align(x, a=4096):
@@ -110,6 +111,10 @@ class NvlTransport(Transport):
         self._push_forked = False
         self._pushed = [False] * self.NB
         self.zeroes_grads = topology == "ps"
+        # K < P / kill / timeout: a worker can be left behind by the server and must FOLLOW its step (the reference's workers receive the step from the
+        # PS every iteration, distributed_worker.py:127-137).  worker_fetch then blocks the host until the weights are there and returns the exact step
+        # the device adopted; with K == P nobody can fall behind and the host just counts (fully asynchronous).
+        self.follow_server = False
         self.zero_on_push = True              # push_kernel leaves zeros behind (accumulate-in-place modes); the worker clears it in gather mode
         # --comm-type Async: the PS only publishes a version; every worker PULLS the weights from the PS replica with P2P loads
         # (the reference's point-to-point weight fetch, distributed_worker.py:201-219, which has no sender in that snapshot)
@@ -255,7 +260,7 @@ class NvlTransport(Transport):
             self.ext.reduce_update(src, scl, int(take), 1.0 / float(k), int(mode), self.arena.local_ptr + self.off_flags + self.F_GREADY,
                                    self.p_psstep, lo, hi, master.flat, s0, s1, s2, hp_ptr, self._ru_dst(d),
                                    (self.arena.mc_ptr + self.off_w) if use_mc else 0, wready, self.p_counters, self.p_err,
-                                   float(timeout_s or self.timeout_s), True, self.p_sel, partial_ok, abort_words)
+                                   float(self.timeout_s), True, self.p_sel, partial_ok, abort_words, float(timeout_s or 0.0))
         finally:
             if nvls:
                 self.ext.ru_set_mc_src(0)
@@ -303,22 +308,49 @@ class NvlTransport(Transport):
         return (self.arena.local_ptr + self.off_flags + self.F_WREADY, n, self.p_wstep, self.p_err, float(self.timeout_s))
 
     def worker_fetch(self, weights, timeout_s=0.0, fused_wait=False):
-        """Enqueue the device-side wait for this step's weights; the host does not block.  ``fused_wait``: the first kernel of the caller's step
-        acquires the ready words itself (ops/csrc/conv2_tcgen05.cu: weight_transpose_batched_kernel) — no wait kernel is launched here."""
+        """Enqueue the device-side wait for this step's weights.  Default: the host does not block and counts the steps itself.  ``fused_wait``: the
+        first kernel of the caller's step acquires the ready words itself (ops/csrc/conv2_tcgen05.cu: weight_transpose_batched_kernel) — no wait kernel
+        is launched here.  ``follow_server`` (K < P, kill / timeout modes): blocks until the weights are there and returns the step the device adopted
+        (wait_flag_kernel moves a worker that fell behind to the server's step); -1 once the server has shut the job down."""
         n = self.NB if self.topology == "ps" else self.world_size
-        if not (fused_wait and not (self.pull_weights and self.rank != 0)):
+        pulls = self.pull_weights and self.rank != 0
+        if self.follow_server or pulls or not fused_wait:
             self.ext.wait_flag(self.arena.local_ptr + self.off_flags + self.F_WREADY, n, self.p_wstep, self.p_err, self.timeout_s)
             ops.count_launch()
         else:
             self.stats["fused_waits"] = self.stats.get("fused_waits", 0) + 1
-        if self.pull_weights and self.rank != 0:
+        if pulls:
             # P2P pull of the fresh weights from the PS replica into ours (no flags to release: nflags = 0)
             self.ext.bcast(self.arena.peer_ptrs[0] + self.off_w, [self.arena.local_ptr + self.off_w], 0, self.T * 2,
                            [self._flag(self.rank, self.F_WREADY)], 0, self.p_wstep, 0, self.p_counters + 4 * (2 * MAXB + 2))
             ops.count_launch()
-        self._host_wstep += 1
         self._pushed = [False] * self.NB
+        if self.follow_server:
+            d = int(self.ctl[0].item())                # host sync: the wait kernel has finished, ctl[0] is the step this worker now computes
+            self.check_error()
+            if d >= DONE_STEP:
+                return -1
+            self._host_wstep = d
+            return d
+        self._host_wstep += 1
         return self._host_wstep
+
+    def next_worker_step(self) -> int:
+        """The step the next worker_fetch will at least ask for (exact in follow_server mode, where the host tracks the device counter)."""
+        return self._host_wstep + 1
+
+    def ps_shutdown(self, step=None):
+        """End of training (C1's step = -1 in the message protocol): publish DONE_STEP as the weights-ready value on every worker.  Kernels still
+        waiting for a publication pass at once, followers see it in their next worker_fetch and stop."""
+        if self.rank != 0 and self.topology != "sharded":
+            return
+        d = self._dests()
+        nfl = self.NB if self.topology == "ps" else self.world_size
+        for r in d:
+            for b in range(nfl):
+                self.ext.set_word(self._flag(r, self.F_WREADY + 8 * b), DONE_STEP)
+        ops.count_launch(len(d) * nfl)
+        torch.cuda.synchronize(self.device)
 
     def _my_slot(self):
         return self.worker_slot(self.rank)
@@ -413,7 +445,8 @@ class NvlTransport(Transport):
         return int(v)
 
     def worker_poll_kill(self, step):
-        return self._read_word(self.F_ABORT) == step
+        # the abort word holds the LAST step this worker was left out of: anything >= the step being computed means "the server has moved on"
+        return self._read_word(self.F_ABORT) >= step
 
     def worker_send_buffers(self, step, flat):
         """BN running statistics -> the PS (checkpoint steps).  One launch of the copy kernel over raw peer pointers: it stores the payload into the
@@ -464,7 +497,7 @@ class NvlTransport(Transport):
                                    self.arena.local_ptr + self.off_flags + self.F_GREADY, self.p_psstep, [lo], [hi], self._ar_w, None, None, None,
                                    self._ar_hp.data_ptr(), [self.arena.peer_ptrs[r] + self.off_grads for r in d], 0,
                                    [self._flag(r, self.F_WREADY + 8 * self.rank) for r in d], self.p_counters, self.p_err, self.timeout_s, True,
-                                   self.p_sel, False, [])
+                                   self.p_sel, False, [], 0.0)
         finally:
             if nvls:
                 self.ext.ru_set_mc_src(0)

@@ -192,6 +192,8 @@ def run_distributed(args):
     proto = build_model(args.network, num_classes)
     layout = ParamLayout.from_module(proto, channels_last=(device.type == "cuda"))
     comm = make_transport(args, layout, device, world, n_buffers=sum(b.numel() for b in proto.buffers()))
+    if hasattr(comm, "follow_server") and (args.mode != "normal" or 0 < int(args.num_aggregate or 0) < comm.num_workers):
+        comm.follow_server = True      # K < P / kill / timeout: workers can be left behind and must follow the server's step
     stragglers = parse_stragglers(args.inject_straggler)
     failures = {int(r): int(st) for r, st in (item.split(":") for item in filter(None, (getattr(args, "inject_failure", "") or "").split(",")))}
     common = dict(batch_size=args.batch_size, learning_rate=args.lr, max_epochs=args.epochs, momentum=args.momentum,

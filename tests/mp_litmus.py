@@ -62,21 +62,31 @@ if K == world:
 else:
     # K of P with staggered arrivals: worker r delays its push by r device-milliseconds, so different workers win in different steps.  Every
     # element of one update must come from ONE set of K workers: (w_prev - w_new) / (pattern * (s%5)) must be the same number everywhere, and
-    # that number must be the mean of K distinct values out of {1..P}.
+    # that number must be the mean of K distinct values out of {1..P}.  A worker whose push came too late finds the server one or more steps ahead,
+    # adopts its step (the payload is built from the step worker_fetch returns) and the job ends with the server's shutdown publication.
     import itertools
     legal = sorted({sum(c) / K for c in itertools.combinations(range(1, world + 1), K)})
     prev = torch.zeros(T, device=dev)
-    for s in range(1, steps + 1):
+    tr.follow_server = True            # K < P: a worker that is left behind adopts the server's step; worker_fetch returns the step it computes
+    it = 0
+    while True:
+        it += 1
         if master is not None:
-            tr.ps_publish(s, lowp)
-        tr.worker_fetch(lowp)
-        torch.cuda._sleep(int(1.5e6 * ((rank + s) % world)))
-        grads.flat.copy_(pattern * float((tr.worker_slot(rank) + 1) * (1 + s % 3)))
-        tr.worker_push(s, grads)
+            if it > steps:
+                tr.ps_shutdown()       # releases everybody who still waits for a publication
+                break
+            tr.ps_publish(it, lowp)
+        d = tr.worker_fetch(lowp)
+        if d < 0 or d > steps:
+            break
+        torch.cuda._sleep(int(1.5e6 * ((rank + it) % world)))
+        grads.flat.copy_(pattern * float((tr.worker_slot(rank) + 1) * (1 + d % 3)))
+        tr.worker_push(d, grads)
         if master is not None:
-            tr.ps_reduce_update(s, K, opt, master, lowp=lowp)
+            assert d == it, (d, it)
+            tr.ps_reduce_update(it, K, opt, master, lowp=lowp)
             torch.cuda.synchronize()
-            q = (prev - master.flat) / (pattern * float(1 + s % 3))
+            q = (prev - master.flat) / (pattern * float(1 + it % 3))
             u = q.unique()
             if u.numel() != 1 or min(abs(float(u[0]) - v) for v in legal) > 1e-4:
                 bad += 1

@@ -916,3 +916,33 @@ def test_model_zoo_step_sm100_vs_fp32(ext, name, shape):
     # bf16 activations through 50 BatchNorm layers at batch 32 decorrelate ANY bf16 gradient from the fp32 one (library: 0.29 on ResNet-50),
     # so the bar is the library path's own agreement with fp32, plus an absolute floor where bf16 can do well
     assert out["sm100"][1] > out["library"][1] - 0.03 and out["sm100"][1] > min(0.85, out["library"][1]), out
+
+
+def test_follow_server_fetch_returns_the_adopted_step_and_shutdown_releases(ext):
+    """K < P / straggler modes: worker_fetch blocks and returns the step the DEVICE adopted — its own next step, or the server's when the worker
+    was left behind — and -1 once the server has published the end of training (NvlTransport.ps_shutdown)."""
+    from ps_pytorch_b200.parallel import nvl as N
+    T = 128 * 512
+    tr, master, opt_, lowp, grads = _k_of_p_setup(T)
+    tr.follow_server = True
+    tr.ps_publish(1, lowp)
+    assert tr.worker_fetch(lowp) == 1
+    for slot in (0, 1, 2):
+        grads.flat.fill_(1.0)
+        tr._slot_override = slot
+        tr.worker_push_bucket(0, grads)
+    tr.ext.add_step(tr.p_wstep, 1)
+    tr.ps_reduce_update(1, 3, opt_, master, lowp=lowp)
+    assert tr.worker_fetch(lowp) == 2 and tr.next_worker_step() == 3
+    # the server ran ahead without this worker: weights of step 7 are published -> the worker adopts step 7
+    for b in range(tr.NB):
+        tr.ext.set_word(tr._flag(0, tr.F_WREADY + 8 * b), 7)
+    tr.ext.add_step(tr.p_wstep, 1)                     # (this worker pushed its late step-2 gradient)
+    assert tr.worker_fetch(lowp) == 7
+    assert not tr.worker_poll_kill(7)
+    tr.ext.set_word(tr._flag(0, tr.F_ABORT), 9)         # left out of step 9: anything up to 9 is to be abandoned
+    torch.cuda.synchronize()
+    assert tr.worker_poll_kill(7) and tr.worker_poll_kill(9) and not tr.worker_poll_kill(10)
+    tr.ps_shutdown()
+    assert tr.worker_fetch(lowp) == -1
+    tr.check_error()
