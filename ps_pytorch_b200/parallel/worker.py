@@ -170,7 +170,10 @@ class DistributedWorker(object):
             logger.error("Worker %d: injected failure at step %d", self.rank, self.cur_step)
             os._exit(17)
         if self._mode == 'timeout':
-            self.compute.kill_deadline = time.time() + float(self.kill_threshold)
+            # the worker's own deadline for this step; not on its first iteration, which pays for lazy kernel loading / autotuning (seconds): with every
+            # worker abandoning step 1 the server would never see a gradient
+            self.compute.kill_deadline = (time.time() + float(self.kill_threshold)) if getattr(self, "_iters_done", 0) > 0 else 0.0
+        self._iters_done = getattr(self, "_iters_done", 0) + 1
         killed = False
         try:
             loss, logits = self.compute.train_step(xb, yb, self.cur_step)

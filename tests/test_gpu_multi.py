@@ -107,8 +107,10 @@ def test_cli_straggler_modes_on_nvlink(tmp_path, mode):
     if n < 3:
         pytest.skip("needs >= 3 GPUs")
     d = str(tmp_path) + "/"
-    extra = ["--max-steps", "8", "--eval-freq", "1000", "--mode", mode, "--inject-straggler", "%d:400" % (n - 1), "--cuda-graph", "false"]
-    extra += ["--num-aggregate", str(n - 1)] if mode == "kill" else ["--kill-threshold", "0.15"]
+    # worker co-located on the PS rank: P = n workers, the last one sleeps 400 ms before every step
+    extra = ["--max-steps", "8", "--eval-freq", "1000", "--mode", mode, "--inject-straggler", "%d:400" % (n - 1), "--cuda-graph", "false",
+             "--colocate-worker", "true"]
+    extra += ["--num-aggregate", str(n - 1)] if mode == "kill" else ["--num-aggregate", str(n), "--kill-threshold", "0.15"]
     r = _cli(n, d, extra)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
     from ps_pytorch_b200.utils.obs import parse_worker_line
