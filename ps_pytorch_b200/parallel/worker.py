@@ -93,7 +93,9 @@ class DistributedWorker(object):
         self.compute = WorkerCompute(net, self._device, self._dtype, layout=self.comm.layout, weight_storage=storage,
                                      use_graph=self._use_graph, grad_storage=gstorage,
                                      zero_grads_in_step=not getattr(self.comm, "zeroes_grads", False))
-        if _FUSE_WAIT and hasattr(self.comm, "fetch_wait_args"):
+        # (not when the worker FOLLOWS the server's step — K < P, kill / timeout: the blocking fetch has already adopted a step and told the host; a
+        # second wait that may adopt a newer publication behind the host's back would desynchronise them)
+        if _FUSE_WAIT and hasattr(self.comm, "fetch_wait_args") and not getattr(self.comm, "follow_server", False):
             self.compute.fetch_wait_args = self.comm.fetch_wait_args()
         self.network = self.compute.network
         self.optimizer = torch.optim.SGD(self.network.parameters(), lr=self.lr, momentum=self.momentum)  # zero_grad only, as in the reference

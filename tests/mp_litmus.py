@@ -87,8 +87,9 @@ else:
             tr.ps_reduce_update(it, K, opt, master, lowp=lowp)
             torch.cuda.synchronize()
             q = (prev - master.flat) / (pattern * float(1 + it % 3))
-            u = q.unique()
-            if u.numel() != 1 or min(abs(float(u[0]) - v) for v in legal) > 1e-4:
+            qlo, qhi = float(q.min()), float(q.max())
+            # 1/K is not a binary fraction for K = 3: allow rounding noise (1e-4), nothing near the 1/K = 0.33 that separates two worker sets
+            if qhi - qlo > 1e-4 or min(abs(qlo - v) for v in legal) > 1e-4:
                 bad += 1
             prev = master.flat.clone()
     torch.cuda.synchronize()
