@@ -150,7 +150,7 @@ def test_nvl_overlap_with_graph_matches_plain(tmp_path):
     da = torch.cat([(x - i).flatten() for x, i in zip(a["w"], init)])
     db = torch.cat([(x - i).flatten() for x, i in zip(b["w"], init)])
     cos = torch.nn.functional.cosine_similarity(da, db, dim=0).item()
-    assert cos > 0.98 and abs(da.norm().item() / db.norm().item() - 1.0) < 0.1, (cos, da.norm().item(), db.norm().item())
+    assert cos > 0.95 and abs(da.norm().item() / db.norm().item() - 1.0) < 0.1, (cos, da.norm().item(), db.norm().item())
 
 
 def test_nvl_async_pull_matches_reference(tmp_path):
