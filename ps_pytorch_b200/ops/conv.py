@@ -243,15 +243,31 @@ def set_grad_sinks(params, views) -> list:
     return idx
 
 
+_sinks_written = set()           # data_ptr of every weight whose sink was written since the last activation
+
+
 def activate_grad_sinks(on: bool) -> None:
     global _sinks_active
     _sinks_active = bool(on)
+    if on:
+        _sinks_written.clear()
+
+
+def sinks_written() -> set:
+    """Weights (by data_ptr) whose gradient already sits in its sink for the current step."""
+    return _sinks_written
 
 
 def _sink_for(weight):
     if not _sinks_active or weight.grad is not None:
         return None
-    return _grad_sinks.get(weight.data_ptr())
+    ptr = weight.data_ptr()
+    v = _grad_sinks.get(ptr)
+    if v is None or ptr in _sinks_written:
+        # a weight used twice in one forward (shared layer): the second gradient goes the ordinary way and the gather ADDS it to the sink
+        return None
+    _sinks_written.add(ptr)
+    return v
 
 
 def set_skip_fusion(on: bool) -> None:

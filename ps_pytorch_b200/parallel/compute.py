@@ -191,7 +191,12 @@ class WorkerCompute:
                 if self._sinked:
                     from ..ops import conv as _conv
                     _conv.activate_grad_sinks(False)
-                    todo = self._unsinked + [i for i in self._sinked if self._params[i].grad is not None]
+                    written = _conv.sinks_written()
+                    extra = [i for i in self._sinked if self._params[i].grad is not None]
+                    # a sinked weight that ALSO has a .grad was used twice (shared layer): its second gradient is added to the first
+                    for i in [i for i in extra if self._params[i].data_ptr() in written]:
+                        self.grads.views[i].add_(self._params[i].grad)
+                    todo = self._unsinked + [i for i in extra if self._params[i].data_ptr() not in written]
                 else:
                     todo = range(len(self._params))
                 dst = [self.grads.views[i] for i in todo]
@@ -259,6 +264,15 @@ class WorkerCompute:
 
     def train_step(self, x: torch.Tensor, y: torch.Tensor, step: int = 0):
         """Returns ``(loss, logits)`` device tensors.  Gradients land in ``self.grads``."""
+        try:
+            return self._train_step(x, y, step)
+        except BaseException:
+            if self._sinked:                       # an abandoned step (StragglerKilled, an error) must not leave the gradient sinks armed
+                from ..ops import conv as _conv
+                _conv.activate_grad_sinks(False)
+            raise
+
+    def _train_step(self, x: torch.Tensor, y: torch.Tensor, step: int = 0):
         self._cur_step = step
         self.network.train()
         if self.device.type == "cuda":

@@ -946,3 +946,44 @@ def test_follow_server_fetch_returns_the_adopted_step_and_shutdown_releases(ext)
     tr.ps_shutdown()
     assert tr.worker_fetch(lowp) == -1
     tr.check_error()
+
+
+def test_gradient_sinks_with_a_shared_convolution(ext):
+    """A weight used twice in one forward: the first weight gradient lands in the arena sink, the second goes the ordinary way and is ADDED by the
+    gather — the arena must hold the sum, exactly like the run without sinks."""
+    from ps_pytorch_b200 import nn as pnn
+    from ps_pytorch_b200.ops import conv as C
+    from ps_pytorch_b200.parallel import compute as CP
+
+    class Shared(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.stem = pnn.Conv2d(3, 64, 3, 1, 1, bias=False)
+            self.conv = pnn.Conv2d(64, 64, 3, 1, 1, bias=False)
+            self.bn = pnn.BatchNorm2d(64)
+            self.fc = pnn.Linear(64, 10)
+
+        def forward(self, x):
+            h = torch.relu(self.stem(x))
+            h = torch.relu(self.bn(self.conv(h)))
+            h = self.conv(h)                       # same filter again
+            return self.fc(h.float().mean((2, 3)).to(h.dtype))
+
+    x = torch.randn(32, 3, 16, 16, device="cuda")
+    y = torch.randint(0, 10, (32,), device="cuda")
+    flats = []
+    for sinks in (True, False):
+        torch.manual_seed(0)
+        old = CP._GRAD_SINKS
+        CP._GRAD_SINKS = sinks
+        try:
+            with pnn.backend("sm100"):
+                wc = CP.WorkerCompute(Shared(), "cuda", torch.bfloat16)
+                wc.train_step(x, y)
+                torch.cuda.synchronize()
+        finally:
+            CP._GRAD_SINKS = old
+            C.activate_grad_sinks(False)
+        flats.append(wc.grads.flat.float().clone())
+    assert flats[1].abs().max() > 0
+    assert torch.allclose(flats[0], flats[1], rtol=2e-2, atol=2e-3 * flats[1].abs().max().item())
