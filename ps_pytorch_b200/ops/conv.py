@@ -337,6 +337,8 @@ class _ConvFn(torch.autograd.Function):
                 for t in (dy, x, dw):
                     t.record_stream(side)
             else:
+                if weight.grad is not None:
+                    _lc.join(dy.device)   # shared weight: the gradient autograd is about to add to may still be in flight on the side stream
                 dw = ext.conv_wgrad(dy, x, _wgrad_scratch(weight), r, weight.size(3), s, p, sink)
             if sink is not None:          # the gradient is already where the push kernel reads it: nothing to hand to autograd
                 global sink_writes

@@ -61,6 +61,7 @@ class _LibConvFn(torch.autograd.Function):
         main = torch.cuda.current_stream(dev)
         if (need_dw or need_db) and (weight.grad is not None):
             # a bound .grad is accumulated on the main stream as soon as backward returns: no side stream in that mode
+            join(dev)                                   # (a shared weight's first gradient may still be in flight on the side stream)
             _, dw, db = torch.ops.aten.convolution_backward(dy, x, weight, [weight.size(0)] if need_db else None, stride, padding, dilation,
                                                             False, [0, 0], groups, [False, need_dw, need_db])
         elif need_dw or need_db:
