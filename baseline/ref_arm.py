@@ -132,6 +132,8 @@ def run(gpus, steps, warmup, network="ResNet18", dataset="Cifar10", batch_size=1
         env.update({"REFSHIM_RANK": str(r), "REFSHIM_SIZE": str(nworkers + 1), "REFSHIM_DIR": os.path.join(work, "sock"),
                     "REFSHIM_TIMELOG": timelog, "PYTHONUNBUFFERED": "1",
                     "REFSHIM_TORCH_THREADS": str(max(1, min(16, ncpu // (nworkers + 1))))})
+        # torchrun exports OMP_NUM_THREADS=1 to its children; the reference's host-side PS must not be throttled by the way THIS arm was launched
+        env["OMP_NUM_THREADS"] = env["REFSHIM_TORCH_THREADS"]
         env["CUDA_VISIBLE_DEVICES"] = "" if (r == 0 or not use_gpu) else visible[(r - 1) % len(visible)]
         out = open(os.path.join(work, "rank%d.log" % r), "w")
         procs.append(subprocess.Popen([sys.executable, os.path.join(HERE, "ref_runner.py"), src, "distributed_nn.py"] + args,
