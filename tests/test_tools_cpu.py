@@ -109,3 +109,21 @@ def test_lr_sweep_script(tmp_path):
     lines = [l for l in r.stdout.splitlines() if l.startswith("Avged loss for lr candidate")]
     assert len(lines) == 2 and "0.01=========>" in lines[0] and "0.1=========>" in lines[1], r.stdout[-1500:]
     assert "Illegal Number of Workers" not in r.stdout
+
+
+def test_scaling_table_from_bench_json(tmp_path):
+    """analysis/scaling.py: speed-up / efficiency against the smallest run, NCCL ratio where the bench measured the baseline in the same job."""
+    import json
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    files = []
+    for n, v, nb in ((1, 100.0, 50.0), (4, 380.0, None)):
+        p = tmp_path / ("n%d.json" % n)
+        p.write_text(json.dumps({"n_gpus": n, "value": v, "ms_per_step": 10.0, "scaling": "weak", "exposed_comm_ms": 0.1,
+                                 "nccl_baseline": {"value": nb} if nb else None}))
+        files.append(str(p))
+    out = subprocess.run([sys.executable, os.path.join(root, "analysis", "scaling.py")] + files[::-1], capture_output=True, text=True, check=True).stdout
+    lines = [l for l in out.splitlines() if l.startswith("| 1 ") or l.startswith("| 4 ")]
+    assert "| 1.00 | 1.000 |" in lines[0] and "| 2.00 |" in lines[0]
+    assert "| 3.80 | 0.950 |" in lines[1] and lines[1].rstrip().endswith("| - | - |")
