@@ -67,12 +67,13 @@ class Transport:
 
 
 # ---------------------------------------------------------------------------------------------------------
-def reduce_k_of_p(arrived: List[torch.Tensor], k: int, strict_reference: bool) -> torch.Tensor:
+def reduce_k_of_p(arrived: List[torch.Tensor], k: int, strict_reference: bool, owned: bool = False) -> torch.Tensor:
     """Sum the first K arrivals and divide by K.  With ``strict_reference`` the reference's gate quirk is
     reproduced: ``counter <= K`` admits K+1 gradients but the divisor stays K
-    (``/root/reference/src/sync_replicas_master_nn.py:179,207``)."""
+    (``/root/reference/src/sync_replicas_master_nn.py:179,207``).  ``owned``: the arrivals are private receive buffers, so the
+    first one may serve as the accumulator (no copy)."""
     take = min(len(arrived), k + 1 if strict_reference else k)
-    acc = arrived[0].to(torch.float32).clone()
+    acc = arrived[0] if (owned and arrived[0].dtype == torch.float32) else arrived[0].to(torch.float32).clone()
     for g in arrived[1:take]:
         acc.add_(g.to(torch.float32))
     return acc.div_(float(k))
@@ -237,8 +238,12 @@ class GlooTransport(Transport):
                 if rx.poll():
                     progressed = True
                     if rx.done and rx.grad_blob is not None:
-                        g = torch.empty(self.layout.total, dtype=torch.float32)
-                        codec.decode_grad(rx.grad_blob, g, self.compress)
+                        if self.compress:
+                            g = torch.empty(self.layout.total, dtype=torch.float32)
+                            codec.decode_grad(rx.grad_blob, g, True)
+                        else:
+                            g = rx.grad_blob.view(torch.float32)       # the receive buffer IS the fp32 gradient: no second copy
+                            assert g.numel() == self.layout.total
                         arrived.append(g)
                     elif rx.done:
                         self.stats["killed"] += 1
@@ -257,7 +262,7 @@ class GlooTransport(Transport):
             if not progressed:
                 time.sleep(0.0002)
         kk = k if strict_reference else min(k, max(1, len(arrived)))
-        avg = reduce_k_of_p(arrived, kk, strict_reference)
+        avg = reduce_k_of_p(arrived, kk, strict_reference, owned=True)      # receive buffers and the co-located clone are ours to overwrite
         optimizer.step(grads=avg)
         self._local_push = None
 
